@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference's model API for the VCGPCM ELBO path.
+
+Same names, argument meaning and error behaviour as ``src/core/cgpcm.py`` for
+``VCGPCM.from_recipe`` (``:32-109``), ``precompute`` / ``undo_precompute`` (``:270-292``), ``elbo``
+(``:518-575``) and the ``vars`` dictionary of trainable variables, so that
+``experiment.train``'s schedule (``src/core/experiment.py:209-250``) runs unchanged.  Nothing is
+computed here: the TF graph of the reference is replaced by one call into ``libcgpcm_b200.so`` per
+``sess.run`` (see ``engine.Engine``).  Tensors of the reference become small lazy handles
+(``Var``, ``Positive``, ``Objective``, ``Term``) that ``Session.run`` evaluates.
+"""
+import os
+
+import numpy as np
+
+from . import config
+from .engine import (Engine, TERM_NAMES, GRAD_S2, GRAD_S2F, GRAD_ALPHA, GRAD_GAMMA, GRAD_OMEGA, GRAD_MU_U,
+                     GRAD_VAR_U, MODE_FROZEN, MODE_FULL)
+from .util import length_scale, to_float, tril_to_vec
+
+_HEAD = ['s2', 's2_f', 'alpha', 'gamma', 'omega']
+_MASK = {'s2': GRAD_S2, 's2_f': GRAD_S2F, 'alpha': GRAD_ALPHA, 'gamma': GRAD_GAMMA, 'omega': GRAD_OMEGA,
+         'mu_u': GRAD_MU_U, 'var_u': GRAD_VAR_U}
+
+
+# ----------------------------------------------------------------------------- lazy handles
+class Var(object):
+    """A trainable variable (the reference: ``tf.Variable``).  Positive quantities are stored as
+    logs, exactly like ``var_pos`` (``src/core/tf_util.py:323-332``)."""
+
+    def __init__(self, name, value):
+        self.name = name
+        self.value = np.array(value, dtype=np.float64)
+
+    def assign(self, value):
+        value = np.asarray(value, dtype=np.float64)
+        if value.size != self.value.size:
+            raise ValueError('cannot assign value of size %d to variable %r of size %d'
+                             % (value.size, self.name, self.value.size))
+        return _Assign(self, value.reshape(self.value.shape))
+
+    def eval(self):
+        return self.value.copy()
+
+    @property
+    def size(self):
+        return self.value.size
+
+
+class _Assign(object):
+    def __init__(self, var, value):
+        self.var, self.value = var, value
+
+    def run(self):
+        self.var.value = self.value.copy()
+        return self.var.value
+
+
+class Positive(object):
+    """``tf.exp(var)`` of a log-variable: ``mod.s2``, ``mod.alpha`` ..."""
+
+    def __init__(self, var):
+        self.var = var
+
+    def eval(self):
+        return float(np.exp(self.var.value))
+
+    def __float__(self):
+        return self.eval()
+
+
+class Term(object):
+    """One of the 7 ELBO terms (``src/core/cgpcm.py:543-566``)."""
+
+    def __init__(self, objective, index):
+        self.objective, self.index = objective, index
+
+    def eval(self):
+        return self.objective.mod._evaluate(want_grad=False)[1][self.index]
+
+
+class Objective(object):
+    """The ELBO as a lazy scalar supporting unary minus (callers minimise ``-elbo``)."""
+
+    def __init__(self, mod, sign=1.0):
+        self.mod, self.sign = mod, sign
+
+    def __neg__(self):
+        return Objective(self.mod, -self.sign)
+
+    def eval(self):
+        return self.sign * self.mod._evaluate(want_grad=False)[0]
+
+    def value_and_grad(self, var_list):
+        """Value and gradient w.r.t. the concatenation of ``var_list`` (what ``ScipyOptimizerInterface``
+        fetches with one ``sess.run([loss, packed_grad])``)."""
+        names = [v.name for v in var_list]
+        e, _, g = self.mod._evaluate(want_grad=True, names=names)
+        return self.sign * e, self.sign * self.mod._slice_grad(g, names)
+
+
+class Session(object):
+    """No-op stand-in for ``tf_util.Session`` (``src/core/tf_util.py:335-400``): owns the device choice
+    and the process-group facts, and evaluates lazy handles."""
+
+    def __init__(self, device=None, rank=None, world=None):
+        self.rank, self.world = 0, 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+        if rank is not None:
+            self.rank = rank
+        if world is not None:
+            self.world = world
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', '0')) if self.world > 1 else 0
+        self.device = device
+
+    def run(self, fetches, feed_dict=None, **kw_args):
+        if isinstance(fetches, (list, tuple)):
+            return [self.run(f) for f in fetches]
+        if isinstance(fetches, _Assign):
+            return fetches.run()
+        if hasattr(fetches, 'eval'):
+            return fetches.eval()
+        return fetches
+
+    def close(self):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *args):
+        return False
+
+
+# ----------------------------------------------------------------------------- model
+class CGPCM(object):
+    """Causal Gaussian Process Convolution Model: hyper-parameters and inducing inputs."""
+
+    _required_pars = ['sess', 'e', 'th', 'tx', 's2', 's2_f', 'alpha', 'gamma', 'omega', 'vars', 'causal',
+                      'causal_id']
+
+    def __init__(self, **kw_args):
+        # same contract as Parametrisable (src/core/parametrisable.py:9-21)
+        for par in self._required_pars:
+            if par not in kw_args:
+                raise RuntimeError('must specify "{}"'.format(par))
+        for k, v in kw_args.items():
+            setattr(self, k, v)
+        self._precomputed = False
+
+    @classmethod
+    def from_recipe(cls, sess, e, nx, nh, tau_w, tau_f, causal, causal_id=False, noise_init=1e-4,
+                    tx_range=None):
+        """Generate parameters for the CGPCM and construct afterwards (``src/core/cgpcm.py:32-109``).
+
+        :param sess: ``Session``
+        :param e: observations (``.x`` inputs, ``.y`` outputs); every rank passes the *whole* series,
+                  the model keeps this rank's contiguous slice
+        :param nx: number of inducing points for noise
+        :param nh: number of inducing points for filter
+        :param tau_w: length of kernel window
+        :param tau_f: length scale of function prior
+        :param causal: causal model
+        :param causal_id: causal interdomain transformation
+        :param noise_init: initialisation of noise
+        :param tx_range: range of the inducing points for x, taken from ``e`` by default
+        """
+        vars = {}
+        tau_ws = 1
+        causal_extra_points = 2
+
+        def var_pos(name, init):
+            vars[name] = Var(name, np.log(init))
+            return Positive(vars[name])
+
+        alpha = 2 * length_scale(tau_w)
+        gamma = length_scale(tau_f) - .5 * alpha
+        s2_f = var_pos('s2_f', to_float((2 * alpha / np.pi) ** .5))
+        if causal:
+            gamma += 3. * alpha / 8.
+            alpha /= 4.
+        alpha = var_pos('alpha', to_float(alpha))
+        gamma = var_pos('gamma', to_float(gamma))
+        if nx > 0:
+            tx_range = (min(e.x), max(e.x)) if tx_range is None else tx_range
+            dtx = (tx_range[1] - tx_range[0]) / nx
+            omega = .5 * length_scale(dtx)
+            tx = np.linspace(tx_range[0], tx_range[1], nx)
+        else:
+            raise ValueError('nx must be positive')
+        omega = var_pos('omega', to_float(omega))
+        if not causal and nh % 2 == 0:
+            nh += 1
+        if causal:
+            th = np.linspace(0, 2 * tau_ws * tau_w, nh)
+            dth = th[1] - th[0]
+            th = th - dth * causal_extra_points
+        else:
+            th = np.linspace(-tau_ws * tau_w, tau_ws * tau_w, nh)
+        s2 = var_pos('s2', to_float(noise_init))
+        return cls(sess=sess, th=th, tx=tx, s2=s2, s2_f=s2_f, alpha=alpha, gamma=gamma, omega=omega, vars=vars,
+                   e=e, causal=causal, causal_id=causal_id, tau_w=tau_w, tau_f=tau_f, nh=nh, nx=nx,
+                   noise_init=noise_init, tx_range=tx_range)
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous slice ``[lo, hi)`` of ``n`` observations owned by ``rank`` (sizes differ by <= 1)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class VCGPCM(CGPCM):
+    """Variational inference in the CGPCM (``src/core/cgpcm.py:425-872``), ELBO path."""
+
+    def __init__(self, **kw_args):
+        CGPCM.__init__(self, **kw_args)
+        if self.causal_id:
+            raise NotImplementedError('causal_id=True is not on the accelerated path (no task enables it)')
+        self.th = np.ascontiguousarray(self.th, dtype=np.float64)
+        self.tx = np.ascontiguousarray(self.tx, dtype=np.float64)
+        self.nh, self.nx = self.th.shape[0], self.tx.shape[0]
+        self.n = self.e.x.shape[0]
+        self.sum_y2 = float(np.sum(self.e.y ** 2))
+        sess = self.sess
+        self.engine = Engine(self.nh, self.nx, causal=self.causal, causal_id=self.causal_id,
+                             device=getattr(sess, 'device', 0))
+        rank, world = getattr(sess, 'rank', 0), getattr(sess, 'world', 1)
+        if world > 1:
+            self._init_comm(rank, world)
+        lo, hi = shard_bounds(self.n, rank, world)
+        self.engine.set_data(self.e.x[lo:hi], self.e.y[lo:hi], self.th, self.tx)
+        self._init_inducing_points()
+        self._cache = None
+        self._frozen_hyp = None
+
+    def _init_comm(self, rank, world):
+        import torch.distributed as dist
+        box = [Engine.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.engine.comm_init(box[0], rank, world)
+
+    def _init_inducing_points(self):
+        """``src/core/cgpcm.py:435-445``: ``mu_u ~ N(0, reg(iKh))``, ``var_u = tril_to_vec(chol(reg(iKh)))``.
+        Host numpy on an nh x nh matrix, once per model; the reference draws with the TF RNG."""
+        r = config.reg
+        alpha, gamma = self.alpha.eval(), self.gamma.eval()
+        th = self.th
+        Kh = np.exp(-alpha * (th[:, None] ** 2 + th[None, :] ** 2) - gamma * (th[:, None] - th[None, :]) ** 2)
+        Kh = Kh + r * np.eye(self.nh)
+        Lh = np.linalg.cholesky(Kh)
+        iLh = np.linalg.solve(Lh, np.eye(self.nh))
+        iKh = iLh.T @ iLh
+        Lp = np.linalg.cholesky(iKh + r * np.eye(self.nh))
+        self.vars['mu_u'] = Var('mu_u', Lp @ np.random.randn(self.nh, 1))
+        self.vars['var_u'] = Var('var_u', tril_to_vec(Lp))
+
+    # -- parameter vector of the C-ABI
+    def _pack(self):
+        return np.concatenate([np.array([float(self.vars[k].value) for k in _HEAD]),
+                               self.vars['mu_u'].value.ravel(), self.vars['var_u'].value.ravel()])
+
+    def _slice_grad(self, g, names):
+        parts = []
+        for nm in names:
+            if nm in _HEAD:
+                parts.append(g[_HEAD.index(nm):_HEAD.index(nm) + 1])
+            elif nm == 'mu_u':
+                parts.append(g[5:5 + self.nh])
+            elif nm == 'var_u':
+                parts.append(g[5 + self.nh:])
+            else:
+                raise KeyError('variable %r is not on the ELBO path' % nm)
+        return np.concatenate(parts)
+
+    def _evaluate(self, want_grad, names=None):
+        p = self._pack()
+        mode = MODE_FROZEN if self._precomputed else MODE_FULL
+        mask = 0
+        for nm in (names or []):
+            mask |= _MASK[nm]
+        key = (p.tobytes(), mode, config.reg, mask if want_grad else -1)
+        if self._cache is not None and self._cache[0][:3] == key[:3] and (
+                not want_grad or self._cache[0][3] == key[3]):
+            return self._cache[1]
+        out = self.engine.elbo_grad(p, mode=mode, grad_mask=mask, reg=config.reg, want_grad=want_grad)
+        self._cache = (key, out)
+        return out
+
+    # -- reference API
+    def precompute(self, recompute=False):
+        """Freeze the Psi statistics at the current hyper-parameters (``src/core/cgpcm.py:270-284``)."""
+        if recompute and self._precomputed:
+            self.undo_precompute()
+        if not self._precomputed:
+            hyp = (self.alpha.eval(), self.gamma.eval(), self.omega.eval())
+            self.engine.precompute(hyp[0], hyp[1], hyp[2], config.reg)
+            self._frozen_hyp = hyp
+            self._precomputed = True
+            self._cache = None
+
+    def undo_precompute(self):
+        """Revert precomputation (``src/core/cgpcm.py:286-292``)."""
+        if self._precomputed:
+            self._precomputed = False
+            self._cache = None
+
+    def elbo(self, smf=False, sample=None, z=True):
+        """Construct the ELBO: ``(elbo, terms)`` with ``terms`` the 7 named fetches
+        (``src/core/cgpcm.py:518-575``)."""
+        if smf or sample is not None or not z:
+            raise NotImplementedError('only the saturated q(z) bound (smf=False, z=True) is accelerated')
+        obj = Objective(self)
+        terms = [{'name': nm, 'tensor': Term(obj, i), 'modifier': '.2e'} for i, nm in enumerate(TERM_NAMES)]
+        return obj, terms
+
+    @property
+    def mats(self):
+        """Psi statistics at the current (or frozen) hyper-parameters as numpy arrays."""
+        hyp = self._frozen_hyp if self._precomputed else (self.alpha.eval(), self.gamma.eval(), self.omega.eval())
+        return self.engine.psi(*hyp)

@@ -1,0 +1,1395 @@
+// libcgpcm_b200.so — host side of the C-ABI declared in include/cgpcm_b200.h.
+//
+// One handle = one GPU + one stream.  An evaluation (cgpcm_elbo_grad) is
+//
+//   1. M x M prologue      prior kernels, Choleskys / inverses, q(u) moments          (linalg.cuh)
+//   2. forward sweep       sum_n Axx (+ tangents) in one launch; per chunk of observations the Ahx
+//                          block A[i][n][k] is generated into HBM and contracted by four DMMA GEMMs
+//                          into C1 = sum_n A_n^T H A_n, Q = sum_n A_n iKx A_n^T, Y = sum_n y_n A_n
+//   3. all-reduce #1       one packed ncclAllReduce of the forward partials (multi-GPU only)
+//   4. M x M algebra       P, its Cholesky / inverse, the 7 ELBO terms, the adjoints that seed the
+//                          backward sweep
+//   5. backward sweep      per chunk: regenerate A, Hbar = sum_n A_n C1bar A_n^T, Abar = H A_n Wx, and
+//                          the contraction of Abar with dA/d(alpha, gamma, omega) on the fly
+//   6. all-reduce #2       Hbar + 3 scalars
+//   7. M x M epilogue      closing adjoint chain, gradient assembly.
+//
+// This replaces `sess.run([elbo, grad])` of the TF graph built by src/core/cgpcm.py:518-575 (ELBO),
+// :458-477 (_optimal_q), :231-268 (model matrices), :214-229 (prior kernels) and
+// src/core/distribution.py:60-76 (KL), differentiated by tf.gradients.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/cgpcm_b200.h"
+#include "linalg.cuh"
+#include "psi_kernels.cuh"
+
+using namespace cg;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library has no link-time dependency on NCCL; inside a torch process the
+// already-loaded libnccl.so.2 is reused.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+  return api;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// matrix slots (each ld x ld doubles)
+enum Mat {
+  M_KH0, M_LH, M_IKH, M_KX0, M_KX, M_LX, M_IKX, M_AHH, M_DAHH_A, M_DAHH_G,
+  M_AXX0, M_AXX1, M_AXX2, M_AXX3,          // sum_Axx and its tangents  } packed contiguously: the
+  M_C1, M_Q, M_Y,                          //                            } forward all-reduce buffer
+  M_HBAR,                                  // backward all-reduce buffer (+ 3 scalars behind it)
+  M_LQ, M_VAR, M_LVAR, M_IVAR, M_M2, M_H, M_S, M_LP, M_PINV, M_PBAR, M_C1BAR, M_WX, M_YBAR,
+  M_SO, M_ISO, M_BHH, M_M2BAR, M_T1, M_T2, M_T3, M_XW, M_WW,
+  M_F_AXX, M_F_BHH, M_F_Y, M_F_IKH,        // frozen ("precomputed") Psi sums
+  M_COUNT
+};
+
+// vector slots (each ld doubles)
+enum Vec { V_MU, V_YTMU, V_LAM, V_LBAR, V_ISOMU, V_MUBAR, V_YLBAR, V_M2BMU, V_COUNT };
+
+// device scalars
+enum Sc {
+  S_LOGDET_KX, S_LOGDET_P, S_LOGDET_SO, S_LOGDET_VAR, S_TR_IKH_AHH, S_TR_IKX_AXX, S_TR_IKH_Q, S_TR_BHH_M2,
+  S_TR_ISO_VAR, S_MU_ISO_MU, S_LAM_LBAR, S_PBAR_S, S_C0BAR, S_G_KH_A, S_G_KH_G, S_G_KX_O, S_G_AHH_A,
+  S_G_AHH_G, S_G_AXX_A, S_G_AXX_G, S_G_AXX_O, S_COUNT
+};
+
+struct Chunk {
+  long n0;      // first observation
+  int nv;       // valid observations
+  int nc;       // padded observation count (multiple of 8)
+  int k_lo;     // first inducing input of the window (multiple of 8)
+  int kwp;      // padded window width (multiple of 8)
+};
+
+}  // namespace
+
+struct cgpcm_handle {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  int nh = 0, nx = 0, nhp = 0, nxp = 0;
+  long ld = 0;
+  int causal = 1, causal_id = 0;
+  // data
+  double *t = nullptr, *y = nullptr, *th = nullptr, *tx = nullptr;
+  long n_local = 0;
+  std::vector<double> h_t, h_th, h_tx;
+  bool t_sorted = false;
+  double sum_y2_local = 0.0;
+  // options
+  int chunk = 256;          // observations per chunk at full window width
+  double cull = 80.0;       // 0 = dense
+  // memory
+  double* mats = nullptr;
+  double* vecs = nullptr;
+  double* sc = nullptr;        // S_COUNT scalars
+  double* fwd_tail = nullptr;  // [n, sum_y2] lives behind M_Y in the packed forward buffer
+  int* info = nullptr;
+  double* params_d = nullptr;
+  double* gvar_d = nullptr;    // packed gradient of var_u
+  // chunk workspaces
+  long ws_elems = 0;
+  double *wsA = nullptr, *wsT = nullptr, *wsV = nullptr;
+  double* part = nullptr;      // split-K partials
+  long part_elems = 0;
+  double* axx_part = nullptr;
+  long axx_part_elems = 0;
+  int axx_slices = 0;
+  double* ypart = nullptr;     // [slices][nhp][ld] private Y accumulators
+  int y_slices = 0;
+  double* gpart = nullptr;     // partial sums of <Abar, dA/dtheta>
+  long gpart_elems = 0;
+  // frozen state
+  bool frozen = false;
+  PsiConst fc;
+  double f_a = 0.0, f_sum_b = 0.0;
+  // comm
+  ncclComm_t comm = nullptr;
+  bool own_comm = false;
+  int rank = 0, world = 1;
+  // bookkeeping
+  std::string err;
+  double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long launches = 0;
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+  double* M(int id) const { return mats + (long)id * ld * ld; }
+  double* V(int id) const { return vecs + (long)id * ld; }
+};
+
+namespace {
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      char buf_[512];                                                                 \
+      snprintf(buf_, sizeof buf_, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+      h->err = buf_;                                                                  \
+      return -2;                                                                      \
+    }                                                                                 \
+  } while (0)
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- small kernels ------------------------------------------------------------------------------
+
+// y[r] = alpha * sum_c op(A)[r][c] x[c]; one warp per row.
+__global__ void matvec_kernel(const double* __restrict__ A, long ld, int rows, int cols, int trans,
+                              const double* __restrict__ x, double alpha, double* __restrict__ y) {
+  int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  double s = 0.0;
+  for (int c = lane; c < cols; c += 32) s += (trans ? A[(long)c * ld + r] : A[(long)r * ld + c]) * x[c];
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if (lane == 0) y[r] = alpha * s;
+}
+
+void matvec(cgpcm_handle* h, const double* A, int rows, int cols, int trans, const double* x, double alpha,
+            double* y) {
+  matvec_kernel<<<(rows + 7) / 8, 256, 0, h->st>>>(A, h->ld, rows, cols, trans, x, alpha, y);
+  h->launches++;
+}
+
+// Sum of the slice-private Axx partials into four full symmetric ld x ld matrices.
+__global__ void axx_reduce_kernel(const double* __restrict__ part, int slices, int nmat, long ld, int nx,
+                                  double* __restrict__ out) {
+  long mat = ld * ld;
+  long total = nmat * mat;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int m = (int)(idx / mat);
+    long e = idx % mat;
+    int r = (int)(e / ld), c = (int)(e % ld);
+    double s = 0.0;
+    if (r < nx && c < nx) {
+      int rr = r >= c ? r : c, cc = r >= c ? c : r;
+      const double* p = part + (long)m * mat + (long)rr * ld + cc;
+      for (int k = 0; k < slices; ++k) s += p[(long)k * 4 * mat];
+    }
+    out[idx] = s;
+  }
+}
+
+// Y[i][k] = sum_s Ypart[s][i][k]
+__global__ void ypart_reduce_kernel(const double* __restrict__ part, int slices, long stride, long total,
+                                    double* __restrict__ out) {
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < slices; ++k) s += part[(long)k * stride + idx];
+    out[idx] = s;
+  }
+}
+
+__global__ void sum3_kernel(const double* __restrict__ gpart, long n, double* __restrict__ out) {
+  __shared__ double sh[3][32];
+  double a0 = 0, a1 = 0, a2 = 0;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+    a0 += gpart[3 * i];
+    a1 += gpart[3 * i + 1];
+    a2 += gpart[3 * i + 2];
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    a0 += __shfl_down_sync(0xffffffffu, a0, off);
+    a1 += __shfl_down_sync(0xffffffffu, a1, off);
+    a2 += __shfl_down_sync(0xffffffffu, a2, off);
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = a0; sh[1][w] = a1; sh[2][w] = a2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b0 = 0, b1 = 0, b2 = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { b0 += sh[0][i]; b1 += sh[1][i]; b2 += sh[2][i]; }
+    out[0] = b0; out[1] = b1; out[2] = b2;
+  }
+}
+
+__global__ void sumsq_kernel(const double* __restrict__ y, long n, double* __restrict__ out, int* __restrict__ bad,
+                             const double* __restrict__ t) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  int nf = 0;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+    double v = y[i];
+    s += v * v;
+    if (!isfinite(v) || !isfinite(t[i])) nf = 1;
+  }
+  if (nf) atomicExch(bad, 1);
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += sh[i];
+    out[0] = a;
+  }
+}
+
+// ---- GEMM helper --------------------------------------------------------------------------------
+
+int pick_splits(int Mr, int Nr, int K, bool lower) {
+  int bm = pick_bm(Mr);
+  int tm = (Mr + bm - 1) / bm, tn = (Nr + G_BN - 1) / G_BN;
+  int tiles = tm * tn;
+  if (lower && tiles > 1) tiles = tiles * 3 / 4 > 0 ? tiles * 3 / 4 : 1;
+  int want = (2 * 148 + tiles - 1) / tiles;
+  int kt = (K + G_BK - 1) / G_BK;
+  int max_by_k = kt / 8 > 0 ? kt / 8 : 1;   // at least 8 k-tiles per split
+  int s = std::min(want, max_by_k);
+  return s < 1 ? 1 : s;
+}
+
+}  // namespace
+
+// The lambdas below are extended __device__ lambdas: they must live in functions with external linkage.
+namespace cgimpl {
+
+using ::cgpcm_handle;
+
+inline void L(cgpcm_handle* h, int n = 1) { h->launches += n; }
+
+// out[0] = sum_{r<rows, c<cols} A[r][c] * B[r][c]
+void frob(cgpcm_handle* h, const double* A, const double* B, int rows, int cols, double* out) {
+  long ld = h->ld;
+  reduce_to(h->st, (long)rows * cols, [=] __device__(long idx) {
+    long r = idx / cols, c = idx % cols;
+    return A[r * ld + c] * B[r * ld + c];
+  }, out);
+  L(h);
+}
+
+void dot(cgpcm_handle* h, const double* a, const double* b, int n, double* out) {
+  reduce_to(h->st, (long)n, [=] __device__(long i) { return a[i] * b[i]; }, out);
+  L(h);
+}
+
+void zero(cgpcm_handle* h, double* p, long n) { cudaMemsetAsync(p, 0, n * sizeof(double), h->st); }
+
+int gemm(cgpcm_handle* h, bool a_kc, bool b_kc, bool c_tr, int Mr, int Nr, int K, double alpha, const double* A,
+         long lda, const double* B, long ldb, double beta, double* C, long ldc, int splits = 1, long stride = 0,
+         int lower = 0) {
+  cudaError_t e = dgemm(h->st, a_kc, b_kc, c_tr, Mr, Nr, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, stride, lower);
+  L(h);
+  if (e != cudaSuccess) {
+    h->err = std::string("dgemm launch failed: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  return 0;
+}
+
+// square ld x ld product on padded sizes
+int mm(cgpcm_handle* h, const double* A, bool ta, const double* B, bool tb, double* C, int Mr, int Nr, int K,
+       double alpha = 1.0, double beta = 0.0) {
+  // A(m,k): stored A[m*ld+k] (a_kc) unless transposed; B(k,n): stored B[k*ld+n] (!b_kc) unless transposed
+  return gemm(h, !ta, tb, false, Mr, Nr, K, alpha, A, h->ld, B, h->ld, beta, C, h->ld);
+}
+
+int chol_inv(cgpcm_handle* h, double* A, double* Ainv, int n, int np, double* logdet, int tag) {
+  cudaError_t e = cholinv(h->st, A, Ainv, h->M(M_XW), h->M(M_WW), n, np, h->ld, logdet, h->info, tag);
+  L(h, 40);
+  if (e != cudaSuccess) {
+    h->err = std::string("cholinv launch failed: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  return 0;
+}
+
+// ---- chunk planning -----------------------------------------------------------------------------
+
+double ahx_radius(const PsiConst& c, double cull) {
+  // E(th, d) <= -(e_dd - e_hd^2 / (4 e_hh)) d^2 for every th
+  double lam = c.e_dd - c.e_hd * c.e_hd / (4.0 * c.e_hh);
+  if (!(lam > 0.0) || !(cull > 0.0)) return INFINITY;
+  return sqrt(cull / lam);
+}
+
+void plan_chunks(cgpcm_handle* h, const PsiConst& c, std::vector<Chunk>& out) {
+  out.clear();
+  const long N = h->n_local;
+  const double R = ahx_radius(c, h->cull);
+  const long budget = (long)h->chunk * h->nxp;    // columns (n, k) per row i
+  long n0 = 0;
+  auto window = [&](long a, long b, int& k_lo, int& kwp) {
+    if (!std::isfinite(R)) { k_lo = 0; kwp = h->nxp; return; }
+    double tmin = INFINITY, tmax = -INFINITY;
+    if (h->t_sorted) { tmin = h->h_t[a]; tmax = h->h_t[b - 1]; }
+    else for (long n = a; n < b; ++n) { tmin = std::min(tmin, h->h_t[n]); tmax = std::max(tmax, h->h_t[n]); }
+    int lo = h->nx, hi = -1;
+    for (int k = 0; k < h->nx; ++k) {
+      double x = h->h_tx[k];
+      if (x >= tmin - R && x <= tmax + R) { lo = std::min(lo, k); hi = std::max(hi, k); }
+    }
+    if (hi < lo) { k_lo = 0; kwp = 8; return; }   // nothing in range: a token all-zero window
+    k_lo = lo / 8 * 8;
+    kwp = round_up(hi + 1 - k_lo, 8);
+    if (k_lo + kwp > h->nxp) kwp = h->nxp - k_lo;
+  };
+  while (n0 < N) {
+    long rem = N - n0;
+    int nc = (int)std::min<long>(rem, h->chunk);
+    int k_lo, kwp;
+    window(n0, n0 + nc, k_lo, kwp);
+    if (kwp < h->nxp && nc < rem) {
+      // narrower window: take more observations for the same workspace
+      for (int it = 0; it < 4; ++it) {
+        long cand = std::min<long>(rem, budget / kwp / 32 * 32);
+        if (cand < 32) cand = std::min<long>(rem, 32);
+        int k2, w2;
+        window(n0, n0 + cand, k2, w2);
+        if (cand * w2 <= budget) { nc = (int)cand; k_lo = k2; kwp = w2; break; }
+        kwp = w2;
+      }
+    }
+    Chunk ch;
+    ch.n0 = n0; ch.nv = nc; ch.nc = round_up(nc, 8); ch.k_lo = k_lo; ch.kwp = kwp;
+    out.push_back(ch);
+    n0 += nc;
+  }
+}
+
+int ensure_ws(cgpcm_handle* h) {
+  long need = (long)h->nhp * (round_up(h->chunk, 32) + 32) * h->nxp;
+  if (need > h->ws_elems) {
+    if (h->wsA) { cudaFree(h->wsA); cudaFree(h->wsT); cudaFree(h->wsV); }
+    h->wsA = h->wsT = h->wsV = nullptr;
+    CK(cudaMalloc(&h->wsA, need * sizeof(double)));
+    CK(cudaMalloc(&h->wsT, need * sizeof(double)));
+    CK(cudaMalloc(&h->wsV, need * sizeof(double)));
+    h->ws_elems = need;
+  }
+  return 0;
+}
+
+// ---- sweeps ---------------------------------------------------------------------------------------
+
+// sum_n Axx (and tangents) over this rank's observations -> M_AXX0..3
+int axx_sweep(cgpcm_handle* h, const PsiConst& c, const BvnTab& T, bool tangents, double* out4) {
+  const int nt = (h->nx + AXX_TILE - 1) / AXX_TILE;
+  const int ntiles = nt * (nt + 1) / 2;
+  int slices = h->axx_slices;
+  dim3 grid(ntiles, slices);
+  if (h->n_local > 0) {
+    if (tangents)
+      axx_sum_kernel<true><<<grid, 256, 0, h->st>>>(h->t, (int)h->n_local, h->t_sorted ? 1 : 0, h->tx, h->nx,
+                                                     h->axx_part, h->ld, c, T);
+    else
+      axx_sum_kernel<false><<<grid, 256, 0, h->st>>>(h->t, (int)h->n_local, h->t_sorted ? 1 : 0, h->tx, h->nx,
+                                                      h->axx_part, h->ld, c, T);
+    L(h);
+    axx_reduce_kernel<<<148 * 4, 256, 0, h->st>>>(h->axx_part, slices, tangents ? 4 : 1, h->ld, h->nx, out4);
+    L(h);
+  } else {
+    zero(h, out4, 4 * h->ld * h->ld);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int gen_chunk(cgpcm_handle* h, const PsiConst& c, const Chunk& ch, bool with_y) {
+  const int threads = std::min(256, round_up(ch.kwp, 32));
+  dim3 grid(h->nhp, (ch.nc + AHX_NSUB - 1) / AHX_NSUB);
+  if ((int)grid.y > h->y_slices) { h->err = "internal: y_slices too small"; return -1; }
+  ahx_gen_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx, h->nx,
+                                              ch.k_lo, ch.kwp, h->wsA, with_y ? h->ypart : nullptr, h->ld,
+                                              (long)h->nhp * h->ld, c);
+  L(h);
+  return 0;
+}
+
+// C (kwp x kwp window of an ld x ld matrix) += sum over splits of a K-split GEMM; symmetric result.
+int gemm_splitk_sym(cgpcm_handle* h, bool a_kc, bool b_kc, int Mr, int K, const double* A, long lda, const double* B,
+                    long ldb, double* Cwin) {
+  int splits = pick_splits(Mr, Mr, K, true);
+  long stride = (long)Mr * Mr;
+  if (splits * stride > h->part_elems) splits = (int)(h->part_elems / stride);
+  if (splits < 1) { h->err = "internal: split-K buffer too small"; return -1; }
+  // number of splits actually used by dgemm (it rounds the k range per split up to whole tiles)
+  int kt = (K + G_BK - 1) / G_BK;
+  int kt_per = (kt + splits - 1) / splits;
+  splits = (kt + kt_per - 1) / kt_per;
+  if (gemm(h, a_kc, b_kc, false, Mr, Mr, K, 1.0, A, lda, B, ldb, 0.0, h->part, Mr, splits, stride, 1)) return -2;
+  long total = (long)Mr * Mr;
+  reduce_partials_kernel<<<(int)((total + 255) / 256), 256, 0, h->st>>>(h->part, stride, splits, Cwin, Mr, Mr, Mr,
+                                                                        h->ld, 1.0, 1);
+  L(h);
+  return 0;
+}
+
+// Forward sweep over chunks: C1 += A^T (H A), and when `full`: Q += A iKx A^T, Y += sum y A.
+int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& chunks, const double* Hm,
+                  const double* iKx, bool full) {
+  zero(h, h->M(M_C1), h->ld * h->ld);
+  if (full) {
+    zero(h, h->M(M_Q), h->ld * h->ld);
+    zero(h, h->ypart, (long)h->y_slices * h->nhp * h->ld);
+  }
+  for (const Chunk& ch : chunks) {
+    if (gen_chunk(h, c, ch, full)) return -2;
+    const long cols = (long)ch.nc * ch.kwp;
+    // T1[i][(n,k)] = sum_j H[i][j] A[j][(n,k)]
+    if (gemm(h, true, false, false, h->nhp, (int)cols, h->nhp, 1.0, Hm, h->ld, h->wsA, cols, 0.0, h->wsT, cols)) return -2;
+    // C1[k][l] += sum_(i,n) A[(i,n)][k] T1[(i,n)][l]
+    if (gemm_splitk_sym(h, false, false, ch.kwp, h->nhp * ch.nc, h->wsA, ch.kwp, h->wsT, ch.kwp,
+                        h->M(M_C1) + (long)ch.k_lo * h->ld + ch.k_lo)) return -2;
+    if (full) {
+      // V[(i,n)][l] = sum_k A[(i,n)][k] iKx[k][l]   (window block of iKx)
+      if (gemm(h, true, false, false, h->nhp * ch.nc, ch.kwp, ch.kwp, 1.0, h->wsA, ch.kwp,
+               iKx + (long)ch.k_lo * h->ld + ch.k_lo, h->ld, 0.0, h->wsV, ch.kwp)) return -2;
+      // Q[i][j] += sum_(n,k) A[i][(n,k)] V[j][(n,k)]
+      if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsA, cols, h->wsV, cols, h->M(M_Q))) return -2;
+    }
+  }
+  if (full) {
+    long total = (long)h->nhp * h->ld;
+    ypart_reduce_kernel<<<148, 256, 0, h->st>>>(h->ypart, h->y_slices, total, total, h->M(M_Y));
+    L(h);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Backward sweep: Hbar = sum_n A_n C1bar A_n^T, and when `full`: g[3] = sum_n <H A_n Wx + y_n Ybar, dA_n/dtheta>.
+int backward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& chunks, const double* Hm,
+                   bool full, double* g3) {
+  zero(h, h->M(M_HBAR), h->ld * h->ld);
+  long gneed = 0;
+  for (const Chunk& ch : chunks) gneed = std::max<long>(gneed, (long)h->nhp * ((ch.nc + AHX_NSUB - 1) / AHX_NSUB));
+  if (full) {
+    if (gneed * 3 > h->gpart_elems) {
+      if (h->gpart) cudaFree(h->gpart);
+      h->gpart = nullptr;
+      CK(cudaMalloc(&h->gpart, gneed * 3 * sizeof(double)));
+      h->gpart_elems = gneed * 3;
+    }
+    zero(h, h->gpart, h->gpart_elems);
+  }
+  for (const Chunk& ch : chunks) {
+    if (gen_chunk(h, c, ch, false)) return -2;
+    const long cols = (long)ch.nc * ch.kwp;
+    // U1[(i,n)][l] = sum_k A[(i,n)][k] C1bar[k][l]
+    if (gemm(h, true, false, false, h->nhp * ch.nc, ch.kwp, ch.kwp, 1.0, h->wsA, ch.kwp,
+             h->M(M_C1BAR) + (long)ch.k_lo * h->ld + ch.k_lo, h->ld, 0.0, h->wsV, ch.kwp)) return -2;
+    // Hbar[i][j] += sum_(n,l) U1[i][(n,l)] A[j][(n,l)]
+    if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsV, cols, h->wsA, cols, h->M(M_HBAR))) return -2;
+    if (full) {
+      // T1 = H A ;  Abar = T1 Wx  (window block)
+      if (gemm(h, true, false, false, h->nhp, (int)cols, h->nhp, 1.0, Hm, h->ld, h->wsA, cols, 0.0, h->wsT, cols)) return -2;
+      if (gemm(h, true, false, false, h->nhp * ch.nc, ch.kwp, ch.kwp, 1.0, h->wsT, ch.kwp,
+               h->M(M_WX) + (long)ch.k_lo * h->ld + ch.k_lo, h->ld, 0.0, h->wsV, ch.kwp)) return -2;
+      const int threads = std::min(256, round_up(ch.kwp, 32));
+      dim3 grid(h->nhp, (ch.nc + AHX_NSUB - 1) / AHX_NSUB);
+      ahx_dot_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx,
+                                                  h->nx, ch.k_lo, ch.kwp, h->wsV, h->M(M_YBAR), h->ld, h->gpart, c);
+      L(h);
+    }
+  }
+  if (full) {
+    sum3_kernel<<<1, 1024, 0, h->st>>>(h->gpart, gneed, g3);
+    L(h);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int allreduce(cgpcm_handle* h, double* buf, long count) {
+  if (h->world <= 1 || !h->comm) return 0;
+  ncclResult_t r = nccl().AllReduce(buf, buf, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->comm, h->st);
+  if (r != 0) {
+    h->err = std::string("ncclAllReduce failed: ") + (nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+    return -2;
+  }
+  return 0;
+}
+
+// ---- M x M prologue: prior kernels, inverses (src/core/cgpcm.py:214-229) -----------------------------
+int prior_stage(cgpcm_handle* h, const PsiConst& c, double reg) {
+  const long ld = h->ld;
+  // Kh0, Kh(+jitter) -> M_LH ; Kx0, Kx(+jitter) -> M_KX ; Ahh and tangents
+  prior_kernels_kernel<<<148 * 2, 256, 0, h->st>>>(h->th, h->nh, ld, h->tx, h->nx, ld, reg, h->M(M_KH0), h->M(M_LH),
+                                                    h->M(M_KX0), h->M(M_KX), h->M(M_AHH), h->M(M_DAHH_A),
+                                                    h->M(M_DAHH_G), c);
+  L(h);
+  CK(cudaMemcpyAsync(h->M(M_LX), h->M(M_KX), ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  if (chol_inv(h, h->M(M_LH), h->M(M_IKH), h->nh, h->nhp, nullptr, 1)) return -2;
+  if (chol_inv(h, h->M(M_LX), h->M(M_IKX), h->nx, h->nxp, h->sc + S_LOGDET_KX, 2)) return -2;
+  return 0;
+}
+
+}  // namespace cgimpl
+
+using namespace cgimpl;
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int causal_id, void* nccl_comm) {
+  if (!out) return -1;
+  *out = nullptr;
+  if (nh < 1 || nx < 1 || nh > 4096 || nx > 4096) return -1;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return -2;   // no CPU fallback
+  }
+  cgpcm_handle* h = new cgpcm_handle();
+  h->device = device;
+  h->nh = nh; h->nx = nx;
+  h->nhp = round_up(nh, 8); h->nxp = round_up(nx, 8);
+  h->ld = std::max(h->nhp, h->nxp);
+  h->causal = causal ? 1 : 0;
+  h->causal_id = causal_id ? 1 : 0;
+  if (causal_id) { delete h; return -1; }   // never enabled by any task
+  auto fail = [&](int code) { cgpcm_destroy(h); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) return fail(-2);
+  if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) return fail(-2);
+  const long l2 = h->ld * h->ld;
+  // forward all-reduce buffer: M_AXX0 .. M_Y contiguous + 2 scalars directly behind M_Y requires M_Y to
+  // be followed by the tail: allocate mats with 8 spare doubles between slots M_Y and M_HBAR?  Simpler:
+  // the tail lives in its own array and the forward reduction is two collectives fused by group size.
+  if (cudaMalloc(&h->mats, (long)M_COUNT * l2 * sizeof(double)) != cudaSuccess) return fail(-2);
+  if (cudaMemsetAsync(h->mats, 0, (long)M_COUNT * l2 * sizeof(double), h->st) != cudaSuccess) return fail(-2);
+  if (cudaMalloc(&h->vecs, (long)V_COUNT * h->ld * sizeof(double)) != cudaSuccess) return fail(-2);
+  cudaMemsetAsync(h->vecs, 0, (long)V_COUNT * h->ld * sizeof(double), h->st);
+  if (cudaMalloc(&h->sc, (S_COUNT + 16) * sizeof(double)) != cudaSuccess) return fail(-2);
+  cudaMemsetAsync(h->sc, 0, (S_COUNT + 16) * sizeof(double), h->st);
+  h->fwd_tail = h->sc + S_COUNT;   // [n, sum_y2, g_alpha, g_gamma, g_omega]
+  if (cudaMalloc(&h->info, 4 * sizeof(int)) != cudaSuccess) return fail(-2);
+  cudaMemsetAsync(h->info, 0, 4 * sizeof(int), h->st);
+  const long np = 5 + nh + (long)nh * (nh + 1) / 2;
+  if (cudaMalloc(&h->params_d, np * sizeof(double)) != cudaSuccess) return fail(-2);
+  if (cudaMalloc(&h->gvar_d, np * sizeof(double)) != cudaSuccess) return fail(-2);
+  h->part_elems = std::max<long>(320 * 64 * 64, 100 * l2);
+  if (cudaMalloc(&h->part, h->part_elems * sizeof(double)) != cudaSuccess) return fail(-2);
+  h->axx_slices = 32;
+  h->axx_part_elems = (long)h->axx_slices * 4 * l2;
+  if (cudaMalloc(&h->axx_part, h->axx_part_elems * sizeof(double)) != cudaSuccess) return fail(-2);
+  for (auto& e : h->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return fail(-2);
+  if (nccl_comm) { h->comm = (ncclComm_t)nccl_comm; h->own_comm = false; }   // rank / world: cgpcm_comm_init(h, NULL, ..)
+  if (cudaStreamSynchronize(h->st) != cudaSuccess) return fail(-2);
+  *out = h;
+  return 0;
+}
+
+int cgpcm_destroy(cgpcm_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->st) cudaStreamSynchronize(h->st);
+  if (h->comm && h->own_comm && nccl().ok) nccl().CommDestroy(h->comm);
+  double* ptrs[] = {h->t, h->y, h->th, h->tx, h->mats, h->vecs, h->sc, h->params_d, h->gvar_d, h->wsA, h->wsT,
+                    h->wsV, h->part, h->axx_part, h->ypart, h->gpart};
+  for (double* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->info) cudaFree(h->info);
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return 0;
+}
+
+const char* cgpcm_last_error(const cgpcm_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int cgpcm_comm_unique_id(void* id128) {
+  if (!id128) return -1;
+  if (!nccl().ok) return -2;
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != 0) return -2;
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+int cgpcm_comm_init(cgpcm_handle* h, const void* id128, int rank, int world) {
+  if (!h || world < 1 || rank < 0 || rank >= world) return -1;
+  CK(cudaSetDevice(h->device));
+  h->rank = rank;
+  h->world = world;
+  if (world == 1) return 0;
+  if (h->comm && !h->own_comm) return 0;   // communicator supplied at create time
+  if (!id128) return -1;
+  if (!nccl().ok) { h->err = "NCCL library not loadable"; return -2; }
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ncclResult_t r = nccl().CommInitRank(&h->comm, world, id, rank);
+  if (r != 0) {
+    h->err = std::string("ncclCommInitRank failed: ") + (nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+    h->comm = nullptr;
+    return -2;
+  }
+  h->own_comm = true;
+  return 0;
+}
+
+int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
+  if (!h || !key) return -1;
+  if (!strcmp(key, "chunk")) {
+    if (value < 8 || value > (1 << 20)) { h->err = "chunk out of range"; return -1; }
+    h->chunk = round_up((int)value, 32);
+    return 0;
+  }
+  if (!strcmp(key, "cull")) {
+    if (value < 0) { h->err = "cull must be >= 0"; return -1; }
+    h->cull = value;
+    return 0;
+  }
+  h->err = std::string("unknown option ") + key;
+  return -1;
+}
+
+int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_local, const double* th,
+                   const double* tx) {
+  if (!h || n_local < 0 || !th || !tx || (n_local > 0 && (!t || !y))) return -1;
+  if (n_local > 2000000000LL) { h->err = "n_local too large"; return -1; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->st));
+  if (h->t) { cudaFree(h->t); h->t = nullptr; }
+  if (h->y) { cudaFree(h->y); h->y = nullptr; }
+  if (!h->th) CK(cudaMalloc(&h->th, h->ld * sizeof(double)));
+  if (!h->tx) CK(cudaMalloc(&h->tx, h->ld * sizeof(double)));
+  h->n_local = n_local;
+  h->frozen = false;
+  const long na = std::max<long>(n_local, 1);
+  CK(cudaMalloc(&h->t, na * sizeof(double)));
+  CK(cudaMalloc(&h->y, na * sizeof(double)));
+  if (n_local > 0) {
+    CK(cudaMemcpyAsync(h->t, t, n_local * sizeof(double), cudaMemcpyDefault, h->st));
+    CK(cudaMemcpyAsync(h->y, y, n_local * sizeof(double), cudaMemcpyDefault, h->st));
+  }
+  CK(cudaMemsetAsync(h->th, 0, h->ld * sizeof(double), h->st));
+  CK(cudaMemsetAsync(h->tx, 0, h->ld * sizeof(double), h->st));
+  CK(cudaMemcpyAsync(h->th, th, h->nh * sizeof(double), cudaMemcpyDefault, h->st));
+  CK(cudaMemcpyAsync(h->tx, tx, h->nx * sizeof(double), cudaMemcpyDefault, h->st));
+  h->h_t.resize(n_local);
+  h->h_th.resize(h->nh);
+  h->h_tx.resize(h->nx);
+  if (n_local > 0) CK(cudaMemcpyAsync(h->h_t.data(), h->t, n_local * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(h->h_th.data(), h->th, h->nh * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(h->h_tx.data(), h->tx, h->nx * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), h->st));
+  CK(cudaMemsetAsync(h->fwd_tail, 0, 2 * sizeof(double), h->st));
+  if (n_local > 0) sumsq_kernel<<<1, 1024, 0, h->st>>>(h->y, n_local, h->fwd_tail + 1, h->info + 1, h->t);
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, h->info + 1, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(&h->sum_y2_local, h->fwd_tail + 1, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  for (int i = 0; i < h->nh; ++i) if (!std::isfinite(h->h_th[i])) bad = 1;
+  for (int i = 0; i < h->nx; ++i) if (!std::isfinite(h->h_tx[i])) bad = 1;
+  if (bad) { h->err = "non-finite value in t, y, th or tx"; return -4; }
+  h->t_sorted = true;
+  for (long i = 1; i < n_local; ++i)
+    if (h->h_t[i] < h->h_t[i - 1]) { h->t_sorted = false; break; }
+  return 0;
+}
+
+}  // extern "C"
+
+namespace cgimpl {
+
+int ensure_sweep_buffers(cgpcm_handle* h) {
+  if (ensure_ws(h)) return -2;
+  int ys = (round_up(h->chunk, 32) + 32) * h->nxp / 8 / AHX_NSUB + 2;   // narrowest window = 8 columns
+  if (ys > h->y_slices) {
+    if (h->ypart) cudaFree(h->ypart);
+    h->ypart = nullptr;
+    CK(cudaMalloc(&h->ypart, (long)ys * h->nhp * h->ld * sizeof(double)));
+    h->y_slices = ys;
+  }
+  return 0;
+}
+
+// copy an (r x c) block of a padded ld-matrix to a dense user buffer (host or device)
+int export_mat(cgpcm_handle* h, const double* src, int r, int c, double* dst) {
+  if (!dst) return 0;
+  CK(cudaMemcpy2DAsync(dst, (size_t)c * sizeof(double), src, (size_t)h->ld * sizeof(double), (size_t)c * sizeof(double),
+                       r, cudaMemcpyDefault, h->st));
+  return 0;
+}
+
+// Psi sums at hyper-parameters c: fills M_AXX0 (+tangents), M_Q, M_Y, M_C1 (with H given) ...
+struct EvalScalars {
+  double n_glob, sum_y2;
+};
+
+}  // namespace cgimpl
+
+extern "C" {
+
+int cgpcm_psi(cgpcm_handle* h, const double hyp[3], double* sum_Axx, double* Ahh, double* a, double* sum_Ahx_y,
+              double* Ahx, double* Axx) {
+  if (!h || !hyp) return -1;
+  if (!h->t) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  for (int i = 0; i < 3; ++i)
+    if (!std::isfinite(hyp[i]) || hyp[i] <= 0) { h->err = "hyper-parameters must be positive and finite"; return -4; }
+  CK(cudaSetDevice(h->device));
+  if (ensure_sweep_buffers(h)) return -2;
+  h->launches = 0;
+  PsiConst c;
+  psi_make_const(hyp[0], hyp[1], hyp[2], h->causal, h->cull, &c);
+  BvnTab T;
+  bvn_make_tab(hyp[1] / (hyp[0] + hyp[1] + hyp[2]), &T);
+  CK(cudaEventRecord(h->ev[0], h->st));
+  const long ld = h->ld;
+  prior_kernels_kernel<<<148 * 2, 256, 0, h->st>>>(h->th, h->nh, ld, h->tx, h->nx, ld, 0.0, h->M(M_KH0), h->M(M_LH),
+                                                    h->M(M_KX0), h->M(M_KX), h->M(M_AHH), h->M(M_DAHH_A),
+                                                    h->M(M_DAHH_G), c);
+  L(h);
+  if (sum_Axx) {
+    if (axx_sweep(h, c, T, false, h->M(M_AXX0))) return -2;
+    if (allreduce(h, h->M(M_AXX0), ld * ld)) return -2;
+    if (export_mat(h, h->M(M_AXX0), h->nx, h->nx, sum_Axx)) return -2;
+  }
+  if (export_mat(h, h->M(M_AHH), h->nh, h->nh, Ahh)) return -2;
+  if (a) {
+    double av = (h->causal ? 0.5 : 1.0) * sqrt(3.14159265358979323846 / (2.0 * hyp[0]));
+    CK(cudaMemcpyAsync(h->sc, &av, sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(a, h->sc, sizeof(double), cudaMemcpyDefault, h->st));
+  }
+  if (sum_Ahx_y) {
+    // Y only: generate chunks with the fused y-reduction, no GEMMs
+    std::vector<Chunk> chunks;
+    plan_chunks(h, c, chunks);
+    zero(h, h->ypart, (long)h->y_slices * h->nhp * ld);
+    for (const Chunk& ch : chunks)
+      if (gen_chunk(h, c, ch, true)) return -2;
+    long total = (long)h->nhp * ld;
+    ypart_reduce_kernel<<<148, 256, 0, h->st>>>(h->ypart, h->y_slices, total, total, h->M(M_Y));
+    L(h);
+    if (allreduce(h, h->M(M_Y), ld * ld)) return -2;
+    if (export_mat(h, h->M(M_Y), h->nh, h->nx, sum_Ahx_y)) return -2;
+  }
+  if (Ahx && h->n_local > 0) {
+    double* dst = Ahx;
+    double* tmp = nullptr;
+    long total = h->n_local * h->nh * h->nx;
+    if (!is_device_ptr(Ahx)) { CK(cudaMalloc(&tmp, total * sizeof(double))); dst = tmp; }
+    ahx_user_kernel<<<148 * 8, 256, 0, h->st>>>(h->t, (int)h->n_local, h->th, h->nh, h->tx, h->nx, dst, c);
+    L(h);
+    if (tmp) {
+      CK(cudaMemcpyAsync(Ahx, tmp, total * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      cudaFree(tmp);
+    }
+  }
+  if (Axx && h->n_local > 0) {
+    double* dst = Axx;
+    double* tmp = nullptr;
+    long total = h->n_local * h->nx * h->nx;
+    if (!is_device_ptr(Axx)) { CK(cudaMalloc(&tmp, total * sizeof(double))); dst = tmp; }
+    axx_user_kernel<<<148 * 8, 256, 0, h->st>>>(h->t, (int)h->n_local, h->tx, h->nx, dst, c, T);
+    L(h);
+    if (tmp) {
+      CK(cudaMemcpyAsync(Axx, tmp, total * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      cudaFree(tmp);
+    }
+  }
+  CK(cudaEventRecord(h->ev[1], h->st));
+  CK(cudaStreamSynchronize(h->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  memset(h->timing, 0, sizeof h->timing);
+  h->timing[0] = ms;
+  h->timing[6] = (double)h->launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+
+namespace cgimpl {
+
+// The whole evaluation.  mode FULL: hyper-parameters from params; mode FROZEN: Psi sums from the frozen
+// state (precompute), prior kernels still from params (they stay symbolic in the reference too).
+// `freeze`: run the forward Psi sums only and store them (cgpcm_precompute).
+int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad_mask, double reg, bool freeze,
+             double* elbo, double* terms, double* grad) {
+  const int nh = h->nh, nx = h->nx, nhp = h->nhp, nxp = h->nxp;
+  const long ld = h->ld, l2 = ld * ld;
+  const long nvar = (long)nh * (nh + 1) / 2;
+  const long np = 5 + nh + nvar;
+  for (long i = 0; i < (freeze ? 5 : np); ++i)
+    if (!std::isfinite(params_host[i])) { h->err = "non-finite parameter"; return -4; }
+  const double s2 = exp(params_host[0]), s2f = exp(params_host[1]);
+  const double alpha = exp(params_host[2]), gamma = exp(params_host[3]), omega = exp(params_host[4]);
+  const double r = s2f / s2, c0 = sqrt(s2f) / s2;
+  const bool full = (mode == CGPCM_MODE_FULL) || freeze;
+  if (!full && !h->frozen) { h->err = "MODE_FROZEN requires cgpcm_precompute"; return -1; }
+  if (ensure_sweep_buffers(h)) return -2;
+  h->launches = 0;
+
+  PsiConst c;
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
+  BvnTab T;
+  bvn_make_tab(gamma / (alpha + gamma + omega), &T);
+  const PsiConst& ca = full ? c : h->fc;       // constants that generate A
+  std::vector<Chunk> chunks;
+  plan_chunks(h, ca, chunks);
+
+  cudaStream_t st = h->st;
+  CK(cudaEventRecord(h->ev[0], st));
+  CK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
+  if (!freeze) CK(cudaMemcpyAsync(h->params_d, params_host, np * sizeof(double), cudaMemcpyHostToDevice, st));
+
+  // ---- 1. prologue
+  if (prior_stage(h, c, reg)) return -2;
+  double* Hm = h->M(M_H);
+  const double* ikh_cur = h->M(M_IKH);
+  const double* tl = h->fwd_tail;               // device: [N (all ranks), sum y^2 (all ranks)]
+  if (!freeze) {
+    // q(u): L from var_u (np.tril_indices order, src/core/tf_util.py:419-447), var = L L^T + reg I
+    // (src/core/cgpcm.py:444-445), m2 = var + mu mu^T (src/core/distribution.py:35-42)
+    double* Lq = h->M(M_LQ);
+    double* mu = h->V(V_MU);
+    const double* pd = h->params_d;
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      Lq[idx] = (i < nh && j <= i) ? pd[5 + nh + (long)i * (i + 1) / 2 + j] : 0.0;
+      if (idx < ld) mu[idx] = idx < nh ? pd[5 + idx] : 0.0;
+    });
+    L(h);
+    if (mm(h, Lq, false, Lq, true, h->M(M_VAR), nhp, nhp, nhp)) return -2;
+    double* var = h->M(M_VAR);
+    double* lvar = h->M(M_LVAR);
+    double* m2 = h->M(M_M2);
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      double v = var[idx] + ((i == j && i < nh) ? reg : 0.0);
+      var[idx] = v;
+      lvar[idx] = v;
+      double m = v + mu[i] * mu[j];
+      m2[idx] = m;
+      // FULL: H = m2 - iKh.  FROZEN: the frozen sum_Bxx already carries -sum A^T iKh A, so H = m2.
+      Hm[idx] = full ? m - ikh_cur[idx] : m;
+    });
+    L(h);
+  } else {
+    // the frozen sums do not depend on q(u): H = -iKh gives C1 = -sum A^T iKh A (so that sum_Bxx = Axx + C1)
+    const double* ik = h->M(M_IKH);
+    ew(st, l2, [=] __device__(long idx) { Hm[idx] = -ik[idx]; });
+    L(h);
+  }
+  CK(cudaEventRecord(h->ev[1], st));
+
+  // ---- 2. forward sweep
+  if (full) {
+    if (axx_sweep(h, c, T, !freeze, h->M(M_AXX0))) return -2;
+  }
+  CK(cudaEventRecord(h->ev[2], st));
+  if (forward_sweep(h, ca, chunks, Hm, h->M(M_IKX), full)) return -2;
+  // tail scalars [n, sum_y2]
+  {
+    double tail[2] = {(double)h->n_local, h->sum_y2_local};
+    CK(cudaMemcpyAsync(h->fwd_tail, tail, sizeof tail, cudaMemcpyHostToDevice, st));
+  }
+  // ---- 3. all-reduce #1 (M_AXX0..M_Y are contiguous)
+  if (h->world > 1) {
+    if (full) { if (allreduce(h, h->M(M_AXX0), 7 * l2)) return -2; }
+    else { if (allreduce(h, h->M(M_C1), l2)) return -2; }
+    if (allreduce(h, h->fwd_tail, 2)) return -2;
+  }
+  CK(cudaEventRecord(h->ev[3], st));
+
+  if (freeze) {
+    // sum_Bhh = N Ahh - Q ; sum_b = N a - N tr(iKh Ahh) - tr(iKx sum_Axx) + tr(iKh Q)
+    frob(h, h->M(M_IKH), h->M(M_AHH), nh, nh, h->sc + S_TR_IKH_AHH);
+    frob(h, h->M(M_IKX), h->M(M_AXX0), nx, nx, h->sc + S_TR_IKX_AXX);
+    frob(h, h->M(M_IKH), h->M(M_Q), nh, nh, h->sc + S_TR_IKH_Q);
+    double hs[S_COUNT + 16];
+    int info[4];
+    CK(cudaMemcpyAsync(hs, h->sc, sizeof hs, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(info, h->info, sizeof info, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->M(M_F_AXX), h->M(M_AXX0), l2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->M(M_F_Y), h->M(M_Y), l2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->M(M_F_IKH), h->M(M_IKH), l2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // frozen sum_Bxx = sum_Axx + C1(-iKh): keep it in M_F_AXX's companion: store C1 into M_T3? -> fold:
+    {
+      double* fa = h->M(M_F_AXX);
+      const double* c1 = h->M(M_C1);
+      ew(st, l2, [=] __device__(long idx) { fa[idx] += c1[idx]; });   // M_F_AXX now holds sum_Bxx
+      L(h);
+    }
+    CK(cudaStreamSynchronize(st));
+    if (info[0]) {
+      char b[128];
+      snprintf(b, sizeof b, "matrix %s is not positive definite (pivot %d)", info[0] / 100000 == 1 ? "Kh" : "Kx",
+               info[0] % 100000);
+      h->err = b;
+      return -3;
+    }
+    const double Ng = hs[S_COUNT + 0];
+    const double a = (h->causal ? 0.5 : 1.0) * sqrt(3.14159265358979323846 / (2.0 * alpha));
+    {
+      double* fb = h->M(M_F_BHH);
+      const double* ahh = h->M(M_AHH);
+      const double* q = h->M(M_Q);
+      ew(st, l2, [=] __device__(long idx) { fb[idx] = Ng * ahh[idx] - q[idx]; });
+      L(h);
+    }
+    h->f_a = a;
+    h->f_sum_b = Ng * a - Ng * hs[S_TR_IKH_AHH] - hs[S_TR_IKX_AXX] + hs[S_TR_IKH_Q];
+    h->fc = c;
+    h->frozen = true;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  // ---- 4. M x M algebra
+  // S = sum_Bxx + sum A^T m2 A.  FULL: sum_Axx + C1 (C1 built with H = m2 - iKh).  FROZEN: frozen sum_Bxx + C1(m2).
+  double* S = h->M(M_S);
+  double* Pm = h->M(M_LP);
+  {
+    const double* axx = full ? h->M(M_AXX0) : h->M(M_F_AXX);
+    const double* c1 = h->M(M_C1);
+    const double* kx = h->M(M_KX);
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      double s = axx[idx] + c1[idx];
+      S[idx] = s;
+      Pm[idx] = kx[idx] + r * s + ((i == j && i < nx) ? reg : 0.0);
+    });
+    L(h);
+  }
+  if (chol_inv(h, Pm, h->M(M_PINV), nx, nxp, h->sc + S_LOGDET_P, 3)) return -2;
+  const double* Ym = full ? h->M(M_Y) : h->M(M_F_Y);
+  matvec(h, Ym, nx, nh, 1, h->V(V_MU), 1.0, h->V(V_YTMU));                 // Y^T mu
+  matvec(h, h->M(M_PINV), nx, nx, 0, h->V(V_YTMU), c0, h->V(V_LBAR));       // lbar = Pinv lam, lam = c0 Y^T mu
+  {
+    const double* ytmu = h->V(V_YTMU);
+    const double* lbar = h->V(V_LBAR);
+    reduce_to(st, (long)nx, [=] __device__(long i) { return c0 * ytmu[i] * lbar[i]; }, h->sc + S_LAM_LBAR);
+    reduce_to(st, (long)nx, [=] __device__(long i) { return ytmu[i] * lbar[i]; }, h->sc + S_C0BAR);
+    L(h, 2);
+  }
+  // adjoint seeds: Pbar = -1/2 Pinv - 1/2 lbar lbar^T ; C1bar = r Pbar ; Wx = r (2 Pbar + iKx) ; Ybar = c0 mu lbar^T
+  {
+    const double* pinv = h->M(M_PINV);
+    const double* lbar = h->V(V_LBAR);
+    const double* mu = h->V(V_MU);
+    const double* ikx = h->M(M_IKX);
+    double* pbar = h->M(M_PBAR);
+    double* c1bar = h->M(M_C1BAR);
+    double* wx = h->M(M_WX);
+    double* ybar = h->M(M_YBAR);
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      double pb = -0.5 * pinv[idx] - 0.5 * lbar[i] * lbar[j];
+      pbar[idx] = pb;
+      c1bar[idx] = r * pb;
+      wx[idx] = r * (2.0 * pb + ikx[idx]);
+      ybar[idx] = c0 * mu[i] * lbar[j];    // rows i < nhp (mu zero-padded), columns j
+    });
+    L(h);
+  }
+  frob(h, h->M(M_PBAR), S, nx, nx, h->sc + S_PBAR_S);
+  // KL pieces (src/core/distribution.py:60-76): So = iKh + reg I, var
+  {
+    double* so = h->M(M_SO);
+    const double* ikh = h->M(M_IKH);
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      so[idx] = ikh[idx] + ((i == j && i < nh) ? reg : 0.0);
+    });
+    L(h);
+  }
+  if (chol_inv(h, h->M(M_SO), h->M(M_ISO), nh, nhp, h->sc + S_LOGDET_SO, 4)) return -2;
+  if (chol_inv(h, h->M(M_LVAR), h->M(M_IVAR), nh, nhp, h->sc + S_LOGDET_VAR, 5)) return -2;
+  frob(h, h->M(M_ISO), h->M(M_VAR), nh, nh, h->sc + S_TR_ISO_VAR);
+  matvec(h, h->M(M_ISO), nh, nh, 0, h->V(V_MU), 1.0, h->V(V_ISOMU));
+  dot(h, h->V(V_MU), h->V(V_ISOMU), nh, h->sc + S_MU_ISO_MU);
+  CK(cudaEventRecord(h->ev[4], st));
+
+  // ---- 5. backward sweep
+  const bool want_hyp = full && (grad_mask & (CGPCM_GRAD_ALPHA | CGPCM_GRAD_GAMMA | CGPCM_GRAD_OMEGA));
+  const bool want_q = grad_mask & (CGPCM_GRAD_MU_U | CGPCM_GRAD_VAR_U);
+  const bool want_grad = grad && grad_mask;
+  if (want_grad && (want_hyp || want_q)) {
+    if (backward_sweep(h, ca, chunks, Hm, want_hyp, h->fwd_tail + 2)) return -2;
+    // ---- 6. all-reduce #2
+    if (h->world > 1) {
+      if (allreduce(h, h->M(M_HBAR), l2)) return -2;
+      if (want_hyp && allreduce(h, h->fwd_tail + 2, 3)) return -2;
+    }
+  }
+  CK(cudaEventRecord(h->ev[5], st));
+  const double a = (h->causal ? 0.5 : 1.0) * sqrt(3.14159265358979323846 / (2.0 * alpha));
+
+  // ---- 7. epilogue
+  double* bhh = h->M(M_BHH);
+  if (full) {
+    const double* ahh = h->M(M_AHH);
+    const double* q = h->M(M_Q);
+    ew(st, l2, [=] __device__(long idx) { bhh[idx] = tl[0] * ahh[idx] - q[idx]; });
+    L(h);
+    frob(h, h->M(M_IKH), h->M(M_AHH), nh, nh, h->sc + S_TR_IKH_AHH);
+    frob(h, h->M(M_IKX), h->M(M_AXX0), nx, nx, h->sc + S_TR_IKX_AXX);
+    frob(h, h->M(M_IKH), h->M(M_Q), nh, nh, h->sc + S_TR_IKH_Q);
+  } else {
+    CK(cudaMemcpyAsync(bhh, h->M(M_F_BHH), l2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  frob(h, bhh, h->M(M_M2), nh, nh, h->sc + S_TR_BHH_M2);
+
+  if (want_grad) {
+    // m2bar = Hbar - 1/2 r sum_Bhh ; varbar = m2bar - 1/2 (iSo - ivar) ; Lbar = tril(2 varbar L)
+    double* m2bar = h->M(M_M2BAR);
+    double* varbar = h->M(M_T1);
+    {
+      const double* hbar = h->M(M_HBAR);
+      const double* iso = h->M(M_ISO);
+      const double* ivar = h->M(M_IVAR);
+      ew(st, l2, [=] __device__(long idx) {
+        double m = hbar[idx] - 0.5 * r * bhh[idx];
+        m2bar[idx] = m;
+        varbar[idx] = m - 0.5 * (iso[idx] - ivar[idx]);
+      });
+      L(h);
+    }
+    if (mm(h, varbar, false, h->M(M_LQ), false, h->M(M_T2), nhp, nhp, nhp, 2.0)) return -2;
+    // mubar = 2 m2bar mu + c0 Y lbar - iSo mu
+    matvec(h, m2bar, nh, nh, 0, h->V(V_MU), 2.0, h->V(V_M2BMU));
+    matvec(h, Ym, nh, nx, 0, h->V(V_LBAR), c0, h->V(V_YLBAR));
+    {
+      const double* t2 = h->M(M_T2);
+      const double* a1 = h->V(V_M2BMU);
+      const double* a2 = h->V(V_YLBAR);
+      const double* a3 = h->V(V_ISOMU);
+      double* g = h->gvar_d;
+      const bool wmu = grad_mask & CGPCM_GRAD_MU_U, wvar = grad_mask & CGPCM_GRAD_VAR_U;
+      ew(st, np, [=] __device__(long idx) {
+        double v = 0.0;
+        if (idx >= 5 && idx < 5 + nh) {
+          long i = idx - 5;
+          if (wmu) v = a1[i] + a2[i] - a3[i];
+        } else if (idx >= 5 + nh && wvar) {
+          long e = idx - 5 - nh;
+          long i = (long)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+          while ((i + 1) * (i + 2) / 2 <= e) ++i;
+          while (i * (i + 1) / 2 > e) --i;
+          long j = e - i * (i + 1) / 2;
+          v = t2[i * ld + j];
+        }
+        g[idx] = v;
+      });
+      L(h);
+    }
+    if (want_hyp) {
+      // Sobar = 1/2 (iSo var iSo + (iSo mu)(iSo mu)^T - iSo)
+      if (mm(h, h->M(M_ISO), false, h->M(M_VAR), false, h->M(M_T2), nhp, nhp, nhp)) return -2;
+      if (mm(h, h->M(M_T2), false, h->M(M_ISO), false, h->M(M_T3), nhp, nhp, nhp)) return -2;
+      // iKhbar = -Hbar + 1/2 r N Ahh - 1/2 r Q + Sobar  -> M_T2
+      {
+        const double* t3 = h->M(M_T3);
+        const double* iso = h->M(M_ISO);
+        const double* ismu = h->V(V_ISOMU);
+        const double* hbar = h->M(M_HBAR);
+        double* out = h->M(M_T2);
+        ew(st, l2, [=] __device__(long idx) {
+          int i = (int)(idx / ld), j = (int)(idx % ld);
+          double sobar = 0.5 * (t3[idx] + ismu[i] * ismu[j] - iso[idx]);
+          out[idx] = -hbar[idx] + 0.5 * r * bhh[idx] + sobar;
+        });
+        L(h);
+      }
+      // Khbar = -iKh iKhbar iKh -> M_T1
+      if (mm(h, h->M(M_IKH), false, h->M(M_T2), false, h->M(M_T3), nhp, nhp, nhp)) return -2;
+      if (mm(h, h->M(M_T3), false, h->M(M_IKH), false, h->M(M_T1), nhp, nhp, nhp, -1.0)) return -2;
+      {
+        const double* khbar = h->M(M_T1);
+        const double* kh0 = h->M(M_KH0);
+        const double* thd = h->th;
+        reduce_to(st, (long)nh * nh, [=] __device__(long idx) {
+          long i = idx / nh, j = idx % nh;
+          double ti = thd[i], tj = thd[j];
+          return -khbar[i * ld + j] * (ti * ti + tj * tj) * kh0[i * ld + j];
+        }, h->sc + S_G_KH_A);
+        reduce_to(st, (long)nh * nh, [=] __device__(long idx) {
+          long i = idx / nh, j = idx % nh;
+          double d = thd[i] - thd[j];
+          return -khbar[i * ld + j] * d * d * kh0[i * ld + j];
+        }, h->sc + S_G_KH_G);
+        L(h, 2);
+      }
+      // Kxbar = -iKx iKxbar iKx + Pbar + 1/2 iKx,  iKxbar = 1/2 r S
+      if (mm(h, h->M(M_IKX), false, S, false, h->M(M_T3), nxp, nxp, nxp)) return -2;
+      if (mm(h, h->M(M_T3), false, h->M(M_IKX), false, h->M(M_T2), nxp, nxp, nxp, -0.5 * r)) return -2;
+      {
+        const double* t2 = h->M(M_T2);
+        const double* pbar = h->M(M_PBAR);
+        const double* ikx = h->M(M_IKX);
+        const double* kx0 = h->M(M_KX0);
+        const double* txd = h->tx;
+        reduce_to(st, (long)nx * nx, [=] __device__(long idx) {
+          long k = idx / nx, l = idx % nx;
+          double kxbar = t2[k * ld + l] + pbar[k * ld + l] + 0.5 * ikx[k * ld + l];
+          double d = txd[k] - txd[l];
+          return -kxbar * (0.5 / omega + 0.5 * d * d) * kx0[k * ld + l];
+        }, h->sc + S_G_KX_O);
+        L(h);
+      }
+      // <Ahhbar, dAhh>,  Ahhbar = 1/2 r N (iKh - m2)
+      {
+        const double* ikh = h->M(M_IKH);
+        const double* m2 = h->M(M_M2);
+        const double* da = h->M(M_DAHH_A);
+        const double* dg = h->M(M_DAHH_G);
+        reduce_to(st, (long)nh * nh, [=] __device__(long idx) {
+          long i = idx / nh, j = idx % nh;
+          return 0.5 * r * tl[0] * (ikh[i * ld + j] - m2[i * ld + j]) * da[i * ld + j];
+        }, h->sc + S_G_AHH_A);
+        reduce_to(st, (long)nh * nh, [=] __device__(long idx) {
+          long i = idx / nh, j = idx % nh;
+          return 0.5 * r * tl[0] * (ikh[i * ld + j] - m2[i * ld + j]) * dg[i * ld + j];
+        }, h->sc + S_G_AHH_G);
+        L(h, 2);
+      }
+      // <Axxbar, dAxx>,  Axxbar = r Pbar + 1/2 r iKx
+      {
+        const double* pbar = h->M(M_PBAR);
+        const double* ikx = h->M(M_IKX);
+        for (int k3 = 0; k3 < 3; ++k3) {
+          const double* dm = h->M(M_AXX1 + k3);
+          reduce_to(st, (long)nx * nx, [=] __device__(long idx) {
+            long k = idx / nx, l = idx % nx;
+            return r * (pbar[k * ld + l] + 0.5 * ikx[k * ld + l]) * dm[k * ld + l];
+          }, h->sc + S_G_AXX_A + k3);
+        }
+        L(h, 3);
+      }
+    }
+  }
+
+  // ---- collect
+  double hs[S_COUNT + 16];
+  int info[4];
+  CK(cudaMemcpyAsync(hs, h->sc, sizeof hs, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(info, h->info, sizeof info, cudaMemcpyDeviceToHost, st));
+  if (want_grad) CK(cudaMemcpyAsync(grad, h->gvar_d, np * sizeof(double), cudaMemcpyDefault, st));
+  CK(cudaEventRecord(h->ev[6], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  const double Ng = hs[S_COUNT + 0], sum_y2 = hs[S_COUNT + 1];
+  if (info[0]) {
+    static const char* names[] = {"?", "Kh", "Kx", "P", "iKh + reg I (prior of q(u))", "q(u) covariance"};
+    int tag = info[0] / 100000;
+    char b[160];
+    snprintf(b, sizeof b, "matrix %s is not positive definite (pivot %d)", tag >= 1 && tag <= 5 ? names[tag] : "?",
+             info[0] % 100000);
+    h->err = b;
+    return -3;
+  }
+  double sum_b, tr_bhh_m2 = hs[S_TR_BHH_M2];
+  if (full) sum_b = Ng * a - Ng * hs[S_TR_IKH_AHH] - hs[S_TR_IKX_AXX] + hs[S_TR_IKH_Q];
+  else sum_b = h->f_sum_b;
+  const double KL = 0.5 * (hs[S_TR_ISO_VAR] + hs[S_MU_ISO_MU] - nh + hs[S_LOGDET_SO] - hs[S_LOGDET_VAR]);
+  double tm[7];
+  tm[0] = -0.5 * Ng * log(2.0 * 3.14159265358979323846 * s2) - 0.5 * sum_y2 / s2;
+  tm[1] = 0.5 * hs[S_LOGDET_KX];
+  tm[2] = -0.5 * hs[S_LOGDET_P];
+  tm[3] = 0.5 * hs[S_LAM_LBAR];
+  tm[4] = -0.5 * r * sum_b;
+  tm[5] = -0.5 * r * tr_bhh_m2;
+  tm[6] = -KL;
+  double e = 0.0;
+  for (int i = 0; i < 7; ++i) e += tm[i];
+  if (terms) memcpy(terms, tm, sizeof tm);
+  if (elbo) *elbo = e;
+  if (want_grad) {
+    const double rbar = hs[S_PBAR_S] - 0.5 * sum_b - 0.5 * tr_bhh_m2;
+    const double c0bar = hs[S_C0BAR];
+    double g5[5] = {0, 0, 0, 0, 0};
+    if (grad_mask & CGPCM_GRAD_S2) g5[0] = -r * rbar - c0 * c0bar - 0.5 * Ng + 0.5 * sum_y2 / s2;
+    if (grad_mask & CGPCM_GRAD_S2F) g5[1] = r * rbar + 0.5 * c0 * c0bar;
+    if (want_hyp) {
+      const double abar = -0.5 * r * Ng;
+      const double* gA = hs + S_COUNT + 2;
+      double ga = hs[S_G_KH_A] + abar * (-a / (2.0 * alpha)) + hs[S_G_AHH_A] + hs[S_G_AXX_A] + gA[0];
+      double gg = hs[S_G_KH_G] + hs[S_G_AHH_G] + hs[S_G_AXX_G] + gA[1];
+      double go = hs[S_G_KX_O] + hs[S_G_AXX_O] + gA[2];
+      if (grad_mask & CGPCM_GRAD_ALPHA) g5[2] = alpha * ga;
+      if (grad_mask & CGPCM_GRAD_GAMMA) g5[3] = gamma * gg;
+      if (grad_mask & CGPCM_GRAD_OMEGA) g5[4] = omega * go;
+    }
+    if (is_device_ptr(grad)) CK(cudaMemcpy(grad, g5, sizeof g5, cudaMemcpyHostToDevice));
+    else memcpy(grad, g5, sizeof g5);
+  }
+  return 0;
+}
+
+}  // namespace cgimpl
+
+extern "C" {
+
+static int fetch_params(cgpcm_handle* h, const double* params, long np, std::vector<double>& host) {
+  host.resize(np);
+  if (is_device_ptr(params)) CK(cudaMemcpy(host.data(), params, np * sizeof(double), cudaMemcpyDeviceToHost));
+  else memcpy(host.data(), params, np * sizeof(double));
+  return 0;
+}
+
+int cgpcm_precompute(cgpcm_handle* h, const double hyp[3], double reg) {
+  if (!h || !hyp) return -1;
+  if (!h->t) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  for (int i = 0; i < 3; ++i)
+    if (!std::isfinite(hyp[i]) || hyp[i] <= 0) { h->err = "hyper-parameters must be positive and finite"; return -4; }
+  if (!std::isfinite(reg) || reg < 0) { h->err = "reg must be finite and >= 0"; return -4; }
+  CK(cudaSetDevice(h->device));
+  double p5[5] = {0.0, 0.0, log(hyp[0]), log(hyp[1]), log(hyp[2])};
+  return evaluate(h, p5, CGPCM_MODE_FULL, 0, reg, true, nullptr, nullptr, nullptr);
+}
+
+int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_t grad_mask, double reg, double* elbo,
+                    double* terms, double* grad) {
+  if (!h || !params || !elbo) return -1;
+  if (mode != CGPCM_MODE_FROZEN && mode != CGPCM_MODE_FULL) { h->err = "bad mode"; return -1; }
+  if (!h->t) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  if (!std::isfinite(reg) || reg < 0) { h->err = "reg must be finite and >= 0"; return -4; }
+  CK(cudaSetDevice(h->device));
+  const long np = 5 + h->nh + (long)h->nh * (h->nh + 1) / 2;
+  std::vector<double> host;
+  if (fetch_params(h, params, np, host)) return -2;
+  double e = 0.0, tm[7];
+  int rc = evaluate(h, host.data(), mode, grad ? grad_mask : 0u, reg, false, &e, tm, grad);
+  if (rc == 0) {
+    float ms[6] = {0, 0, 0, 0, 0, 0};
+    cudaEventElapsedTime(&ms[0], h->ev[0], h->ev[6]);
+    cudaEventElapsedTime(&ms[1], h->ev[1], h->ev[3]);   // forward sweep (Axx + chunks + all-reduce)
+    cudaEventElapsedTime(&ms[2], h->ev[4], h->ev[5]);   // backward sweep
+    cudaEventElapsedTime(&ms[3], h->ev[3], h->ev[4]);   // M x M algebra between the sweeps
+    cudaEventElapsedTime(&ms[4], h->ev[1], h->ev[2]);   // Axx kernels
+    h->timing[0] = ms[0]; h->timing[1] = ms[1]; h->timing[2] = ms[2]; h->timing[3] = ms[3]; h->timing[4] = ms[4];
+    h->timing[5] = ms[1] - ms[4] + ms[2];
+    h->timing[6] = (double)h->launches;
+    h->timing[7] = 0.0;
+    if (is_device_ptr(elbo)) cudaMemcpy(elbo, &e, sizeof e, cudaMemcpyHostToDevice); else *elbo = e;
+    if (terms) { if (is_device_ptr(terms)) cudaMemcpy(terms, tm, sizeof tm, cudaMemcpyHostToDevice); else memcpy(terms, tm, sizeof tm); }
+  }
+  return rc;
+}
+
+int cgpcm_last_timing(cgpcm_handle* h, double out[8]) {
+  if (!h || !out) return -1;
+  memcpy(out, h->timing, sizeof h->timing);
+  return 0;
+}
+
+int cgpcm_bvn_cdf(const double* x1, const double* x2, const double* rho, double* out, size_t n, void* stream) {
+  if (n == 0) return 0;
+  if (!x1 || !x2 || !rho || !out) return -1;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); return -2; }
+  const bool dev = is_device_ptr(x1) && is_device_ptr(x2) && is_device_ptr(rho) && is_device_ptr(out);
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dev) {
+    bvn_cdf_kernel<<<(int)blocks, 256, 0, st>>>(x1, x2, rho, out, n);
+    if (cudaGetLastError() != cudaSuccess) return -2;
+    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -2;
+  }
+  double* d = nullptr;
+  if (cudaMalloc(&d, 4 * n * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return -2; }
+  int rc = 0;
+  if (cudaMemcpyAsync(d, x1, n * sizeof(double), cudaMemcpyDefault, st) != cudaSuccess ||
+      cudaMemcpyAsync(d + n, x2, n * sizeof(double), cudaMemcpyDefault, st) != cudaSuccess ||
+      cudaMemcpyAsync(d + 2 * n, rho, n * sizeof(double), cudaMemcpyDefault, st) != cudaSuccess) rc = -2;
+  if (!rc) {
+    bvn_cdf_kernel<<<(int)blocks, 256, 0, st>>>(d, d + n, d + 2 * n, d + 3 * n, n);
+    if (cudaGetLastError() != cudaSuccess) rc = -2;
+  }
+  if (!rc && cudaMemcpyAsync(out, d + 3 * n, n * sizeof(double), cudaMemcpyDefault, st) != cudaSuccess) rc = -2;
+  if (cudaStreamSynchronize(st) != cudaSuccess) rc = -2;
+  cudaFree(d);
+  return rc;
+}
+
+int cgpcm_dgemm(int a_kc, int b_kc, int c_tr, int M, int N, int K, double alpha, const double* A, int64_t lda,
+                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int splits, int64_t c_split_stride,
+                int lower_only, void* stream) {
+  if (M < 0 || N < 0 || K < 0 || (M % 8) || (N % 8) || (K % 2) || (lda % 2) || (ldb % 2) || (ldc % 2)) return -1;
+  if (!A || !B || !C) return -1;
+  cudaError_t e = dgemm((cudaStream_t)stream, a_kc, b_kc, c_tr, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splits,
+                        c_split_stride, lower_only);
+  if (e != cudaSuccess) return -2;
+  return cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess ? 0 : -2;
+}
+
+int cgpcm_cholinv(double* A, double* Ainv, double* logdet, int n, int64_t ld, int* info_host) {
+  if (!A || n < 1 || ld < n || (ld % 8)) return -1;
+  int np = round_up(n, 8);
+  if (np > ld) return -1;
+  double *X = nullptr, *W = nullptr, *ld_d = nullptr;
+  int* info = nullptr;
+  int rc = 0;
+  if (cudaMalloc(&X, ld * ld * sizeof(double)) != cudaSuccess || cudaMalloc(&W, ld * ld * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&ld_d, sizeof(double)) != cudaSuccess || cudaMalloc(&info, sizeof(int)) != cudaSuccess) rc = -2;
+  if (!rc) {
+    cudaMemset(info, 0, sizeof(int));
+    if (cholinv(nullptr, A, Ainv, X, W, n, np, ld, logdet ? ld_d : nullptr, info, 1) != cudaSuccess) rc = -2;
+    if (cudaDeviceSynchronize() != cudaSuccess) rc = -2;
+    int hi = 0;
+    cudaMemcpy(&hi, info, sizeof(int), cudaMemcpyDeviceToHost);
+    if (info_host) *info_host = hi % 100000;
+    if (logdet) cudaMemcpy(logdet, ld_d, sizeof(double), cudaMemcpyDefault);
+    if (!rc && hi) rc = -3;
+  }
+  if (X) cudaFree(X);
+  if (W) cudaFree(W);
+  if (ld_d) cudaFree(ld_d);
+  if (info) cudaFree(info);
+  return rc;
+}
+
+}  // extern "C"

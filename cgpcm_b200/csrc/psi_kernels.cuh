@@ -1,0 +1,341 @@
+// Interdomain expected-kernel ("Psi") statistics of the CGPCM on sm_100a, FP64.
+//
+// Replaces the reference's symbolic construction (src/core/exponentiated_quadratic.py:430-559 driven
+// by src/core/cgpcm.py:111-203), which materialises N x nx x nx and N x nh x nx broadcast tensors,
+// by closed forms evaluated in registers and reduced over observations on the fly:
+//
+//   axx_sum_kernel   sum_n Axx[n] (+ its three tangents d/d(alpha,gamma,omega), forward mode, App. E):
+//                    one thread per (k,l) pair of the lower triangle, a register loop over the
+//                    observations of its slice, in-register Genz BVN with per-launch tables.
+//   ahx_gen_kernel   A[i][n][k] = Ahx[n,i,k] for a chunk of observations, written in the [i][n][k]
+//                    layout that turns every contraction into a plain GEMM, fused with
+//                    Y[i,k] += sum_n y_n A[i,n,k]  (cgpcm.py:243).
+//   ahx_dot_kernel   sum_{i,n,k} Abar[i,n,k] * dA[i,n,k]/d(alpha,gamma,omega): the adjoint of the
+//                    Ahx construction (replaces tf.gradients through exp/erf).
+//   ahx_user_kernel  Ahx in the reference's [n][i][k] layout (cgpcm.py:239) for parity checks/predict.
+//   ahh_kernel       Ahh[i,j] and tangents; prior kernels Kh, Kx (kernel.py:43-46).
+#pragma once
+#include "bvn.cuh"
+
+namespace cg {
+
+struct PsiConst {
+  double alpha, gamma, omega, A;
+  int causal;
+  // Ahx
+  double pref_hx;      // causal: 0.5 sqrt(pi/A)   acausal: sqrt(pi/A)
+  double e_hh, e_dd, e_hd;
+  double inv_sqrtA, inv_2A;
+  // Axx
+  double pref_xx;      // 2 pi / sqrt(det)
+  double g1, g2, p, q;
+  double dhalf_logdet[3], dg1[3], dg2[3], dp[3], dq[3], drho[3];
+  // Ahh
+  double pref_hh;      // causal: 0.5 sqrt(pi/2B)  acausal: sqrt(pi/2B),  B = alpha + gamma
+  // culling: elements whose Gaussian envelope is below exp(-cull) are exactly 0 (1e300 = never)
+  double cull;
+  double r_xx;         // |t - tx| beyond which every Axx element of that row / column is culled
+};
+
+inline void psi_make_const(double alpha, double gamma, double omega, int causal, double cull, PsiConst* c) {
+  const double PI = 3.14159265358979323846;
+  double A = alpha + gamma + omega;
+  c->alpha = alpha; c->gamma = gamma; c->omega = omega; c->A = A; c->causal = causal;
+  c->pref_hx = (causal ? 0.5 : 1.0) * sqrt(PI / A);
+  c->e_hh = ((alpha + gamma) * A - gamma * gamma) / A;
+  c->e_dd = omega * (alpha + gamma) / A;
+  c->e_hd = 2.0 * gamma * omega / A;
+  c->inv_sqrtA = 1.0 / sqrt(A);
+  c->inv_2A = 0.5 / A;
+  double det = 4.0 * (A * A - gamma * gamma);
+  double ddet[3] = {8.0 * A, 8.0 * A - 8.0 * gamma, 8.0 * A};
+  double S11 = 2.0 * A / det, S12 = 2.0 * gamma / det;
+  double dgam[3] = {0.0, 1.0, 0.0}, dom[3] = {0.0, 0.0, 1.0};
+  double sq = sqrt(S11);
+  c->pref_xx = 2.0 * PI / sqrt(det);
+  c->g1 = omega * (1.0 - 2.0 * omega * S11);
+  c->g2 = 4.0 * omega * omega * S12;
+  c->p = 2.0 * omega * sq;
+  c->q = 2.0 * omega * S12 / sq;
+  for (int i = 0; i < 3; ++i) {
+    double dS11 = 2.0 / det - 2.0 * A * ddet[i] / (det * det);
+    double dS12 = 2.0 * dgam[i] / det - 2.0 * gamma * ddet[i] / (det * det);
+    c->dhalf_logdet[i] = ddet[i] / (2.0 * det);
+    c->dg1[i] = dom[i] * (1.0 - 2.0 * omega * S11) + omega * (-2.0 * dom[i] * S11 - 2.0 * omega * dS11);
+    c->dg2[i] = 8.0 * omega * dom[i] * S12 + 4.0 * omega * omega * dS12;
+    c->dp[i] = 2.0 * dom[i] * sq + omega * dS11 / sq;
+    c->dq[i] = 2.0 * dom[i] * S12 / sq + 2.0 * omega * dS12 / sq - omega * S12 * dS11 / (S11 * sq);
+    c->drho[i] = dgam[i] / A - gamma / (A * A);
+  }
+  c->pref_hh = (causal ? 0.5 : 1.0) * sqrt(PI / (2.0 * (alpha + gamma)));
+  c->cull = cull > 0.0 ? cull : 1e300;
+  // g1 (dk^2 + dl^2) - g2 dk dl >= (g1 - |g2| / 2) (dk^2 + dl^2)
+  double lam = c->g1 - 0.5 * fabs(c->g2);
+  c->r_xx = (cull > 0.0 && lam > 0.0) ? sqrt(cull / lam) : INFINITY;
+}
+
+// Elements whose Gaussian envelope is below exp(-c.cull) (default 80: < 2e-35 of an O(1) prefactor)
+// are set to exactly 0 without evaluating erfc / the BVN: far below one ulp of any sum they enter.
+
+constexpr int AXX_TILE = 16;
+
+// part layout: [slices][4][ld][ld]; slice blockIdx.y owns observations n_lo + blockIdx.y (+ gridDim.y ...)
+// of the tile's observation range and *stores* its lower-triangle partial sums (no zero-init needed).
+// When t is sorted the observation range of a (k, l) tile is cut down by binary search to the
+// observations within r_xx of both the tile's tx_k and tx_l ranges; everything outside is culled anyway.
+template <bool TANGENTS>
+__global__ void __launch_bounds__(256) axx_sum_kernel(const double* __restrict__ t, int n_obs, int sorted,
+                                                      const double* __restrict__ tx, int nx,
+                                                      double* __restrict__ part, long ld, const PsiConst c,
+                                                      const BvnTab T) {
+  // decode lower-triangular tile index
+  int tidx = blockIdx.x;
+  int tk = (int)((sqrt(8.0 * tidx + 1.0) - 1.0) * 0.5);
+  while ((tk + 1) * (tk + 2) / 2 <= tidx) ++tk;
+  while (tk * (tk + 1) / 2 > tidx) --tk;
+  int tl = tidx - tk * (tk + 1) / 2;
+  const int k0 = tk * AXX_TILE, l0 = tl * AXX_TILE;
+  const int k = k0 + (threadIdx.x >> 4);
+  const int l = l0 + (threadIdx.x & 15);
+  if (k >= nx || l >= nx || l > k) return;
+  int n_lo = 0, n_hi = n_obs;
+  if (sorted && c.r_xx < 1e300) {
+    double kmin = tx[k0], kmax = kmin, lmin = tx[l0], lmax = lmin;
+    for (int j = 1; j < AXX_TILE; ++j) {
+      if (k0 + j < nx) { double v = tx[k0 + j]; kmin = fmin(kmin, v); kmax = fmax(kmax, v); }
+      if (l0 + j < nx) { double v = tx[l0 + j]; lmin = fmin(lmin, v); lmax = fmax(lmax, v); }
+    }
+    const double lo = fmax(kmin, lmin) - c.r_xx, hi = fmin(kmax, lmax) + c.r_xx;
+    int a = 0, b = n_obs;                       // first n with t[n] >= lo
+    while (a < b) { int m = (a + b) >> 1; if (__ldg(t + m) < lo) a = m + 1; else b = m; }
+    n_lo = a;
+    b = n_obs;                                  // first n with t[n] > hi
+    while (a < b) { int m = (a + b) >> 1; if (__ldg(t + m) <= hi) a = m + 1; else b = m; }
+    n_hi = a;
+  }
+  const double txk = tx[k], txl = tx[l];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int n = n_lo + blockIdx.y; n < n_hi; n += gridDim.y) {
+    const double tn = __ldg(t + n);
+    const double dk = tn - txk, dl = tn - txl;
+    const double q2 = dk * dk + dl * dl, pr = dk * dl;
+    const double G = -c.g1 * q2 + c.g2 * pr;
+    if (G < -c.cull) continue;
+    const double env = c.pref_xx * exp(G);
+    if (!c.causal) {
+      s0 += env;
+      if (TANGENTS) {
+        s1 += env * (-c.dg1[0] * q2 + c.dg2[0] * pr - c.dhalf_logdet[0]);
+        s2 += env * (-c.dg1[1] * q2 + c.dg2[1] * pr - c.dhalf_logdet[1]);
+        s3 += env * (-c.dg1[2] * q2 + c.dg2[2] * pr - c.dhalf_logdet[2]);
+      }
+      continue;
+    }
+    const double x1 = c.p * dk + c.q * dl, x2 = c.q * dk + c.p * dl;
+    if (!TANGENTS) {
+      s0 += env * bvnd_tab(-x1, -x2, T);
+    } else {
+      double cdf, d1, d2, dr;
+      bvn_cdf_grad_tab(x1, x2, T, cdf, d1, d2, dr);
+      const double V = env * cdf;
+      s0 += V;
+      s1 += V * (-c.dg1[0] * q2 + c.dg2[0] * pr - c.dhalf_logdet[0]) +
+            env * (d1 * (c.dp[0] * dk + c.dq[0] * dl) + d2 * (c.dq[0] * dk + c.dp[0] * dl) + dr * c.drho[0]);
+      s2 += V * (-c.dg1[1] * q2 + c.dg2[1] * pr - c.dhalf_logdet[1]) +
+            env * (d1 * (c.dp[1] * dk + c.dq[1] * dl) + d2 * (c.dq[1] * dk + c.dp[1] * dl) + dr * c.drho[1]);
+      s3 += V * (-c.dg1[2] * q2 + c.dg2[2] * pr - c.dhalf_logdet[2]) +
+            env * (d1 * (c.dp[2] * dk + c.dq[2] * dl) + d2 * (c.dq[2] * dk + c.dp[2] * dl) + dr * c.drho[2]);
+    }
+  }
+  const long mat = ld * ld;
+  double* o = part + (long)blockIdx.y * 4 * mat + (long)k * ld + l;
+  o[0] = s0;
+  if (TANGENTS) { o[mat] = s1; o[2 * mat] = s2; o[3 * mat] = s3; }
+}
+
+// Per-observation Axx in the reference's [n][k][l] layout (parity / predict use).
+__global__ void axx_user_kernel(const double* __restrict__ t, int n_obs, const double* __restrict__ tx,
+                                int nx, double* __restrict__ out, const PsiConst c, const BvnTab T) {
+  long total = (long)n_obs * nx * nx;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int l = (int)(idx % nx);
+    int k = (int)((idx / nx) % nx);
+    int n = (int)(idx / ((long)nx * nx));
+    double dk = t[n] - tx[k], dl = t[n] - tx[l];
+    double G = -c.g1 * (dk * dk + dl * dl) + c.g2 * dk * dl;
+    double v = 0.0;
+    if (G >= -c.cull) {
+      v = c.pref_xx * exp(G);
+      if (c.causal) v *= bvnd_tab(-(c.p * dk + c.q * dl), -(c.q * dk + c.p * dl), T);
+    }
+    out[idx] = v;
+  }
+}
+
+__device__ __forceinline__ double ahx_value(double th, double d, const PsiConst& c) {
+  const double E = -c.e_hh * th * th - c.e_dd * d * d + c.e_hd * th * d;
+  if (E < -c.cull) return 0.0;
+  double v = c.pref_hx * exp(E);
+  if (c.causal) v *= erfc(-(c.gamma * th + c.omega * d) * c.inv_sqrtA);
+  return v;
+}
+
+constexpr int AHX_NSUB = 32;
+
+// A[(i*nc + n)*kwp + k] for i < nhp, n < nc, k < kwp (zero outside the valid nh x n_valid x nx box).
+// Ypart[blockIdx.y][i][k_lo + k] += sum_n y_n A   (slice-private accumulation, reduced later).
+__global__ void __launch_bounds__(256) ahx_gen_kernel(const double* __restrict__ t, const double* __restrict__ y,
+                                                      int n_valid, int nc, const double* __restrict__ th, int nh,
+                                                      const double* __restrict__ tx, int nx, int k_lo, int kwp,
+                                                      double* __restrict__ A, double* __restrict__ Ypart,
+                                                      long ldy, long ypart_stride, const PsiConst c) {
+  const int i = blockIdx.x;
+  const int n0 = blockIdx.y * AHX_NSUB;
+  const int n1 = min(nc, n0 + AHX_NSUB);
+  const bool row_ok = i < nh;
+  const double thi = row_ok ? th[i] : 0.0;
+  for (int k = threadIdx.x; k < kwp; k += blockDim.x) {
+    const int kg = k_lo + k;
+    const bool ok = row_ok && kg < nx;
+    const double txk = ok ? tx[kg] : 0.0;
+    double ysum = 0.0;
+    double* dst = A + ((long)i * nc + n0) * kwp + k;
+    for (int n = n0; n < n1; ++n, dst += kwp) {
+      double v = 0.0;
+      if (ok && n < n_valid) {
+        v = ahx_value(thi, __ldg(t + n) - txk, c);
+        ysum += __ldg(y + n) * v;
+      }
+      *dst = v;
+    }
+    if (ok && Ypart) Ypart[(long)blockIdx.y * ypart_stride + (long)i * ldy + kg] += ysum;
+  }
+}
+
+// gpart[(blockIdx.y * gridDim.x + blockIdx.x) * 3 + theta] += sum over the block's elements of
+//   (W[i][n][k] + y_n * Ybar[i][k_lo + k]) * dA[i,n,k]/dtheta.
+__global__ void __launch_bounds__(256) ahx_dot_kernel(const double* __restrict__ t, const double* __restrict__ y,
+                                                      int n_valid, int nc, const double* __restrict__ th, int nh,
+                                                      const double* __restrict__ tx, int nx, int k_lo, int kwp,
+                                                      const double* __restrict__ W, const double* __restrict__ Ybar,
+                                                      long ldy, double* __restrict__ gpart, const PsiConst c) {
+  const int i = blockIdx.x;
+  const int n0 = blockIdx.y * AHX_NSUB;
+  const int n1 = min(n_valid, n0 + AHX_NSUB);
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+  if (i < nh) {
+    const double thi = th[i];
+    for (int k = threadIdx.x; k < kwp; k += blockDim.x) {
+      const int kg = k_lo + k;
+      if (kg >= nx) continue;
+      const double txk = tx[kg];
+      const double yb = Ybar[(long)i * ldy + kg];
+      const double* src = W + ((long)i * nc + n0) * kwp + k;
+      for (int n = n0; n < n1; ++n, src += kwp) {
+        const double d = __ldg(t + n) - txk;
+        const double E = -c.e_hh * thi * thi - c.e_dd * d * d + c.e_hd * thi * d;
+        if (E < -c.cull) continue;
+        const double w = *src + __ldg(y + n) * yb;
+        const double bh = -(c.gamma * thi + c.omega * d);    // b / 2
+        const double u = bh * 2.0 * c.inv_2A;                // b / (2A)
+        const double z = bh * c.inv_sqrtA;
+        const double eE = exp(E);
+        double F, X;
+        if (c.causal) {
+          F = c.pref_hx * eE * erfc(z);
+          X = exp(E - z * z) * c.inv_sqrtA;
+        } else {
+          F = c.pref_hx * eE;
+          X = 0.0;
+        }
+        const double zc = z * c.inv_2A;
+        const double da = F * (-thi * thi - u * u - c.inv_2A) + X * zc;
+        const double dg = F * (-(thi + u) * (thi + u) - c.inv_2A) + X * (thi * c.inv_sqrtA + zc);
+        const double dw = F * (-(d + u) * (d + u) - c.inv_2A) + X * (d * c.inv_sqrtA + zc);
+        g0 += w * da; g1 += w * dg; g2 += w * dw;
+      }
+    }
+  }
+  // block reduction (deterministic)
+  __shared__ double sh[3][8];
+  for (int off = 16; off > 0; off >>= 1) {
+    g0 += __shfl_down_sync(0xffffffffu, g0, off);
+    g1 += __shfl_down_sync(0xffffffffu, g1, off);
+    g2 += __shfl_down_sync(0xffffffffu, g2, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][warp] = g0; sh[1][warp] = g1; sh[2][warp] = g2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int w = 0; w < nw; ++w) { a0 += sh[0][w]; a1 += sh[1][w]; a2 += sh[2][w]; }
+    double* o = gpart + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 3;
+    o[0] += a0; o[1] += a1; o[2] += a2;
+  }
+}
+
+__global__ void ahx_user_kernel(const double* __restrict__ t, int n_obs, const double* __restrict__ th, int nh,
+                                const double* __restrict__ tx, int nx, double* __restrict__ out, const PsiConst c) {
+  long total = (long)n_obs * nh * nx;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int k = (int)(idx % nx);
+    int i = (int)((idx / nx) % nh);
+    int n = (int)(idx / ((long)nx * nh));
+    out[idx] = ahx_value(th[i], t[n] - tx[k], c);
+  }
+}
+
+// Prior kernels and Ahh on padded ld x ld storage (zero padding).
+// Kh0 = exp(-alpha (ti^2 + tj^2) - gamma (ti - tj)^2); Kx0 = sqrt(pi/2omega) exp(-omega/2 (tk - tl)^2).
+__global__ void prior_kernels_kernel(const double* __restrict__ th, int nh, long ldh, const double* __restrict__ tx,
+                                     int nx, long ldx, double reg, double* __restrict__ Kh0, double* __restrict__ Kh,
+                                     double* __restrict__ Kx0, double* __restrict__ Kx, double* __restrict__ Ahh,
+                                     double* __restrict__ dAhh_a, double* __restrict__ dAhh_g, const PsiConst c) {
+  const long nh2 = ldh * ldh, nx2 = ldx * ldx;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < nh2 + nx2; idx += (long)gridDim.x * blockDim.x) {
+    if (idx < nh2) {
+      int i = (int)(idx / ldh), j = (int)(idx % ldh);
+      double k0 = 0.0, ahh = 0.0, da = 0.0, dg = 0.0;
+      if (i < nh && j < nh) {
+        double ti = th[i], tj = th[j];
+        double q2 = ti * ti + tj * tj, s = ti + tj;
+        k0 = exp(-c.alpha * q2 - c.gamma * (ti - tj) * (ti - tj));
+        // Ahh: D = 2B, b = -2 gamma s, cc = -B q2, E = cc + b^2/(4D), z = b / (2 sqrt D)
+        double B = c.alpha + c.gamma, D = 2.0 * B;
+        double b = -2.0 * c.gamma * s;
+        double E = -B * q2 + b * b / (4.0 * D);
+        double isd = 1.0 / sqrt(D);
+        double z = 0.5 * b * isd;
+        double u = b / (2.0 * D);
+        double eE = exp(E);
+        double F, X;
+        if (c.causal) { F = c.pref_hh * eE * erfc(z); X = exp(E - z * z) * isd; }
+        else { F = c.pref_hh * eE; X = 0.0; }
+        ahh = F;
+        // tangents: D_theta = 2; alpha: b_t = 0, c_t = -q2 ; gamma: b_t = -2 s, c_t = -q2
+        double Ea = -q2 - 2.0 * u * u, Eg = -q2 - 2.0 * u * s - 2.0 * u * u;
+        double za = -z / D, zg = -s * isd - z / D;
+        da = F * (Ea - 1.0 / D) - X * za;
+        dg = F * (Eg - 1.0 / D) - X * zg;
+      }
+      Kh0[idx] = k0;
+      Kh[idx] = k0 + ((i == j && i < nh) ? reg : 0.0);
+      Ahh[idx] = ahh;
+      dAhh_a[idx] = da;
+      dAhh_g[idx] = dg;
+    } else {
+      long id2 = idx - nh2;
+      int k = (int)(id2 / ldx), l = (int)(id2 % ldx);
+      double k0 = 0.0;
+      if (k < nx && l < nx) {
+        double d = tx[k] - tx[l];
+        k0 = sqrt(1.5707963267948966 / c.omega) * exp(-0.5 * c.omega * d * d);
+      }
+      Kx0[id2] = k0;
+      Kx[id2] = k0 + ((k == l && k < nx) ? reg : 0.0);
+    }
+  }
+}
+
+}  // namespace cg

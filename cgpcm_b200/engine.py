@@ -1,0 +1,134 @@
+"""Thin object wrapper over the C-ABI handle: one ``Engine`` = one GPU + one stream.
+
+Every method is a single call into ``libcgpcm_b200.so``; numpy arrays / torch tensors are only
+containers for the bytes that cross the boundary.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import (GRAD_ALL, GRAD_ALPHA, GRAD_GAMMA, GRAD_MU_U, GRAD_OMEGA, GRAD_S2, GRAD_S2F, GRAD_VAR_U,
+                   MODE_FROZEN, MODE_FULL)
+
+TERM_NAMES = ['s2 complexity', 'p(z) complexity', 'q*(z) complexity', 'q*(z) fit',
+              'general conditioning penalty', 'q(u) conditioning penalty', '-KL[q(u)||p(u)]']
+
+
+def n_params(nh):
+    return 5 + nh + nh * (nh + 1) // 2
+
+
+class Engine(object):
+    def __init__(self, nh, nx, causal=True, causal_id=False, device=0):
+        self.nh, self.nx = int(nh), int(nx)
+        self.device = int(device)
+        self._h = ctypes.c_void_p()
+        L = _lib.lib()
+        rc = L.cgpcm_create(ctypes.byref(self._h), self.device, self.nh, self.nx, int(bool(causal)),
+                            int(bool(causal_id)), None)
+        if rc != 0:
+            self._h = ctypes.c_void_p()
+            if rc == -2:
+                raise _lib.CgpcmError(rc, 'no usable CUDA device %d (cgpcm_b200 has no CPU fallback)' % self.device)
+            _lib.check(rc)
+        self.n_local = 0
+        self.rank, self.world = 0, 1
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, '_h', None) and self._h.value:
+            _lib.lib().cgpcm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _lib.check(rc, self._h)
+
+    # -- configuration
+    def set_option(self, key, value):
+        self._ck(_lib.lib().cgpcm_set_option(self._h, key.encode(), float(value)))
+
+    def comm_init(self, unique_id, rank, world):
+        """Join the NCCL communicator described by the 128-byte ``unique_id`` (see ``unique_id()``)."""
+        buf = (ctypes.c_char * 128).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+        self._ck(_lib.lib().cgpcm_comm_init(self._h, buf, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    @staticmethod
+    def unique_id():
+        buf = (ctypes.c_char * 128)()
+        _lib.check(_lib.lib().cgpcm_comm_unique_id(buf))
+        return bytes(buf)
+
+    def set_data(self, t, y, th, tx):
+        """This rank's observations and the inducing inputs (host or device float64 buffers)."""
+        n = int(t.shape[0])
+        if int(y.shape[0]) != n or int(th.shape[0]) != self.nh or int(tx.shape[0]) != self.nx:
+            raise ValueError('shape mismatch in set_data')
+        self._ck(_lib.lib().cgpcm_set_data(self._h, _lib.ptr(t) if n else None, _lib.ptr(y) if n else None, n,
+                                            _lib.ptr(th), _lib.ptr(tx)))
+        self.n_local = n
+
+    # -- compute
+    def psi(self, alpha, gamma, omega, per_observation=False):
+        """Psi statistics (``mats[...]`` of ``src/core/cgpcm.py:235-243``) as numpy arrays."""
+        hyp = np.array([alpha, gamma, omega], dtype=np.float64)
+        out = {'sum_Axx': np.empty((self.nx, self.nx)), 'Ahh': np.empty((self.nh, self.nh)),
+               'a': np.empty(1), 'sum_Ahx_y': np.empty((self.nh, self.nx))}
+        ahx = axx = None
+        if per_observation:
+            ahx = np.empty((self.n_local, self.nh, self.nx))
+            axx = np.empty((self.n_local, self.nx, self.nx))
+        self._ck(_lib.lib().cgpcm_psi(self._h, _lib.ptr(hyp), _lib.ptr(out['sum_Axx']), _lib.ptr(out['Ahh']),
+                                       _lib.ptr(out['a']), _lib.ptr(out['sum_Ahx_y']), _lib.ptr(ahx), _lib.ptr(axx)))
+        out['a'] = float(out['a'][0])
+        if per_observation:
+            out['Ahx'], out['Axx'] = ahx, axx
+        return out
+
+    def precompute(self, alpha, gamma, omega, reg):
+        hyp = np.array([alpha, gamma, omega], dtype=np.float64)
+        self._ck(_lib.lib().cgpcm_precompute(self._h, _lib.ptr(hyp), float(reg)))
+
+    def elbo_grad(self, params, mode=MODE_FULL, grad_mask=GRAD_ALL, reg=1e-8, want_grad=True, out_grad=None):
+        """(elbo, terms[7], grad or None).  ``params``: host numpy (pinned torch also fine) or CUDA tensor."""
+        if int(params.shape[0]) != n_params(self.nh):
+            raise ValueError('params must have length %d' % n_params(self.nh))
+        elbo = np.empty(1)
+        terms = np.empty(7)
+        grad = None
+        if want_grad:
+            grad = out_grad if out_grad is not None else np.empty(n_params(self.nh))
+        self._ck(_lib.lib().cgpcm_elbo_grad(self._h, _lib.ptr(params), int(mode), int(grad_mask), float(reg),
+                                             _lib.ptr(elbo), _lib.ptr(terms), _lib.ptr(grad)))
+        return float(elbo[0]), terms, grad
+
+    def last_timing(self):
+        t = np.zeros(8)
+        self._ck(_lib.lib().cgpcm_last_timing(self._h, _lib.ptr(t)))
+        return dict(total_ms=t[0], forward_ms=t[1], backward_ms=t[2], algebra_ms=t[3], axx_ms=t[4],
+                    contraction_ms=t[5], launches=int(t[6]))
+
+
+def bvn_cdf(x1, x2, rho):
+    """The reference's native op ``bvn_cdf(x1, x2, rho)`` (``src/core/exponentiated_quadratic.py:552``):
+    element-wise on three equal-length float64 vectors (numpy -> numpy, CUDA tensor -> CUDA tensor)."""
+    if isinstance(x1, np.ndarray):
+        x1, x2, rho = [np.ascontiguousarray(v, dtype=np.float64).ravel() for v in (x1, x2, rho)]
+        if not (x1.shape == x2.shape == rho.shape):
+            raise ValueError('x1, x2, rho must have equal length')
+        out = np.empty_like(x1)
+    else:
+        import torch
+        if not (x1.shape == x2.shape == rho.shape) or x1.dim() != 1:
+            raise ValueError('x1, x2, rho must be rank-1 and of equal length')
+        out = torch.empty_like(x1)
+    _lib.check(_lib.lib().cgpcm_bvn_cdf(_lib.ptr(x1), _lib.ptr(x2), _lib.ptr(rho), _lib.ptr(out), int(x1.shape[0]),
+                                         None))
+    return out

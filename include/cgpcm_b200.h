@@ -1,0 +1,108 @@
+/* cgpcm_b200 — C-ABI of the B200-native VCGPCM hot path (libcgpcm_b200.so).
+ *
+ * Drop-in boundary for ONE path of wesselb/cgpcm: evaluating the saturated VCGPCM evidence lower
+ * bound and its gradient.  The reference is pure Python + TensorFlow; its only native
+ * FFI on this path is the external custom op `bvn_cdf` (loaded at src/core/tf_util.py:9-13, called at
+ * src/core/exponentiated_quadratic.py:552).  Everything else this header exposes replaces a
+ * `sess.run(...)` of a TF sub-graph; each entry point cites the reference code it stands in for.
+ *
+ * Conventions
+ *   - Plain C types only.  All floating point data is IEEE double.
+ *   - Return value: 0 = success, -1 = bad argument, -2 = CUDA / NCCL error, -3 = a matrix was not
+ *     positive definite (which one: cgpcm_last_error), -4 = non-finite input.  No exceptions.
+ *   - Every pointer argument may be a CUDA device pointer or a host pointer unless stated otherwise
+ *     (resolved with cudaPointerGetAttributes); host buffers are copied inside the call.
+ *   - Calls are host-synchronous: they return after the handle's stream has drained.
+ *   - A handle owns one device, one stream and all scratch memory; it is not thread-safe; different
+ *     handles are independent (one per GPU / per restart).
+ *   - There is no CPU fallback: without a CUDA device cgpcm_create fails with -2.
+ *
+ * Parameter vector (all unconstrained, exactly the reference's TF variables:
+ * var_pos logs src/core/tf_util.py:323-332, mu_u / var_u src/core/cgpcm.py:435-445, packing of
+ * var_u = np.tril_indices order src/core/tf_util.py:419-447):
+ *     params = [log s2, log s2_f, log alpha, log gamma, log omega, mu_u[nh], var_u[nh(nh+1)/2]]
+ * Gradients are with respect to this vector (so d/dlog theta for the five positives).
+ */
+#ifndef CGPCM_B200_H
+#define CGPCM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgpcm_handle cgpcm_handle;
+
+/* grad_mask bits: which entries of the gradient are wanted (others are returned as 0). */
+#define CGPCM_GRAD_S2     (1u << 0)
+#define CGPCM_GRAD_S2F    (1u << 1)
+#define CGPCM_GRAD_ALPHA  (1u << 2)
+#define CGPCM_GRAD_GAMMA  (1u << 3)
+#define CGPCM_GRAD_OMEGA  (1u << 4)
+#define CGPCM_GRAD_MU_U   (1u << 5)
+#define CGPCM_GRAD_VAR_U  (1u << 6)
+#define CGPCM_GRAD_ALL    0x7fu
+
+/* Evaluation regimes (src/core/cgpcm.py:270-292, src/core/experiment.py:217-250). */
+#define CGPCM_MODE_FROZEN 0  /* "precomputed": Psi statistics frozen by cgpcm_precompute            */
+#define CGPCM_MODE_FULL   1  /* Psi statistics rebuilt and differentiated every evaluation            */
+
+/* Model construction: the state VCGPCM.__init__ builds (src/core/cgpcm.py:24-30,430-433).
+ * nccl_comm: an existing ncclComm_t to reduce over, or NULL (single GPU, or use cgpcm_comm_init). */
+int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int causal_id, void* nccl_comm);
+int cgpcm_destroy(cgpcm_handle* h);
+const char* cgpcm_last_error(const cgpcm_handle* h);
+
+/* Multi-GPU: rank 0 makes a 128-byte NCCL unique id, every rank joins with it (one process per GPU).
+ * After this, the sums over observations (src/core/cgpcm.py:240-267,473-475) are all-reduced. */
+int cgpcm_comm_unique_id(void* id128);
+int cgpcm_comm_init(cgpcm_handle* h, const void* id128, int rank, int world);
+
+/* This rank's slice of the observations e.x, e.y (src/core/cgpcm.py:208-212) and the inducing inputs
+ * th, tx (src/core/cgpcm.py:72-95). */
+int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_local, const double* th,
+                   const double* tx);
+
+/* Tuning knobs: "chunk" (observations per contraction chunk), "cull" (0 = dense; e > 0 = skip inducing
+ * inputs whose Psi entries are provably below exp(-e) for the whole chunk). */
+int cgpcm_set_option(cgpcm_handle* h, const char* key, double value);
+
+/* Psi statistics at hyper-parameters hyp = {alpha, gamma, omega}: what `sess.run(mats[...])` returns
+ * for 'sum_Axx' [nx*nx], 'Ahh' [nh*nh], 'a' [1], 'sum_Ahx_y' [nh*nx] and optionally 'Ahx'
+ * [n_local*nh*nx] and 'Axx' [n_local*nx*nx] (src/core/cgpcm.py:235-243).  Any output may be NULL.
+ * sum_* are summed over all ranks. */
+int cgpcm_psi(cgpcm_handle* h, const double hyp[3], double* sum_Axx, double* Ahh, double* a, double* sum_Ahx_y,
+              double* Ahx, double* Axx);
+
+/* mod.precompute() (src/core/cgpcm.py:270-284): freeze the Psi statistics at hyp for MODE_FROZEN. */
+int cgpcm_precompute(cgpcm_handle* h, const double hyp[3], double reg);
+
+/* One `sess.run([elbo, grad] + terms)` (src/core/cgpcm.py:518-575 through
+ * src/core/learn.py:102-133): ELBO, its 7 terms and the gradient w.r.t. params.
+ * reg = config.reg (src/config.py:3).  elbo[1], terms[7], grad[5 + nh + nh(nh+1)/2]; grad may be NULL. */
+int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_t grad_mask, double reg,
+                    double* elbo, double* terms, double* grad);
+
+/* Timing of the last cgpcm_elbo_grad / cgpcm_psi on the handle's stream (CUDA events, ms):
+ * out[0] total device time, out[1] forward sweep, out[2] backward sweep, out[3] M x M algebra,
+ * out[4] Axx kernels, out[5] contraction GEMMs, out[6] number of kernel launches. */
+int cgpcm_last_timing(cgpcm_handle* h, double out[8]);
+
+/* The reference's native op: Phi_2(x1, x2; rho) element-wise on three FP64 vectors of length n
+ * (src/core/exponentiated_quadratic.py:547-552).  stream: a cudaStream_t or NULL. */
+int cgpcm_bvn_cdf(const double* x1, const double* x2, const double* rho, double* out, size_t n, void* stream);
+
+/* Building blocks exported for tests and micro-benchmarks (device pointers only).
+ * cgpcm_dgemm: C = alpha op(A) op(B) + beta C on the DMMA kernel; a_kc/b_kc/c_tr as in dgemm_dmma.cuh.
+ * cgpcm_cholinv: A (n x n, ld) -> L in place, Ainv, logdet (each may be NULL). */
+int cgpcm_dgemm(int a_kc, int b_kc, int c_tr, int M, int N, int K, double alpha, const double* A, int64_t lda,
+                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int splits,
+                int64_t c_split_stride, int lower_only, void* stream);
+int cgpcm_cholinv(double* A, double* Ainv, double* logdet, int n, int64_t ld, int* info_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,77 @@
+"""Synthetic inputs of the named configurations at sizes the oracle finishes in seconds.
+Shared by the CPU oracle tests, the GPU parity tests and tools/make_golden.py."""
+import numpy as np
+
+from oracle import model as om
+
+
+def _unit(y):
+    return (y - y.mean()) / y.std()
+
+
+def make_case(name, seed=0, n=None):
+    """dict(t, y, th, tx, hyp (alpha, gamma, omega), s2, s2_f, reg, causal)."""
+    rng = np.random.default_rng(seed)
+    causal = True
+    if name == 'toy_test':          # src/tasks/toy.py:25-55, 'test' option
+        n = n or 150
+        t = np.linspace(0, 1, n)
+        rec = om.recipe(t, nx=60, nh=41, tau_w=.1, tau_f=.05, causal=True)
+        y, reg = _unit(rng.standard_normal(n)), 1e-6
+    elif name == 'toy_small':       # a shrunken toy for finite differences
+        n = n or 40
+        t = np.linspace(0, 1, n)
+        rec = om.recipe(t, nx=18, nh=11, tau_w=.1, tau_f=.05, causal=True)
+        y, reg = _unit(rng.standard_normal(n)), 1e-6
+    elif name == 'toy_acausal_model':
+        n = n or 60
+        t = np.linspace(0, 1, n)
+        rec = om.recipe(t, nx=24, nh=13, tau_w=.1, tau_f=.05, causal=False)
+        y, reg, causal = _unit(rng.standard_normal(n)), 1e-6, False
+    elif name == 'ou':              # src/tasks/ou.py:23-45 (shrunk)
+        n = n or 120
+        t = np.linspace(0, 1, n)
+        rec = om.recipe(t, nx=64, nh=25, tau_w=.15, tau_f=.025, causal=True)
+        K = np.exp(-np.abs(t[:, None] - t[None, :]) / .05)
+        y = _unit(np.linalg.cholesky(K + 1e-10 * np.eye(n)) @ rng.standard_normal(n))
+        reg = 1e-5
+    elif name == 'hrir':            # src/tasks/hrir.py:20-40 (shrunk)
+        n = n or 100
+        t = np.arange(n) / 44100.
+        rec = om.recipe(t, nx=56, nh=31, tau_w=1.5e-3, tau_f=5e-5, causal=True)
+        filt = rng.standard_normal(40) * np.exp(-np.arange(40) / 8.)
+        y = _unit(np.convolve(rng.standard_normal(n + 39), filt, mode='valid'))
+        reg = 1e-8
+    elif name == 'crude':           # src/tasks/crude.py:25-48: uneven time stamps
+        n = n or 90
+        stamps = 2010 + 4 * np.sort(rng.choice(1013, size=n, replace=False)) / 1013.
+        t = stamps
+        rec = om.recipe(t, nx=50, nh=21, tau_w=1., tau_f=.1, causal=True)
+        y = np.cumsum(rng.standard_normal(n))
+        y = _unit(y - np.polyval(np.polyfit(t, y, 1), t))
+        reg = 1e-4
+    elif name == 'sweep':           # scaling sweep shape: rho ~ 0.9+ (high Genz branch), sparse windows
+        n = n or 400
+        t = np.linspace(0, n / 1000., n)
+        rec = om.recipe(t, nx=24, nh=16, tau_w=.1, tau_f=.025, causal=True)
+        w = np.exp(-40 * np.linspace(-.3, .3, 61) ** 2)
+        y = _unit(np.convolve(rng.standard_normal(n + 60), w, mode='valid'))
+        reg = 1e-6
+    elif name == 'sweep_wide':      # long series, few inducing inputs per unit time -> narrow windows
+        n = n or 3000
+        t = np.linspace(0, n / 100., n)
+        rec = om.recipe(t, nx=40, nh=12, tau_w=.1, tau_f=.025, causal=True)
+        y, reg = _unit(rng.standard_normal(n)), 1e-6
+    else:
+        raise KeyError(name)
+    hyp = (rec['alpha'], rec['gamma'], rec['omega'])
+    mu_u, var_u = om.init_q(rec['th'], rec['alpha'], rec['gamma'], reg, rng)
+    # move q(u) off the prior so that every gradient entry is exercised
+    var_u = var_u * (1 + .1 * rng.standard_normal(var_u.shape[0]))
+    s2 = 0.3 if name != 'hrir' else 0.05
+    params = om.pack(s2, rec['s2_f'], hyp[0], hyp[1], hyp[2], mu_u, var_u)
+    return dict(name=name, t=np.ascontiguousarray(t), y=np.ascontiguousarray(y), th=rec['th'], tx=rec['tx'],
+                hyp=hyp, reg=reg, causal=causal, params=params, nh=len(rec['th']), nx=len(rec['tx']))
+
+
+CASES = ['toy_test', 'toy_small', 'toy_acausal_model', 'ou', 'hrir', 'crude', 'sweep']

@@ -1,0 +1,56 @@
+"""The reference-facing Python API on the GPU: the training schedule of src/core/experiment.py:209-250
+(precompute -> L-BFGS on q(u) -> + noise -> undo_precompute -> + hyper-parameters) runs unchanged, and
+the ELBO it reaches is the oracle's ELBO at the same variables."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+import cgpcm_b200
+from cgpcm_b200 import VCGPCM, Data, Session, config, learn
+from oracle import model as om
+
+
+def test_train_schedule_toy():
+    config.reg = 1e-6
+    np.random.seed(1005)
+    rng = np.random.default_rng(1005)
+    n = 120
+    t = np.linspace(0, 1, n)
+    w = np.exp(-300 * np.linspace(-.2, .2, 41) ** 2)
+    y = np.convolve(rng.standard_normal(n + 40), w, mode='valid')
+    y = (y - y.mean()) / y.std()
+    sess = Session()
+    mod = VCGPCM.from_recipe(sess, Data(t, y), nx=40, nh=21, tau_w=.1, tau_f=.05, causal=True, noise_init=1e-2)
+    mod.precompute()
+    elbo, terms = mod.elbo()
+    e_start = sess.run(elbo)
+    fetches = [{'name': 'ELBO', 'tensor': elbo, 'modifier': '.2e'},
+               {'name': 's2', 'tensor': mod.s2, 'modifier': '.2e'}]
+    learn.minimise_lbfgs(sess, -elbo, vars=[mod.vars['mu_u'], mod.vars['var_u']], iters=30,
+                         fetches_config=fetches + terms, name='pretraining using L-BFGS', quiet=True)
+    e_pre = sess.run(elbo)
+    learn.minimise_lbfgs(sess, -elbo, vars=[mod.vars['mu_u'], mod.vars['var_u'], mod.vars['s2_f'], mod.vars['s2']],
+                         iters=40, fetches_config=fetches + terms, name='training using L-BFGS', quiet=True)
+    e_main = sess.run(elbo)
+    mod.undo_precompute()
+    elbo, terms = mod.elbo()
+    assert sess.run(elbo) == pytest.approx(e_main, rel=1e-9)      # frozen == full at the freeze point
+    learn.minimise_lbfgs(sess, -elbo, vars=[mod.vars[k] for k in ['mu_u', 'var_u', 's2_f', 's2', 'gamma', 'omega',
+                                                                   'alpha']],
+                         iters=15, fetches_config=fetches + terms, name='posttraining using L-BFGS', quiet=True)
+    e_post = sess.run(elbo)
+    assert e_start < e_pre <= e_main + 1e-9 and e_main <= e_post + 1e-9
+    assert sum(sess.run([tm['tensor'] for tm in terms])) == pytest.approx(e_post, rel=1e-12)
+    # the oracle agrees at the trained variables
+    p = mod._pack()
+    om.PW_DISTS_EXACT = True
+    try:
+        want = om.elbo_and_grad(p, t, y, mod.th, mod.tx, config.reg)
+    finally:
+        om.PW_DISTS_EXACT = False
+    assert abs(want[0] - e_post) <= 1e-9 * abs(want[0])
+    mats = mod.mats
+    assert mats['sum_Axx'].shape == (40, 40) and mats['Ahh'].shape == (21, 21)
+    config.reg = 1e-8

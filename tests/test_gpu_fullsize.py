@@ -1,0 +1,72 @@
+"""BASELINE.json's full size (N = 1e5 observations, M = 200 inducing points) through size-independent
+properties — the oracle cannot run there:
+  * additivity: Psi sums of two half series add up to those of the whole series (the sharding identity),
+  * dense and culled evaluation agree,
+  * the analytic gradient matches central differences of the GPU ELBO along random directions,
+  * symmetry of sum_Axx, and sum of the 7 terms == ELBO."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+import cgpcm_b200
+from tests.workload import sweep_workload
+
+N, M = 100000, 200
+
+
+@pytest.fixture(scope='module')
+def wl():
+    return sweep_workload(N, M, seed=0)
+
+
+@pytest.fixture(scope='module')
+def eng(wl):
+    e = cgpcm_b200.Engine(M, M)
+    e.set_data(wl['t'], wl['y'], wl['th'], wl['tx'])
+    return e
+
+
+def test_psi_additivity_over_shards(wl, eng):
+    whole = eng.psi(*wl['hyp'])
+    half = N // 2
+    parts = []
+    for sl in [slice(0, half), slice(half, N)]:
+        e2 = cgpcm_b200.Engine(M, M)
+        e2.set_data(wl['t'][sl], wl['y'][sl], wl['th'], wl['tx'])
+        parts.append(e2.psi(*wl['hyp']))
+        e2.close()
+    for k in ['sum_Axx', 'sum_Ahx_y']:
+        s = parts[0][k] + parts[1][k]
+        assert np.abs(s - whole[k]).max() <= 1e-12 * np.abs(whole[k]).max()
+    np.testing.assert_array_equal(whole['sum_Axx'], whole['sum_Axx'].T)
+
+
+def test_dense_equals_culled_and_terms_sum(wl, eng):
+    eng.set_option('cull', 80.0)
+    culled = eng.elbo_grad(wl['params'], reg=wl['reg'])
+    t_c = eng.last_timing()
+    eng.set_option('cull', 0.0)
+    dense = eng.elbo_grad(wl['params'], reg=wl['reg'])
+    eng.set_option('cull', 80.0)
+    assert abs(dense[0] - culled[0]) <= 1e-11 * abs(dense[0])
+    assert np.abs(dense[2] - culled[2]).max() <= 1e-9 * np.abs(dense[2]).max()
+    assert dense[1].sum() == pytest.approx(dense[0], rel=1e-13)
+    assert t_c['total_ms'] > 0
+
+
+def test_gradient_directional_derivative(wl, eng):
+    rng = np.random.default_rng(3)
+    p = wl['params']
+    e0, _, g = eng.elbo_grad(p, reg=wl['reg'])
+    for k in range(3):
+        d = rng.standard_normal(p.shape[0])
+        d[:5] *= 0.3
+        d /= np.linalg.norm(d)
+        h = 1e-5
+        f1 = eng.elbo_grad(p + h * d, reg=wl['reg'], want_grad=False)[0]
+        f2 = eng.elbo_grad(p - h * d, reg=wl['reg'], want_grad=False)[0]
+        fd = (f1 - f2) / (2 * h)
+        an = float(g @ d)
+        assert abs(fd - an) <= 1e-5 * max(abs(an), np.abs(g).max() * 1e-3), (k, fd, an)

@@ -1,0 +1,118 @@
+"""GPU building blocks through the C-ABI against numpy / the oracle: the stand-alone bvn_cdf op (the
+reference's only native FFI, src/core/exponentiated_quadratic.py:552), the DMMA GEMM and the Cholesky /
+inverse / log-det kernels."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+import cgpcm_b200
+from cgpcm_b200 import _lib
+from oracle import bvn as obvn
+
+RHOS = [0.0, 0.032, 0.122, 0.29, 0.31, 0.422, 0.65, 0.74, 0.76, 0.86, 0.92, 0.93, 0.969, 0.999, -0.5, -0.95]
+
+
+def test_bvn_cdf_matches_oracle_host_buffers():
+    rng = np.random.default_rng(0)
+    n = 4000
+    x1, x2 = rng.uniform(-6, 6, n), rng.uniform(-6, 6, n)
+    rho = rng.choice(RHOS, n)
+    got = cgpcm_b200.bvn_cdf(x1, x2, rho)
+    want = obvn.bvn_cdf(x1, x2, rho)
+    np.testing.assert_allclose(got, want, atol=3e-16, rtol=2e-14)
+
+
+def test_bvn_cdf_device_buffers_and_edge_cases():
+    x1 = torch.tensor([0., 40., -40., 1e-300, 3., -3., 0.], dtype=torch.float64, device='cuda')
+    x2 = torch.tensor([0., 40., 0., -1e-300, -3., 3., 0.], dtype=torch.float64, device='cuda')
+    rho = torch.tensor([.5, .5, .5, .3, .97, -.97, 0.], dtype=torch.float64, device='cuda')
+    got = cgpcm_b200.bvn_cdf(x1, x2, rho).cpu().numpy()
+    want = obvn.bvn_cdf(x1.cpu().numpy(), x2.cpu().numpy(), rho.cpu().numpy())
+    np.testing.assert_allclose(got, want, atol=3e-16, rtol=2e-14)
+    assert got[1] == pytest.approx(1.0, abs=1e-15) and got[2] == 0.0 and got[6] == pytest.approx(.25, abs=1e-16)
+    empty = cgpcm_b200.bvn_cdf(np.zeros(0), np.zeros(0), np.zeros(0))
+    assert empty.shape == (0,)
+    with pytest.raises(ValueError):
+        cgpcm_b200.bvn_cdf(np.zeros(3), np.zeros(2), np.zeros(3))
+
+
+def _dgemm(a_kc, b_kc, c_tr, A, B, C, alpha, beta, splits=1, lower=0):
+    """A: logical M x K, B: logical K x N, C: logical M x N numpy; stored per the layout flags."""
+    M, K = A.shape
+    N = B.shape[1]
+    dev = lambda x: torch.tensor(np.ascontiguousarray(x), dtype=torch.float64, device='cuda')
+    As = dev(A if a_kc else A.T)
+    Bs = dev(B.T if b_kc else B)
+    if splits > 1:
+        Cs = torch.zeros(splits, M, N, dtype=torch.float64, device='cuda')
+        stride = M * N
+    else:
+        Cs = dev(C.T if c_tr else C)
+        stride = 0
+    rc = _lib.lib().cgpcm_dgemm(int(a_kc), int(b_kc), int(c_tr), M, N, K, alpha, As.data_ptr(), As.shape[1],
+                                 Bs.data_ptr(), Bs.shape[1], beta, Cs.data_ptr(), Cs.shape[-1], splits, stride,
+                                 lower, None)
+    assert rc == 0
+    out = Cs.cpu().numpy()
+    if splits > 1:
+        return out.sum(0)
+    return out.T if c_tr else out
+
+
+@pytest.mark.parametrize('a_kc', [0, 1])
+@pytest.mark.parametrize('b_kc', [0, 1])
+@pytest.mark.parametrize('c_tr', [0, 1])
+@pytest.mark.parametrize('shape', [(8, 8, 2), (200, 200, 200), (104, 136, 50), (216, 8, 34), (40, 264, 1026)])
+def test_dgemm_layouts(a_kc, b_kc, c_tr, shape):
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    A, B, C = rng.standard_normal((M, K)), rng.standard_normal((K, N)), rng.standard_normal((M, N))
+    got = _dgemm(a_kc, b_kc, c_tr, A, B, C, 1.25, -0.5)
+    want = 1.25 * A @ B - 0.5 * C
+    np.testing.assert_allclose(got, want, atol=1e-12 * np.sqrt(K) * 10)
+
+
+def test_dgemm_split_k_and_lower_only():
+    rng = np.random.default_rng(5)
+    M, K = 200, 5000
+    A = rng.standard_normal((M, K))
+    got = _dgemm(1, 1, 0, A, A.T.copy(), np.zeros((M, M)), 1.0, 0.0, splits=7)
+    np.testing.assert_allclose(got, A @ A.T, atol=1e-10)
+    low = _dgemm(1, 1, 0, A, A.T.copy(), np.zeros((M, M)), 1.0, 0.0, splits=5, lower=1)
+    np.testing.assert_allclose(np.tril(low), np.tril(A @ A.T), atol=1e-10)
+
+
+@pytest.mark.parametrize('n', [1, 5, 32, 33, 41, 150, 200, 301])
+def test_cholinv(n):
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((n, n + 3))
+    A = X @ X.T + 1e-3 * np.eye(n)
+    ld = (n + 7) // 8 * 8
+    buf = np.zeros((ld, ld))
+    buf[:n, :n] = A
+    dA = torch.tensor(buf, device='cuda')
+    dI = torch.zeros_like(dA)
+    logdet = np.zeros(1)
+    info = ctypes.c_int(0)
+    rc = _lib.lib().cgpcm_cholinv(dA.data_ptr(), dI.data_ptr(), logdet.ctypes.data, n, ld, ctypes.byref(info))
+    assert rc == 0 and info.value == 0
+    L = dA.cpu().numpy()[:n, :n]
+    np.testing.assert_allclose(L, np.linalg.cholesky(A), rtol=1e-9, atol=1e-11)
+    inv = dI.cpu().numpy()[:n, :n]
+    np.testing.assert_allclose(inv @ A, np.eye(n), atol=1e-7)
+    np.testing.assert_allclose(inv, np.linalg.inv(A), rtol=1e-6, atol=1e-8 * np.abs(np.linalg.inv(A)).max())
+    assert logdet[0] == pytest.approx(np.linalg.slogdet(A)[1], rel=1e-12, abs=1e-12)
+
+
+def test_cholinv_reports_non_positive_definite():
+    n, ld = 16, 16
+    A = np.eye(n)
+    A[7, 7] = -1.0
+    dA = torch.tensor(A, device='cuda')
+    info = ctypes.c_int(0)
+    rc = _lib.lib().cgpcm_cholinv(dA.data_ptr(), None, None, n, ld, ctypes.byref(info))
+    assert rc == -3 and info.value == 8

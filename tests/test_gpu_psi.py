@@ -1,0 +1,91 @@
+"""Psi statistics from the CUDA path against the CPU oracle on the named shapes.
+Tolerance: BASELINE.json asks for 1e-10 absolute on the Psi matrices; the tests hold the sums to a
+tighter relative bound and the per-observation tensors to 1e-13 absolute."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+import cgpcm_b200
+from oracle import model as om
+from tests.cases import CASES, make_case
+
+PSI_ATOL = 1e-10     # BASELINE.json: Psi matrices within 1e-10 absolute
+
+
+def _engine(c, **opts):
+    eng = cgpcm_b200.Engine(c['nh'], c['nx'], causal=c['causal'])
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    eng.set_data(c['t'], c['y'], c['th'], c['tx'])
+    return eng
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_psi_against_oracle(name):
+    c = make_case(name)
+    eng = _engine(c)
+    got = eng.psi(*c['hyp'], per_observation=True)
+    a, Ahh, Axx, Ahx = [np.asarray(v) for v in om.psi_closed(c['t'], c['th'], c['tx'], *c['hyp'], causal=c['causal'])]
+    y = c['y']
+    assert got['a'] == pytest.approx(float(a), rel=1e-15)
+    np.testing.assert_allclose(got['Ahh'], Ahh, atol=1e-14, rtol=1e-12)
+    np.testing.assert_allclose(got['Ahx'], Ahx, atol=1e-13, rtol=1e-11)
+    np.testing.assert_allclose(got['Axx'], Axx, atol=1e-13, rtol=1e-11)
+    sum_Axx = Axx.sum(0)
+    sum_Ahx_y = (y[:, None, None] * Ahx).sum(0)
+    assert np.abs(got['sum_Axx'] - sum_Axx).max() < min(PSI_ATOL, 1e-12 * np.abs(sum_Axx).max() + 1e-14)
+    assert np.abs(got['sum_Ahx_y'] - sum_Ahx_y).max() < min(PSI_ATOL, 1e-12 * np.abs(Ahx).sum(0).max() + 1e-14)
+    np.testing.assert_array_equal(got['sum_Axx'], got['sum_Axx'].T)
+
+
+@pytest.mark.parametrize('name', ['toy_small', 'sweep_wide'])
+def test_psi_dense_equals_culled(name):
+    c = make_case(name)
+    dense = _engine(c, cull=0.0).psi(*c['hyp'], per_observation=True)
+    cull = _engine(c, cull=80.0, chunk=64).psi(*c['hyp'], per_observation=True)
+    for k in ['sum_Axx', 'sum_Ahx_y', 'Ahx', 'Axx']:
+        np.testing.assert_allclose(cull[k], dense[k], atol=1e-30 + 1e-13 * np.abs(dense[k]).max(), rtol=0)
+
+
+def test_psi_unsorted_and_duplicate_times():
+    c = make_case('sweep_wide', n=500)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(500)
+    t = np.ascontiguousarray(c['t'][perm])
+    t[:5] = t[5]                                   # duplicates
+    y = np.ascontiguousarray(c['y'][perm])
+    eng = cgpcm_b200.Engine(c['nh'], c['nx'])
+    eng.set_data(t, y, c['th'], c['tx'])
+    got = eng.psi(*c['hyp'])
+    a, Ahh, Axx, Ahx = [np.asarray(v) for v in om.psi_closed(t, c['th'], c['tx'], *c['hyp'])]
+    np.testing.assert_allclose(got['sum_Axx'], Axx.sum(0), atol=1e-12 * np.abs(Axx.sum(0)).max())
+    np.testing.assert_allclose(got['sum_Ahx_y'], (y[:, None, None] * Ahx).sum(0), atol=1e-12 * np.abs(Ahx).sum(0).max())
+
+
+def test_psi_edge_sizes():
+    """nh = nx = 1 and a single observation (tf.squeeze breaks the reference here);
+    an empty shard contributes zeros."""
+    th, tx = np.array([0.05]), np.array([0.3])
+    eng = cgpcm_b200.Engine(1, 1)
+    eng.set_data(np.array([0.4]), np.array([2.0]), th, tx)
+    got = eng.psi(3.0, 5.0, 7.0, per_observation=True)
+    a, Ahh, Axx, Ahx = [np.asarray(v) for v in om.psi_closed(np.array([0.4]), th, tx, 3.0, 5.0, 7.0)]
+    assert got['Axx'][0, 0, 0] == pytest.approx(float(Axx.reshape(-1)[0]), rel=1e-12)
+    assert got['sum_Ahx_y'][0, 0] == pytest.approx(2.0 * float(Ahx.reshape(-1)[0]), rel=1e-12)
+    eng.set_data(np.zeros(0), np.zeros(0), th, tx)
+    got = eng.psi(3.0, 5.0, 7.0)
+    assert got['sum_Axx'][0, 0] == 0.0 and got['sum_Ahx_y'][0, 0] == 0.0
+
+
+def test_psi_rejects_bad_input():
+    eng = cgpcm_b200.Engine(4, 4)
+    th, tx = np.linspace(0, .1, 4), np.linspace(0, 1, 4)
+    with pytest.raises(ValueError):
+        eng.set_data(np.array([0., np.nan]), np.zeros(2), th, tx)
+    eng.set_data(np.array([0., 1.]), np.zeros(2), th, tx)
+    with pytest.raises(ValueError):
+        eng.psi(1.0, -1.0, 1.0)
+    with pytest.raises(ValueError):
+        cgpcm_b200.Engine(4, 4).psi(1.0, 1.0, 1.0)      # set_data not called

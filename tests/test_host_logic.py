@@ -1,0 +1,136 @@
+"""Host-side mirror of the reference API: recipe values, variable packing, sharding, lazy handles."""
+import numpy as np
+import pytest
+
+import cgpcm_b200
+from cgpcm_b200 import cgpcm as cg
+from cgpcm_b200 import util
+from oracle import model as om
+
+
+class _FakeEngine(object):
+    """Stands in for the GPU engine so that the host logic can be exercised without a device."""
+    calls = []
+
+    def __init__(self, nh, nx, **kw):
+        self.nh, self.nx = nh, nx
+
+    def set_data(self, t, y, th, tx):
+        self.t, self.y = t, y
+
+    def precompute(self, *a):
+        _FakeEngine.calls.append(('precompute',) + a)
+
+    def elbo_grad(self, params, mode, grad_mask, reg, want_grad):
+        _FakeEngine.calls.append(('elbo_grad', mode, grad_mask, reg, want_grad))
+        g = np.arange(params.shape[0], dtype=np.float64) if want_grad else None
+        return float(np.sum(params)), np.arange(7.), g
+
+
+@pytest.fixture
+def model(monkeypatch):
+    monkeypatch.setattr(cg, 'Engine', _FakeEngine)
+    _FakeEngine.calls = []
+    np.random.seed(0)
+    t = np.linspace(0, 1, 50)
+    e = cgpcm_b200.Data(t, np.sin(9 * t))
+    return cg.VCGPCM.from_recipe(cgpcm_b200.Session(device=0, rank=0, world=1), e, nx=20, nh=9, tau_w=.1,
+                                 tau_f=.05, causal=True)
+
+
+def test_recipe_matches_oracle_restatement(model):
+    rec = om.recipe(model.e.x, nx=20, nh=9, tau_w=.1, tau_f=.05, causal=True)
+    for k in ['alpha', 'gamma', 'omega', 's2', 's2_f']:
+        assert getattr(model, k).eval() == pytest.approx(rec[k], rel=1e-15)
+        assert float(model.vars[k].value) == pytest.approx(np.log(rec[k]), rel=1e-15)
+    np.testing.assert_array_equal(model.th, rec['th'])
+    np.testing.assert_array_equal(model.tx, rec['tx'])
+
+
+def test_recipe_acausal_forces_odd_nh(monkeypatch):
+    monkeypatch.setattr(cg, 'Engine', _FakeEngine)
+    e = cgpcm_b200.Data(np.linspace(0, 1, 30), np.zeros(30))
+    mod = cg.VCGPCM.from_recipe(cgpcm_b200.Session(device=0, rank=0, world=1), e, nx=10, nh=8, tau_w=.1, tau_f=.05,
+                                causal=False)
+    assert mod.nh == 9 and mod.th[4] == 0.0
+
+
+def test_initial_var_u_is_cholesky_of_prior(model):
+    rec = om.recipe(model.e.x, nx=20, nh=9, tau_w=.1, tau_f=.05, causal=True)
+    _, var_u = om.init_q(rec['th'], rec['alpha'], rec['gamma'], cgpcm_b200.config.reg, np.random.default_rng(0))
+    np.testing.assert_allclose(model.vars['var_u'].value, var_u, rtol=1e-6, atol=1e-8)
+    assert model.vars['mu_u'].value.shape == (9, 1)
+
+
+def test_pack_layout_and_grad_slicing(model):
+    p = model._pack()
+    assert p.shape[0] == cgpcm_b200.n_params(9)
+    assert p[2] == float(model.vars['alpha'].value)
+    np.testing.assert_array_equal(p[5:14], model.vars['mu_u'].value.ravel())
+    g = np.arange(p.shape[0], dtype=np.float64)
+    out = model._slice_grad(g, ['mu_u', 's2', 'var_u', 'omega'])
+    np.testing.assert_array_equal(out, np.concatenate([g[5:14], g[0:1], g[14:], g[4:5]]))
+
+
+def test_elbo_objective_modes_and_masks(model):
+    sess = model.sess
+    elbo, terms = model.elbo()
+    assert [t['name'] for t in terms] == list(cgpcm_b200.TERM_NAMES) and terms[0]['modifier'] == '.2e'
+    v = sess.run(elbo)
+    assert v == pytest.approx(np.sum(model._pack()))
+    assert sess.run(-elbo) == -v
+    assert sess.run([t['tensor'] for t in terms]) == list(range(7))
+    assert _FakeEngine.calls[-1][1] == cgpcm_b200.MODE_FULL
+    model.precompute()
+    assert _FakeEngine.calls[-1][0] == 'precompute'
+    f, g = (-elbo).value_and_grad([model.vars['mu_u'], model.vars['s2']])
+    call = _FakeEngine.calls[-1]
+    assert call[1] == cgpcm_b200.MODE_FROZEN
+    assert call[2] == cgpcm_b200.GRAD_MU_U | cgpcm_b200.GRAD_S2
+    assert f == -v and g.shape == (10,) and g[-1] == -0.0
+    model.undo_precompute()
+    model.sess.run(model.vars['s2'].assign(np.log(.5)))
+    assert model.s2.eval() == pytest.approx(.5)
+    with pytest.raises(ValueError):
+        model.vars['mu_u'].assign(np.zeros(3))
+    with pytest.raises(NotImplementedError):
+        model.elbo(z=False)
+
+
+def test_minimise_lbfgs_drives_objective(model):
+    class Quad(object):
+        def __init__(self, mod):
+            self.mod = mod
+
+        def value_and_grad(self, vs):
+            x = np.concatenate([v.value.ravel() for v in vs])
+            return float(np.sum((x - 1.5) ** 2)), 2 * (x - 1.5)
+
+    res = cgpcm_b200.learn.minimise_lbfgs(model.sess, Quad(model), [model.vars['mu_u'], model.vars['s2']], iters=30,
+                                          quiet=True)
+    np.testing.assert_allclose(model.vars['mu_u'].value, 1.5, atol=1e-5)
+    assert model.vars['mu_u'].value.shape == (9, 1)
+    assert cgpcm_b200.learn.minimise_lbfgs(model.sess, None, [], iters=0) is None
+    assert res.nit <= 28
+
+
+def test_required_parameters():
+    with pytest.raises(RuntimeError, match='must specify'):
+        cg.CGPCM(sess=None)
+
+
+def test_shard_bounds_partition():
+    for n in [0, 1, 7, 100, 100001]:
+        for w in [1, 2, 3, 8]:
+            b = [cg.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_tril_packing_matches_numpy_order():
+    L = np.tril(np.arange(1., 17.).reshape(4, 4))
+    v = util.tril_to_vec(L)
+    np.testing.assert_array_equal(v, L[np.tril_indices(4)])
+    np.testing.assert_array_equal(util.vec_to_tril(v), L)

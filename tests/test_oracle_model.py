@@ -1,0 +1,72 @@
+"""The oracle's closed-form Psi statistics against (i) the reference's own
+integrands pushed through the restated integrate_box on the reference's 6-D layout and (ii) direct
+quadrature; the oracle's gradient against central finite differences."""
+import numpy as np
+import pytest
+import torch
+from scipy import integrate
+
+from oracle import model as om
+from tests.cases import make_case
+
+
+@pytest.mark.parametrize('name', ['toy_small', 'toy_acausal_model', 'sweep'])
+def test_closed_forms_equal_generic_integrals(name):
+    c = make_case(name, n=7)
+    hyp = [torch.tensor(v, dtype=torch.float64) for v in c['hyp']]
+    a0, Ahh0, Axx0, Ahx0 = om.psi_generic(c['t'], c['th'], c['tx'], *hyp, causal=c['causal'])
+    a1, Ahh1, Axx1, Ahx1 = om.psi_closed(c['t'], c['th'], c['tx'], *hyp, causal=c['causal'])
+    assert abs(float(a0) - float(a1)) < 1e-14
+    np.testing.assert_allclose(Ahh0.numpy(), Ahh1.numpy(), atol=1e-14, rtol=1e-12)
+    np.testing.assert_allclose(Axx0.numpy(), Axx1.numpy(), atol=1e-14, rtol=1e-10)
+    np.testing.assert_allclose(Ahx0.numpy(), Ahx1.numpy(), atol=1e-14, rtol=1e-11)
+
+
+def test_closed_forms_equal_quadrature():
+    c = make_case('toy_small', n=5)
+    al, ga, om_ = c['hyp']
+    kh = lambda x, y: np.exp(-al * (x * x + y * y) - ga * (x - y) ** 2)
+    kxs = lambda x, y: np.exp(-om_ * (x - y) ** 2)
+    a, Ahh, Axx, Ahx = [np.asarray(v) for v in om.psi_closed(c['t'], c['th'], c['tx'], *c['hyp'])]
+    t = c['t'][3]
+    i, j, k, l = 4, 6, 9, 11
+    thi, thj, txk, txl = c['th'][i], c['th'][j], c['tx'][k], c['tx'][l]
+    lo = t - 2.0
+    v, _ = integrate.quad(lambda s: kh(t - s, t - s), lo, t, epsabs=1e-15, epsrel=1e-13, limit=400)
+    assert abs(v - float(a)) < 1e-12
+    v, _ = integrate.quad(lambda s: kh(t - s, thi) * kh(thj, t - s), lo, t, epsabs=1e-16, epsrel=1e-13, limit=400)
+    assert abs(v - Ahh[i, j]) < 1e-13
+    v, _ = integrate.quad(lambda s: kh(t - s, thi) * kxs(s, txk), lo, t, epsabs=1e-16, epsrel=1e-13, limit=400)
+    assert abs(v - Ahx[3, i, k]) < 1e-13
+    v, _ = integrate.dblquad(lambda s2, s1: kh(t - s1, t - s2) * kxs(s1, txk) * kxs(txl, s2), lo, t, lo, t,
+                             epsabs=1e-14, epsrel=1e-11)
+    assert abs(v - Axx[3, k, l]) < 1e-11
+
+
+@pytest.mark.parametrize('name', ['toy_small', 'sweep'])
+def test_gradient_against_finite_differences(name):
+    c = make_case(name, n=20)
+    e0, terms, g = om.elbo_and_grad(c['params'], c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'])
+    assert abs(terms.sum() - e0) < 1e-9 * abs(e0)
+    rng = np.random.default_rng(1)
+    idx = list(range(5)) + list(rng.choice(np.arange(5, len(g)), size=6, replace=False))
+    for i in idx:
+        h = 1e-6
+        p1, p2 = c['params'].copy(), c['params'].copy()
+        p1[i] += h
+        p2[i] -= h
+        f1 = om.elbo_and_grad(p1, c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'])[0]
+        f2 = om.elbo_and_grad(p2, c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'])[0]
+        fd = (f1 - f2) / (2 * h)
+        assert abs(fd - g[i]) < 2e-5 * max(1.0, abs(g[i])), (i, fd, g[i])
+
+
+def test_frozen_regime_matches_full_at_freeze_point():
+    c = make_case('toy_small')
+    full = om.elbo_and_grad(c['params'], c['t'], c['y'], c['th'], c['tx'], c['reg'])
+    fr = om.precompute(c['params'], c['t'], c['y'], c['th'], c['tx'], c['reg'])
+    froz = om.elbo_and_grad(c['params'], c['t'], c['y'], c['th'], c['tx'], c['reg'], frozen=fr)
+    assert abs(full[0] - froz[0]) < 1e-10 * abs(full[0])
+    np.testing.assert_allclose(full[2][:2], froz[2][:2], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(full[2][5:], froz[2][5:], rtol=1e-9, atol=1e-8)
+    assert np.all(froz[2][2:5] == 0)
