@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the VCGPCM ELBO + gradient hot path (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+One "step" = one full-regime evaluation (ELBO + gradient w.r.t. every variable, Psi statistics rebuilt
+and differentiated) on the synthetic scaling-sweep series with N = 1e5 observations and nh = nx = 200
+inducing points.  With several ranks the N observations are sharded (strong scaling:
+total work fixed); every rank ends each step with the same ELBO and gradient.
+
+Timing: every step is timed on the device with CUDA events on the library's stream (returned by
+cgpcm_last_timing), L2 is flushed between steps, the per-step maximum over ranks is summed.  `e2e` times the
+same step through the C-ABI with HOST buffers (pinned) by wall clock, including the upload of the
+observations and the variables and the download of ELBO / terms / gradient.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests.workload import sweep_workload  # noqa: E402
+
+METRIC = 'VCGPCM ELBO+grad evals/sec (N=1e5, M=200)'
+UNIT = 'evals/s'
+FP64_PEAK_FALLBACK_TFLOPS = 37.16     # tools/fp64_peaks.cu on this pool's B200 (profiles/fp64_peaks_r01.json)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n', type=int, default=100000)
+    ap.add_argument('--m', type=int, default=200)
+    ap.add_argument('--cull', type=float, default=0.0,
+                    help='headline runs dense (0): every Psi element and GEMM tile is evaluated; the culled '
+                         'evaluation is reported beside it')
+    ap.add_argument('--chunk', type=int, default=512)
+    ap.add_argument('--cpu-sample', type=int, default=300, help='observations in the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        # "under load": samples in the upper half of the observed power range
+        if sm:
+            thr = min(power) + .5 * (max(power) - min(power))
+            load = [s for s, p in zip(sm, power) if p >= thr] or sm
+            return {'sm_mhz': float(np.median(load)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                    'power_w_max': float(max(power)), 'samples': len(sm)}
+        return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_baseline_eval(wl, sample, steps=1, warmup=0):
+    """Times the CPU oracle (numpy / torch-CPU restatement of the reference's algorithm) on the first
+    `sample` observations of the workload; the cost is linear in N, so evals/s at N = sample / N of that."""
+    import torch
+    from oracle import model as om
+    sl = slice(0, sample)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        om.elbo_and_grad(wl['params'], wl['t'][sl], wl['y'][sl], wl['th'], wl['tx'], wl['reg'])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    per_eval_s = float(np.mean(times)) * wl['n'] / sample
+    return {'value': 1.0 / per_eval_s, 'unit': UNIT, 'cores': int(torch.get_num_threads()), 'kind': 'port',
+            'sample': 'oracle (numpy/torch-CPU FP64 restatement of the reference) on the first %d of %d observations, '
+                      'nh=nx=%d, full regime; %.2f s per sample evaluation, scaled linearly to N'
+                      % (sample, wl['n'], wl['nh'], float(np.mean(times))),
+            'seconds_per_sample_eval': float(np.mean(times))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    wl = sweep_workload(args.n, args.m)
+    sample = args.cpu_sample
+    cb = cpu_baseline_eval(wl, sample, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / cb['value'], 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'scaling sweep N=%d, nh=nx=%d, causal VCGPCM, full regime' % (args.n, args.m),
+                       'n': args.n, 'nh': args.m, 'nx': args.m},
+            'cpu_baseline': cb,
+            'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'note': 'the reference itself (Python 2 + TensorFlow 1.x + bvn-cdf) cannot run here; this is the CPU '
+                    'oracle port of its algorithm on %d host threads' % cb['cores']}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def fp64_peak():
+    """Measured FP64 tensor (DMMA) peak: live from tools/fp64_peaks if present, else the committed number."""
+    exe = os.path.join(ROOT, 'tools', 'fp64_peaks')
+    if os.path.exists(exe):
+        try:
+            out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+            d = json.loads(out)
+            return float(d['dmma_m8n8k4_tflops']), 'measured live by tools/fp64_peaks (DMMA m8n8k4 burst)', d
+        except Exception:
+            pass
+    return FP64_PEAK_FALLBACK_TFLOPS, 'tools/fp64_peaks on this pool (profiles/fp64_peaks_r01.json)', None
+
+
+def run_ours(args):
+    import torch
+    import cgpcm_b200
+    from cgpcm_b200.cgpcm import shard_bounds
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torch.distributed.run --nproc-per-node %d' % args.gpus)
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    wl = sweep_workload(args.n, args.m)
+    lo, hi = shard_bounds(args.n, rank, world)
+    eng = cgpcm_b200.Engine(args.m, args.m, causal=True, device=local_rank)
+    if world > 1:
+        box = [cgpcm_b200.Engine.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0], rank, world)
+    eng.set_option('chunk', args.chunk)
+    eng.set_option('cull', args.cull)
+    # pinned host buffers for the e2e leg
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    t_h, y_h = pin(wl['t'][lo:hi]), pin(wl['y'][lo:hi])
+    th_h, tx_h, p_h = pin(wl['th']), pin(wl['tx']), pin(wl['params'])
+    g_h = torch.empty(p_h.shape[0], dtype=torch.float64).pin_memory()
+    eng.set_data(t_h, y_h, th_h, tx_h)
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device='cuda')   # 512 MB > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return eng.elbo_grad(p_h, mode=cgpcm_b200.MODE_FULL, grad_mask=cgpcm_b200.GRAD_ALL, reg=wl['reg'],
+                             out_grad=g_h)
+
+    for _ in range(args.warmup):
+        step()
+    # ---- timed region: K steps, device time per step from CUDA events on the library's stream
+    eng.set_option('profile', 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    dev_ms, gemm_ms, gemm_flops, gemm_launches, launches, axx_ms = [], 0.0, 0.0, 0, 0, 0.0
+    last = None
+    for _ in range(args.steps):
+        flush.zero_()                      # L2 flush between timed iterations (not inside the event bracket)
+        torch.cuda.synchronize()
+        last = step()
+        tm = eng.last_timing()
+        dev_ms.append(tm['total_ms'])
+        gemm_ms += tm['gemm_ms']
+        gemm_flops += tm['gemm_flops']
+        gemm_launches += tm['gemm_launches']
+        launches += tm['launches']
+        axx_ms += tm['axx_ms']
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    eng.set_option('profile', 0)
+    dev = torch.tensor(dev_ms, dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(dev, op=dist.ReduceOp.MAX)
+    total_ms = float(dev.sum().item())
+    value = args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: the same step through the C-ABI with host buffers, wall clock, uploads/downloads included
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.set_data(t_h, y_h, th_h, tx_h)
+        step()
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = args.steps / float(e2e_t.item())
+    npar = p_h.shape[0]
+    h2d = 8 * (2 * (hi - lo) + 2 * args.m + npar)
+    d2h = 8 * (npar + 8 + (hi - lo) + 2 * args.m)    # gradient, ELBO + terms; set_data reads t, th, tx back for planning
+
+    # ---- the culled evaluation beside the dense headline (or vice versa)
+    other = {}
+    alt = 80.0 if args.cull == 0.0 else 0.0
+    eng.set_option('cull', alt)
+    for _ in range(2):
+        step()
+    ms = []
+    for _ in range(max(2, min(args.steps, 5))):
+        flush.zero_()
+        torch.cuda.synchronize()
+        alt_out = step()
+        ms.append(eng.last_timing()['total_ms'])
+    alt_tm = eng.last_timing()
+    alt_dev = torch.tensor(ms, dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(alt_dev, op=dist.ReduceOp.MAX)
+    other = {'cull': alt, 'value': len(ms) / (float(alt_dev.sum().item()) * 1e-3), 'unit': UNIT,
+             'gemm_flops_per_step': alt_tm['gemm_flops'],
+             'elbo_rel_diff_vs_headline': abs(alt_out[0] - last[0]) / abs(last[0])}
+    eng.set_option('cull', args.cull)
+
+    # ---- frozen ("precomputed") regime, reported beside
+    eng.precompute(*wl['hyp'], reg=wl['reg'])
+    fms = []
+    for i in range(4):
+        eng.elbo_grad(p_h, mode=cgpcm_b200.MODE_FROZEN, reg=wl['reg'], out_grad=g_h)
+        if i >= 1:
+            fms.append(eng.last_timing()['total_ms'])
+    fdev = torch.tensor(fms, dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(fdev, op=dist.ReduceOp.MAX)
+    frozen_value = len(fms) / (float(fdev.sum().item()) * 1e-3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src, peak_raw = fp64_peak()
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    n, m = args.n, args.m
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'scaling sweep N=%d observations, nh=nx=%d, causal VCGPCM, full regime (Psi rebuilt '
+                               'and differentiated), grad w.r.t. all %d variables' % (n, m, npar),
+                   'n': n, 'nh': m, 'nx': m, 'cull': args.cull, 'chunk': args.chunk,
+                   'l2': 'flushed between timed steps (512 MB write); chunk workspaces (3 x %.0f MB) exceed L2'
+                         % (8e-6 * m * (args.chunk + 32) * m),
+                   'parallelism': 'observations sharded over %d GPU(s), one packed ncclAllReduce per sweep' % world},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'how': 'wall clock of set_data(host t, y, th, tx) + cgpcm_elbo_grad(host params) -> host gradient'},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'dgemm_dmma_kernel (FP64 DMMA m8n8k4 contraction GEMMs)',
+                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
+                     'traffic': None, 'peak_source': peak_src,
+                     'launches_per_step': gemm_launches / args.steps,
+                     'flops_per_step': gemm_flops / args.steps,
+                     'avg_launch_ms': gemm_ms / max(1, gemm_launches),
+                     'share_of_step': gemm_ms / total_ms if total_ms else None,
+                     'note': 'MEASURED_PEAKS.json has no FP64 figure; peak = FP64 tensor (DMMA) rate measured by '
+                             'tools/fp64_peaks.cu; flops = 2*K*(cells of the CTA tiles computed)'},
+        'breakdown_ms_per_step': {'axx_kernel': axx_ms / args.steps, 'gemm_kernels': gemm_ms / args.steps},
+        'elbo': last[0],
+        'other_cull_setting': other,
+        'frozen_regime': {'value': frozen_value, 'unit': UNIT,
+                          'note': 'Psi sums frozen by precompute(); gradient w.r.t. log s2, log s2_f, mu_u, var_u'},
+        'wall_s_timed_region': wall,
+    }
+    if not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline_eval(wl, args.cpu_sample)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

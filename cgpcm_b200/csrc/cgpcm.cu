@@ -123,6 +123,11 @@ struct cgpcm_handle {
   // options
   int chunk = 256;          // observations per chunk at full window width
   double cull = 80.0;       // 0 = dense
+  int profile = 0;          // 1 = CUDA events around every GEMM launch (roofline measurement)
+  std::vector<cudaEvent_t> pev;
+  size_t pev_used = 0;
+  double gemm_flops = 0.0;  // flops of the tiles the GEMM launches of the last evaluation computed
+  long gemm_launches = 0;
   // memory
   double* mats = nullptr;
   double* vecs = nullptr;
@@ -153,7 +158,7 @@ struct cgpcm_handle {
   int rank = 0, world = 1;
   // bookkeeping
   std::string err;
-  double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double timing[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long launches = 0;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
@@ -316,10 +321,33 @@ void dot(cgpcm_handle* h, const double* a, const double* b, int n, double* out) 
 
 void zero(cgpcm_handle* h, double* p, long n) { cudaMemsetAsync(p, 0, n * sizeof(double), h->st); }
 
+cudaEvent_t prof_event(cgpcm_handle* h) {
+  if (h->pev_used == h->pev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->pev.push_back(e);
+  }
+  return h->pev[h->pev_used++];
+}
+
 int gemm(cgpcm_handle* h, bool a_kc, bool b_kc, bool c_tr, int Mr, int Nr, int K, double alpha, const double* A,
          long lda, const double* B, long ldb, double beta, double* C, long ldc, int splits = 1, long stride = 0,
          int lower = 0) {
+  {
+    // flops of the CTA tiles this launch computes (tiles strictly above the diagonal are skipped when lower)
+    const int bm = pick_bm(Mr);
+    double cells = 0.0;
+    for (int m0 = 0; m0 < Mr; m0 += bm)
+      for (int n0 = 0; n0 < Nr; n0 += G_BN) {
+        if (lower && n0 > m0 + bm - 1) continue;
+        cells += (double)std::min(bm, Mr - m0) * std::min(G_BN, Nr - n0);
+      }
+    h->gemm_flops += 2.0 * cells * K;
+    h->gemm_launches++;
+  }
+  if (h->profile) cudaEventRecord(prof_event(h), h->st);
   cudaError_t e = dgemm(h->st, a_kc, b_kc, c_tr, Mr, Nr, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, stride, lower);
+  if (h->profile) cudaEventRecord(prof_event(h), h->st);
   L(h);
   if (e != cudaSuccess) {
     h->err = std::string("dgemm launch failed: ") + cudaGetErrorString(e);
@@ -636,6 +664,7 @@ int cgpcm_destroy(cgpcm_handle* h) {
   if (h->info) cudaFree(h->info);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : h->pev) cudaEventDestroy(e);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return 0;
@@ -678,6 +707,10 @@ int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
   if (!strcmp(key, "chunk")) {
     if (value < 8 || value > (1 << 20)) { h->err = "chunk out of range"; return -1; }
     h->chunk = round_up((int)value, 32);
+    return 0;
+  }
+  if (!strcmp(key, "profile")) {
+    h->profile = value != 0.0;
     return 0;
   }
   if (!strcmp(key, "cull")) {
@@ -869,6 +902,9 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   if (!full && !h->frozen) { h->err = "MODE_FROZEN requires cgpcm_precompute"; return -1; }
   if (ensure_sweep_buffers(h)) return -2;
   h->launches = 0;
+  h->pev_used = 0;
+  h->gemm_flops = 0.0;
+  h->gemm_launches = 0;
 
   PsiConst c;
   psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
@@ -1311,17 +1347,27 @@ int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_
     cudaEventElapsedTime(&ms[4], h->ev[1], h->ev[2]);   // Axx kernels
     h->timing[0] = ms[0]; h->timing[1] = ms[1]; h->timing[2] = ms[2]; h->timing[3] = ms[3]; h->timing[4] = ms[4];
     h->timing[5] = ms[1] - ms[4] + ms[2];
+    if (h->profile) {
+      double tot = 0.0;
+      for (size_t i = 0; i + 1 < h->pev_used; i += 2) {
+        float g = 0;
+        cudaEventElapsedTime(&g, h->pev[i], h->pev[i + 1]);
+        tot += g;
+      }
+      h->timing[5] = tot;
+    }
     h->timing[6] = (double)h->launches;
-    h->timing[7] = 0.0;
+    h->timing[7] = h->gemm_flops;
+    h->timing[8] = (double)h->gemm_launches;
     if (is_device_ptr(elbo)) cudaMemcpy(elbo, &e, sizeof e, cudaMemcpyHostToDevice); else *elbo = e;
     if (terms) { if (is_device_ptr(terms)) cudaMemcpy(terms, tm, sizeof tm, cudaMemcpyHostToDevice); else memcpy(terms, tm, sizeof tm); }
   }
   return rc;
 }
 
-int cgpcm_last_timing(cgpcm_handle* h, double out[8]) {
+int cgpcm_last_timing(cgpcm_handle* h, double out[12]) {
   if (!h || !out) return -1;
-  memcpy(out, h->timing, sizeof h->timing);
+  memcpy(out, h->timing, 12 * sizeof(double));
   return 0;
 }
 

@@ -110,10 +110,11 @@ class Engine(object):
         return float(elbo[0]), terms, grad
 
     def last_timing(self):
-        t = np.zeros(8)
+        t = np.zeros(12)
         self._ck(_lib.lib().cgpcm_last_timing(self._h, _lib.ptr(t)))
-        return dict(total_ms=t[0], forward_ms=t[1], backward_ms=t[2], algebra_ms=t[3], axx_ms=t[4],
-                    contraction_ms=t[5], launches=int(t[6]))
+        return dict(total_ms=float(t[0]), forward_ms=float(t[1]), backward_ms=float(t[2]), algebra_ms=float(t[3]),
+                    axx_ms=float(t[4]), gemm_ms=float(t[5]), launches=int(t[6]), gemm_flops=float(t[7]),
+                    gemm_launches=int(t[8]))
 
 
 def bvn_cdf(x1, x2, rho):

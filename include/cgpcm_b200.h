@@ -65,8 +65,9 @@ int cgpcm_comm_init(cgpcm_handle* h, const void* id128, int rank, int world);
 int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_local, const double* th,
                    const double* tx);
 
-/* Tuning knobs: "chunk" (observations per contraction chunk), "cull" (0 = dense; e > 0 = skip inducing
- * inputs whose Psi entries are provably below exp(-e) for the whole chunk). */
+/* Tuning knobs: "chunk" (observations per contraction chunk), "cull" (0 = dense; e > 0 = Psi entries whose
+ * Gaussian envelope is below exp(-e) are exactly 0 and whole windows of them are skipped; default 80),
+ * "profile" (1 = CUDA events around every GEMM launch so that cgpcm_last_timing reports their sum). */
 int cgpcm_set_option(cgpcm_handle* h, const char* key, double value);
 
 /* Psi statistics at hyper-parameters hyp = {alpha, gamma, omega}: what `sess.run(mats[...])` returns
@@ -87,8 +88,10 @@ int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_
 
 /* Timing of the last cgpcm_elbo_grad / cgpcm_psi on the handle's stream (CUDA events, ms):
  * out[0] total device time, out[1] forward sweep, out[2] backward sweep, out[3] M x M algebra,
- * out[4] Axx kernels, out[5] contraction GEMMs, out[6] number of kernel launches. */
-int cgpcm_last_timing(cgpcm_handle* h, double out[8]);
+ * out[4] Axx kernel, out[5] contraction GEMM kernels (exact sum with option "profile", else the sweeps
+ * minus the Axx kernel), out[6] number of kernel launches, out[7] FP64 flops of the CTA tiles those GEMM
+ * launches computed, out[8] number of GEMM launches; out[9..11] reserved. */
+int cgpcm_last_timing(cgpcm_handle* h, double out[12]);
 
 /* The reference's native op: Phi_2(x1, x2; rho) element-wise on three FP64 vectors of length n
  * (src/core/exponentiated_quadratic.py:547-552).  stream: a cudaStream_t or NULL. */

@@ -36,7 +36,9 @@ def test_train_schedule_toy():
     e_main = sess.run(elbo)
     mod.undo_precompute()
     elbo, terms = mod.elbo()
-    assert sess.run(elbo) == pytest.approx(e_main, rel=1e-9)      # frozen == full at the freeze point
+    # frozen == full at the freeze point, up to the reformulation noise of the two regimes (sum_Bxx is
+    # pre-summed in one, H = m2 - iKh contracted in the other; cond(Kh) ~ 1/reg amplifies the difference)
+    assert sess.run(elbo) == pytest.approx(e_main, rel=1e-7)
     learn.minimise_lbfgs(sess, -elbo, vars=[mod.vars[k] for k in ['mu_u', 'var_u', 's2_f', 's2', 'gamma', 'omega',
                                                                    'alpha']],
                          iters=15, fetches_config=fetches + terms, name='posttraining using L-BFGS', quiet=True)
@@ -50,7 +52,14 @@ def test_train_schedule_toy():
         want = om.elbo_and_grad(p, t, y, mod.th, mod.tx, config.reg)
     finally:
         om.PW_DISTS_EXACT = False
-    assert abs(want[0] - e_post) <= 1e-9 * abs(want[0])
+    # the trained ELBO (~ -8) is a sum of terms of magnitude ~1e2..1e3 that cancel: parity is 1e-9 relative
+    # to the largest term, term by term
+    got_terms = np.array(sess.run([tm['tensor'] for tm in terms]))
+    scale = np.abs(want[1]).max()
+    assert np.abs(got_terms - want[1]).max() <= 1e-9 * scale, (got_terms, want[1])
+    assert abs(want[0] - e_post) <= 1e-9 * scale
+    gsel = mod._evaluate(True, ['mu_u', 'var_u', 's2_f', 's2', 'gamma', 'omega', 'alpha'])[2]
+    assert np.abs(gsel - want[2]).max() <= 1e-9 * np.abs(want[2]).max()
     mats = mod.mats
     assert mats['sum_Axx'].shape == (40, 40) and mats['Ahh'].shape == (21, 21)
     config.reg = 1e-8

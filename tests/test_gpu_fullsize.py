@@ -50,23 +50,32 @@ def test_dense_equals_culled_and_terms_sum(wl, eng):
     eng.set_option('cull', 0.0)
     dense = eng.elbo_grad(wl['params'], reg=wl['reg'])
     eng.set_option('cull', 80.0)
-    assert abs(dense[0] - culled[0]) <= 1e-11 * abs(dense[0])
+    # rounding noise of one evaluation is ~1e-11 relative here (cond(Kh) ~ 1/reg = 1e6 amplifies summation order)
+    assert abs(dense[0] - culled[0]) <= 2e-10 * abs(dense[0])
     assert np.abs(dense[2] - culled[2]).max() <= 1e-9 * np.abs(dense[2]).max()
     assert dense[1].sum() == pytest.approx(dense[0], rel=1e-13)
     assert t_c['total_ms'] > 0
 
 
 def test_gradient_directional_derivative(wl, eng):
+    """Central differences of the GPU ELBO, Richardson-extrapolated (h = 2e-3, 1e-3: smaller steps drown in the
+    ~1e-11 relative evaluation noise of an ELBO of magnitude 1e6), against the analytic gradient."""
     rng = np.random.default_rng(3)
     p = wl['params']
     e0, _, g = eng.elbo_grad(p, reg=wl['reg'])
-    for k in range(3):
-        d = rng.standard_normal(p.shape[0])
-        d[:5] *= 0.3
-        d /= np.linalg.norm(d)
-        h = 1e-5
+    gnorm = np.linalg.norm(g)
+
+    def fd(d, h):
         f1 = eng.elbo_grad(p + h * d, reg=wl['reg'], want_grad=False)[0]
         f2 = eng.elbo_grad(p - h * d, reg=wl['reg'], want_grad=False)[0]
-        fd = (f1 - f2) / (2 * h)
+        return (f1 - f2) / (2 * h)
+
+    m = wl['nh']
+    for sl in [slice(0, 5), slice(5, 5 + m), slice(5 + m, None), slice(0, None)]:
+        d = np.zeros_like(p)
+        d[sl] = rng.standard_normal(d[sl].shape[0])
+        d /= np.linalg.norm(d)
+        est = (4 * fd(d, 1e-3) - fd(d, 2e-3)) / 3
         an = float(g @ d)
-        assert abs(fd - an) <= 1e-5 * max(abs(an), np.abs(g).max() * 1e-3), (k, fd, an)
+        # evaluation noise ~1e-10 * |ELBO| = 1e-4 over 2h = 2e-3 -> ~0.1 absolute = 4e-8 * |g|
+        assert abs(est - an) <= 2e-5 * abs(an) + 2e-7 * gnorm, (sl, est, an)
