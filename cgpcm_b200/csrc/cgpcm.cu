@@ -284,15 +284,19 @@ __global__ void sumsq_kernel(const double* __restrict__ y, long n, double* __res
 // ---- GEMM helper --------------------------------------------------------------------------------
 
 int pick_splits(int Mr, int Nr, int K, bool lower) {
-  int bm = pick_bm(Mr);
-  int tm = (Mr + bm - 1) / bm, tn = (Nr + G_BN - 1) / G_BN;
-  int tiles = tm * tn;
-  if (lower && tiles > 1) tiles = tiles * 3 / 4 > 0 ? tiles * 3 / 4 : 1;
-  int want = (2 * 148 + tiles - 1) / tiles;
-  int kt = (K + G_BK - 1) / G_BK;
-  int max_by_k = kt / 8 > 0 ? kt / 8 : 1;   // at least 8 k-tiles per split
-  int s = std::min(want, max_by_k);
-  return s < 1 ? 1 : s;
+  // number of CTA tiles the launch computes per split
+  const int bm = pick_bm(Mr);
+  int tiles = 0;
+  for (int m0 = 0; m0 < Mr; m0 += bm)
+    for (int n0 = 0; n0 < Nr; n0 += G_BN)
+      if (!(lower && n0 > m0 + bm - 1)) ++tiles;
+  const int kt = (K + G_BK - 1) / G_BK;
+  const int max_by_k = kt / 8 > 0 ? kt / 8 : 1;   // at least 8 k-tiles per split
+  // two full waves of 148 CTAs (one CTA per SM) when K is long enough, else one
+  int s = 296 / tiles;
+  if (s < 1) s = 1;
+  if (kt / s < 48) s = std::max(1, 148 / tiles);
+  return std::min(s, max_by_k);
 }
 
 }  // namespace
@@ -494,6 +498,14 @@ int gemm_splitk_sym(cgpcm_handle* h, bool a_kc, bool b_kc, int Mr, int K, const 
   return 0;
 }
 
+// out[(i,n)][l] = sum_k X[(i,n)][k] W[k][l] for the chunk's window block of a *symmetric* ld x ld matrix W.
+// Evaluated as out^T = W X^T with a transposed store, so that the 8-row-block dimension of the CTA tile is
+// the window width (split evenly) and the long (i,n) dimension runs along the 128-wide tile columns.
+int right_mul_sym(cgpcm_handle* h, const double* X, const double* W, const Chunk& ch, double* out) {
+  return gemm(h, true, true, true, ch.kwp, h->nhp * ch.nc, ch.kwp, 1.0, W + (long)ch.k_lo * h->ld + ch.k_lo, h->ld, X,
+              ch.kwp, 0.0, out, ch.kwp);
+}
+
 // Forward sweep over chunks: C1 += A^T (H A), and when `full`: Q += A iKx A^T, Y += sum y A.
 int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& chunks, const double* Hm,
                   const double* iKx, bool full) {
@@ -512,8 +524,8 @@ int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& 
                         h->M(M_C1) + (long)ch.k_lo * h->ld + ch.k_lo)) return -2;
     if (full) {
       // V[(i,n)][l] = sum_k A[(i,n)][k] iKx[k][l]   (window block of iKx)
-      if (gemm(h, true, false, false, h->nhp * ch.nc, ch.kwp, ch.kwp, 1.0, h->wsA, ch.kwp,
-               iKx + (long)ch.k_lo * h->ld + ch.k_lo, h->ld, 0.0, h->wsV, ch.kwp)) return -2;
+      // (computed as V^T = iKx A2^T with the transposed store: 200-row tiles split 104 + 96 instead of 128 + 72)
+      if (right_mul_sym(h, h->wsA, iKx, ch, h->wsV)) return -2;
       // Q[i][j] += sum_(n,k) A[i][(n,k)] V[j][(n,k)]
       if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsA, cols, h->wsV, cols, h->M(M_Q))) return -2;
     }
@@ -546,15 +558,13 @@ int backward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>&
     if (gen_chunk(h, c, ch, false)) return -2;
     const long cols = (long)ch.nc * ch.kwp;
     // U1[(i,n)][l] = sum_k A[(i,n)][k] C1bar[k][l]
-    if (gemm(h, true, false, false, h->nhp * ch.nc, ch.kwp, ch.kwp, 1.0, h->wsA, ch.kwp,
-             h->M(M_C1BAR) + (long)ch.k_lo * h->ld + ch.k_lo, h->ld, 0.0, h->wsV, ch.kwp)) return -2;
+    if (right_mul_sym(h, h->wsA, h->M(M_C1BAR), ch, h->wsV)) return -2;
     // Hbar[i][j] += sum_(n,l) U1[i][(n,l)] A[j][(n,l)]
     if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsV, cols, h->wsA, cols, h->M(M_HBAR))) return -2;
     if (full) {
       // T1 = H A ;  Abar = T1 Wx  (window block)
       if (gemm(h, true, false, false, h->nhp, (int)cols, h->nhp, 1.0, Hm, h->ld, h->wsA, cols, 0.0, h->wsT, cols)) return -2;
-      if (gemm(h, true, false, false, h->nhp * ch.nc, ch.kwp, ch.kwp, 1.0, h->wsT, ch.kwp,
-               h->M(M_WX) + (long)ch.k_lo * h->ld + ch.k_lo, h->ld, 0.0, h->wsV, ch.kwp)) return -2;
+      if (right_mul_sym(h, h->wsT, h->M(M_WX), ch, h->wsV)) return -2;
       const int threads = std::min(256, round_up(ch.kwp, 32));
       dim3 grid(h->nhp, (ch.nc + AHX_NSUB - 1) / AHX_NSUB);
       ahx_dot_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx,

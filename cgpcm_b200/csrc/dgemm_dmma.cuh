@@ -21,14 +21,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 namespace cg {
 
 constexpr int G_BM = 104;      // max rows per CTA tile
 constexpr int G_MB = 13;       // max 8-row blocks per CTA tile
-constexpr int G_BN = 128;
+constexpr int G_BN = 64;       // 4 warps x 16 columns
 constexpr int G_BK = 16;
 constexpr int G_STAGES = 3;
-constexpr int G_THREADS = 256;
+constexpr int G_THREADS = 128;
+constexpr int G_CTAS_PER_SM = 2;  // two co-resident CTAs: one's prologue / epilogue overlaps the other's DMMA loop
 constexpr int G_AS = (G_BM * (G_BK + 4) > G_BK * (G_BM + 4)) ? G_BM * (G_BK + 4) : G_BK * (G_BM + 4);
 constexpr int G_BS = (G_BN * (G_BK + 4) > G_BK * (G_BN + 4)) ? G_BN * (G_BK + 4) : G_BK * (G_BN + 4);
 constexpr int G_SMEM_BYTES = G_STAGES * (G_AS + G_BS) * 8;
@@ -40,7 +43,7 @@ struct GemmArgs {
   int M, N, K;
   long lda, ldb, ldc;
   double alpha, beta;
-  int bm;               // rows per CTA tile (multiple of 8, <= 104)
+  int splits;           // number of K splits (third tile-list dimension)
   int k_per_split;      // multiple of G_BK
   long c_split_stride;  // elements between split-K partial results
   int lower_only;       // skip CTA tiles that lie strictly above the diagonal (symmetric results)
@@ -61,122 +64,152 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
                : "d"(a), "d"(b));
 }
 
-template <bool A_KC, bool B_KC, bool C_TR>
-__global__ void __launch_bounds__(G_THREADS, 1) dgemm_dmma_kernel(const GemmArgs g) {
+// One CTA = one (split, row tile, column tile).  Compile-time number MB of 8-row blocks per tile: every loop
+// is fully unrolled and every shared-memory fragment address is `thread base + immediate`.  Rows / columns
+// beyond the matrix edge are zero-filled in shared memory (cp.async src-size 0) and not stored.
+// The operand fragments are double-buffered in registers (load k4+1 while the DMMAs of k4 issue): with a
+// single buffer every LDS has to wait for the in-flight DMMA that still reads its destination register.
+// The cp.async source pointers / shared offsets are computed once per CTA and only advanced per k-tile.
+template <int MB, bool A_KC, bool B_KC, bool C_TR>
+__global__ void __launch_bounds__(G_THREADS, G_CTAS_PER_SM) dgemm_dmma_kernel(const GemmArgs g) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = lane >> 2, tig = lane & 3;
-  const int m0 = blockIdx.y * g.bm;
+  const int nw = warp * 16;
+  constexpr int STAGE = G_AS + G_BS;
+  constexpr int TROWS = MB * 8;
+  const int m0 = blockIdx.y * TROWS;
   const int n0 = blockIdx.x * G_BN;
-  if (g.lower_only && n0 > m0 + g.bm - 1) return;
-  const int rows = min(g.bm, g.M - m0);       // valid rows of this tile (multiple of 8)
-  const int cols = min(G_BN, g.N - n0);       // valid columns (multiple of 8)
-  const int mb_count = rows >> 3;
-  const int nw = warp * 16;                   // this warp's first column inside the tile
-  const bool nb_ok0 = nw < cols, nb_ok1 = nw + 8 < cols;
+  if (g.lower_only && n0 > m0 + TROWS - 1) return;
+  const int rows = g.M - m0, cols = g.N - n0;     // valid rows / columns from the tile origin (may exceed tile)
   const int kbeg = blockIdx.z * g.k_per_split;
   const int kend = min(g.K, kbeg + g.k_per_split);
-  const int ktiles = (kend - kbeg + G_BK - 1) / G_BK;
+  const int ktiles = kend > kbeg ? (kend - kbeg + G_BK - 1) / G_BK : 0;
 
-  double acc[G_MB][2][2];
+  // ---- loader state: NA + NB 16-byte chunks per thread per k-tile
+  constexpr int NCH_A = A_KC ? TROWS * (G_BK / 2) : G_BK * (TROWS / 2);
+  constexpr int NA = (NCH_A + G_THREADS - 1) / G_THREADS;
+  constexpr int NCH_B = G_BN * G_BK / 2;
+  constexpr int NB = NCH_B / G_THREADS;
+  const double* ga[NA];
+  int sa[NA];        // shared offset (doubles) inside a stage, or -1 if this slot is unused
+  int ka[NA];        // k offset of the chunk inside the k-tile
+  const double* gb[NB];
+  int sb[NB], kb[NB];
 #pragma unroll
-  for (int i = 0; i < G_MB; ++i) { acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0; }
-
-  auto load_tile = [&](int stage, int kt) {
-    double* As = smem + stage * (G_AS + G_BS);
-    double* Bs = As + G_AS;
-    const int k0 = kbeg + kt * G_BK;
+  for (int j = 0; j < NA; ++j) {
+    const int ch = j * G_THREADS + tid;
     if (A_KC) {
-      const int nch = rows * (G_BK / 2);
-      for (int c = tid; c < nch; c += G_THREADS) {
-        int m = c >> 3, kc = (c & 7) * 2;
-        bool ok = (k0 + kc) < kend;
-        const double* src = ok ? g.A + (long)(m0 + m) * g.lda + k0 + kc : g.A;
-        cp_async16(As + m * (G_BK + 4) + kc, src, ok);
-      }
+      const int m = ch / (G_BK / 2), kc = (ch % (G_BK / 2)) * 2;
+      const bool ok = ch < NCH_A && m < rows;
+      sa[j] = ch < NCH_A ? m * (G_BK + 4) + kc : -1;
+      ka[j] = ok ? kc : (1 << 28);
+      ga[j] = g.A + (ok ? (long)(m0 + m) * g.lda + kbeg + kc : 0);
     } else {
-      const int half = rows >> 1;
-      const int nch = G_BK * half;
-      for (int c = tid; c < nch; c += G_THREADS) {
-        int kk = c / half, mc = (c - kk * half) * 2;
-        bool ok = (k0 + kk) < kend;
-        const double* src = ok ? g.A + (long)(k0 + kk) * g.lda + m0 + mc : g.A;
-        cp_async16(As + kk * (G_BM + 4) + mc, src, ok);
-      }
+      constexpr int HALF = TROWS / 2;
+      const int kk = ch / HALF, mc = (ch - kk * HALF) * 2;
+      const bool ok = ch < NCH_A && mc < rows;
+      sa[j] = ch < NCH_A ? kk * (G_BM + 4) + mc : -1;
+      ka[j] = ok ? kk : (1 << 28);
+      ga[j] = g.A + (ok ? (long)(kbeg + kk) * g.lda + m0 + mc : 0);
     }
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int ch = j * G_THREADS + tid;
     if (B_KC) {
-      const int nch = cols * (G_BK / 2);
-      for (int c = tid; c < nch; c += G_THREADS) {
-        int n = c >> 3, kc = (c & 7) * 2;
-        bool ok = (k0 + kc) < kend;
-        const double* src = ok ? g.B + (long)(n0 + n) * g.ldb + k0 + kc : g.B;
-        cp_async16(Bs + n * (G_BK + 4) + kc, src, ok);
-      }
+      const int n = ch / (G_BK / 2), kc = (ch % (G_BK / 2)) * 2;
+      const bool ok = n < cols;
+      sb[j] = G_AS + n * (G_BK + 4) + kc;
+      kb[j] = ok ? kc : (1 << 28);
+      gb[j] = g.B + (ok ? (long)(n0 + n) * g.ldb + kbeg + kc : 0);
     } else {
-      const int half = cols >> 1;
-      const int nch = G_BK * half;
-      for (int c = tid; c < nch; c += G_THREADS) {
-        int kk = c / half, nc = (c - kk * half) * 2;
-        bool ok = (k0 + kk) < kend;
-        const double* src = ok ? g.B + (long)(k0 + kk) * g.ldb + n0 + nc : g.B;
-        cp_async16(Bs + kk * (G_BN + 4) + nc, src, ok);
+      constexpr int HALF = G_BN / 2;
+      const int kk = ch / HALF, nc = (ch - kk * HALF) * 2;
+      const bool ok = nc < cols;
+      sb[j] = G_AS + kk * (G_BN + 4) + nc;
+      kb[j] = ok ? kk : (1 << 28);
+      gb[j] = g.B + (ok ? (long)(kbeg + kk) * g.ldb + n0 + nc : 0);
+    }
+  }
+  const long a_step = A_KC ? G_BK : (long)G_BK * g.lda;
+  const long b_step = B_KC ? G_BK : (long)G_BK * g.ldb;
+  int kleft = kend - kbeg;       // k extent not yet issued
+  auto issue = [&](int stage) {
+    double* base = smem + stage * STAGE;
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      if (NCH_A % G_THREADS == 0 || sa[j] >= 0) {
+        const bool ok = ka[j] < kleft;
+        cp_async16(base + sa[j], ok ? ga[j] : g.A, ok);
+        ga[j] += a_step;
       }
     }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const bool ok = kb[j] < kleft;
+      cp_async16(base + sb[j], ok ? gb[j] : g.B, ok);
+      gb[j] += b_step;
+    }
+    kleft -= G_BK;
   };
 
 #pragma unroll
-  for (int s = 0; s < G_STAGES - 1; ++s) {
-    if (s < ktiles) load_tile(s, s);
+  for (int s0 = 0; s0 < G_STAGES - 1; ++s0) {
+    if (s0 < ktiles) issue(s0);
     cp_async_commit();
   }
 
+  const int a_off = A_KC ? grp * (G_BK + 4) + tig : tig * (G_BM + 4) + grp;
+  const int b_off = G_AS + (B_KC ? (nw + grp) * (G_BK + 4) + tig : tig * (G_BN + 4) + nw + grp);
+  const bool warp_live = nw < cols;
+
+  double acc[MB][2][2];
+#pragma unroll
+  for (int i = 0; i < MB; ++i) { acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0; }
+
+  auto load_frags = [&](const double* Ap, const double* Bp, int k4, double (&a)[MB], double (&b)[2]) {
+    b[0] = B_KC ? Bp[k4 * 4] : Bp[k4 * 4 * (G_BN + 4)];
+    b[1] = B_KC ? Bp[8 * (G_BK + 4) + k4 * 4] : Bp[k4 * 4 * (G_BN + 4) + 8];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb)
+      a[mb] = A_KC ? Ap[mb * 8 * (G_BK + 4) + k4 * 4] : Ap[k4 * 4 * (G_BM + 4) + mb * 8];
+  };
+
+  int stage = 0;
   for (int kt = 0; kt < ktiles; ++kt) {
     cp_async_wait<G_STAGES - 2>();
     __syncthreads();
     {
-      int nt = kt + G_STAGES - 1;
-      if (nt < ktiles) load_tile(nt % G_STAGES, nt);
+      int st2 = stage + G_STAGES - 1;
+      if (st2 >= G_STAGES) st2 -= G_STAGES;
+      if (kt + G_STAGES - 1 < ktiles) issue(st2);
       cp_async_commit();
     }
-    const double* As = smem + (kt % G_STAGES) * (G_AS + G_BS);
-    const double* Bs = As + G_AS;
-    if (nb_ok0) {
+    if (warp_live) {
+      const double* Ap = smem + stage * STAGE + a_off;
+      const double* Bp = smem + stage * STAGE + b_off;
+      double fa[2][MB], fb[2][2];
+      load_frags(Ap, Bp, 0, fa[0], fb[0]);
 #pragma unroll
       for (int k4 = 0; k4 < G_BK / 4; ++k4) {
-        double b0, b1;
-        if (B_KC) {
-          b0 = Bs[(nw + grp) * (G_BK + 4) + k4 * 4 + tig];
-          b1 = Bs[(nw + 8 + grp) * (G_BK + 4) + k4 * 4 + tig];
-        } else {
-          b0 = Bs[(k4 * 4 + tig) * (G_BN + 4) + nw + grp];
-          b1 = Bs[(k4 * 4 + tig) * (G_BN + 4) + nw + 8 + grp];
-        }
-        double a[G_MB];
+        if (k4 + 1 < G_BK / 4) load_frags(Ap, Bp, k4 + 1, fa[(k4 + 1) & 1], fb[(k4 + 1) & 1]);
 #pragma unroll
-        for (int mb = 0; mb < G_MB; ++mb) {
-          if (mb < mb_count) {
-            a[mb] = A_KC ? As[(mb * 8 + grp) * (G_BK + 4) + k4 * 4 + tig]
-                         : As[(k4 * 4 + tig) * (G_BM + 4) + mb * 8 + grp];
-          } else {
-            a[mb] = 0.0;
-          }
-        }
-#pragma unroll
-        for (int mb = 0; mb < G_MB; ++mb) {
-          if (mb < mb_count) {
-            dmma_8x8x4(acc[mb][0][0], acc[mb][0][1], a[mb], b0);
-            dmma_8x8x4(acc[mb][1][0], acc[mb][1][1], a[mb], b1);
-          }
+        for (int mb = 0; mb < MB; ++mb) {
+          dmma_8x8x4(acc[mb][0][0], acc[mb][0][1], fa[k4 & 1][mb], fb[k4 & 1][0]);
+          dmma_8x8x4(acc[mb][1][0], acc[mb][1][1], fa[k4 & 1][mb], fb[k4 & 1][1]);
         }
       }
     }
+    if (++stage == G_STAGES) stage = 0;
   }
   cp_async_wait<0>();
 
   double* C = g.C + (long)blockIdx.z * g.c_split_stride;
+  const bool nb_ok0 = nw < cols, nb_ok1 = nw + 8 < cols;
 #pragma unroll
-  for (int mb = 0; mb < G_MB; ++mb) {
-    if (mb >= mb_count) continue;
+  for (int mb = 0; mb < MB; ++mb) {
+    if (mb * 8 >= rows) continue;
     const int row = m0 + mb * 8 + grp;
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) {
@@ -222,12 +255,21 @@ __global__ void reduce_partials_kernel(const double* __restrict__ part, long spl
   *o = (beta != 0.0 ? beta * *o : 0.0) + s;
 }
 
-inline int pick_bm(int M) {
-  int tiles = (M + G_BM - 1) / G_BM;
-  int bm = (M + tiles - 1) / tiles;
-  bm = (bm + 7) & ~7;
-  return bm > G_BM ? G_BM : bm;
+// Rows per CTA tile: the smallest supported block count (4 / 7 / 13 blocks of 8 rows) whose tiles cover M
+// with the fewest padded rows.
+inline int pick_mb(int M) {
+  const int cand[3] = {4, 7, 13};
+  int best = 13;
+  long best_cost = -1;
+  for (int i = 0; i < 3; ++i) {
+    int rows = cand[i] * 8;
+    long tiles = (M + rows - 1) / rows;
+    long cost = tiles * rows;                     // rows of DMMA work issued
+    if (best_cost < 0 || cost < best_cost || (cost == best_cost && cand[i] > best)) { best = cand[i]; best_cost = cost; }
+  }
+  return best;
 }
+inline int pick_bm(int M) { return pick_mb(M) * 8; }
 
 // Launch.  Returns cudaError_t of the launch.
 inline cudaError_t dgemm(cudaStream_t st, bool a_kc, bool b_kc, bool c_tr, int M, int N, int K, double alpha,
@@ -237,43 +279,58 @@ inline cudaError_t dgemm(cudaStream_t st, bool a_kc, bool b_kc, bool c_tr, int M
   GemmArgs g;
   g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K;
   g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.alpha = alpha; g.beta = beta;
-  g.bm = pick_bm(M);
+  const int mb = pick_mb(M);
   if (splits < 1) splits = 1;
   int kt = (K + G_BK - 1) / G_BK;
   int kt_per = (kt + splits - 1) / splits;
   if (kt_per < 1) kt_per = 1;
+  g.splits = splits;
   g.k_per_split = kt_per * G_BK;
   g.c_split_stride = c_split_stride;
   g.lower_only = lower_only;
-  dim3 grid((N + G_BN - 1) / G_BN, (M + g.bm - 1) / g.bm, splits);
+  const int rows = mb * 8;
+  dim3 grid((N + G_BN - 1) / G_BN, (M + rows - 1) / rows, splits);
   static bool attr_done = false;
-  auto set_attr = [](const void* f) {
-    cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
-  };
+#define CG_FOR_ALL(X) X(4) X(7) X(13)
+#define CG_SET(MBV)                                                                                              \
+  cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<MBV, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);  \
+  cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<MBV, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES); \
+  cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<MBV, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);\
+  cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<MBV, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
   if (!attr_done) {
-    set_attr((const void*)dgemm_dmma_kernel<true, true, false>);
-    set_attr((const void*)dgemm_dmma_kernel<true, false, false>);
-    set_attr((const void*)dgemm_dmma_kernel<false, true, false>);
-    set_attr((const void*)dgemm_dmma_kernel<false, false, false>);
-    set_attr((const void*)dgemm_dmma_kernel<true, true, true>);
-    set_attr((const void*)dgemm_dmma_kernel<true, false, true>);
-    set_attr((const void*)dgemm_dmma_kernel<false, true, true>);
-    set_attr((const void*)dgemm_dmma_kernel<false, false, true>);
+    CG_FOR_ALL(CG_SET)
+    cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<13, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
+    cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<13, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
+    cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<13, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
+    cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<13, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
     attr_done = true;
   }
-#define CG_LAUNCH(AK, BK, CT) dgemm_dmma_kernel<AK, BK, CT><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(g)
+#undef CG_SET
+#define CG_LAUNCH(MBV, AK, BK, CT) dgemm_dmma_kernel<MBV, AK, BK, CT><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(g)
+#define CG_PICK(AK, BK, CT)                      \
+  do {                                           \
+    if (mb == 4) CG_LAUNCH(4, AK, BK, CT);       \
+    else if (mb == 7) CG_LAUNCH(7, AK, BK, CT);  \
+    else CG_LAUNCH(13, AK, BK, CT);              \
+  } while (0)
+  // the four layouts the ELBO path uses come in every tile height; the others (C-ABI export only) in one
   if (!c_tr) {
-    if (a_kc && b_kc) CG_LAUNCH(true, true, false);
-    else if (a_kc && !b_kc) CG_LAUNCH(true, false, false);
-    else if (!a_kc && b_kc) CG_LAUNCH(false, true, false);
-    else CG_LAUNCH(false, false, false);
+    if (a_kc && b_kc) CG_PICK(true, true, false);
+    else if (a_kc && !b_kc) CG_PICK(true, false, false);
+    else if (!a_kc && !b_kc) CG_PICK(false, false, false);
+    else { grid.y = (M + 103) / 104; CG_LAUNCH(13, false, true, false); }
   } else {
-    if (a_kc && b_kc) CG_LAUNCH(true, true, true);
-    else if (a_kc && !b_kc) CG_LAUNCH(true, false, true);
-    else if (!a_kc && b_kc) CG_LAUNCH(false, true, true);
-    else CG_LAUNCH(false, false, true);
+    if (a_kc && b_kc) CG_PICK(true, true, true);
+    else {
+      grid.y = (M + 103) / 104;
+      if (a_kc && !b_kc) CG_LAUNCH(13, true, false, true);
+      else if (!a_kc && b_kc) CG_LAUNCH(13, false, true, true);
+      else CG_LAUNCH(13, false, false, true);
+    }
   }
+#undef CG_PICK
 #undef CG_LAUNCH
+#undef CG_FOR_ALL
   return cudaGetLastError();
 }
 

@@ -1,0 +1,35 @@
+"""One full-regime ELBO + gradient evaluation at the bench shape for ncu (launch list / --set full).
+Warm-up evaluations run before cudaProfilerStart so that `ncu --profile-from-start off` captures exactly one."""
+import argparse
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, '.')
+import cgpcm_b200
+from tests.workload import sweep_workload
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--n', type=int, default=100000)
+ap.add_argument('--m', type=int, default=200)
+ap.add_argument('--cull', type=float, default=0.0)
+ap.add_argument('--chunk', type=int, default=512)
+ap.add_argument('--warmup', type=int, default=2)
+ap.add_argument('--mode', type=int, default=1)
+a = ap.parse_args()
+wl = sweep_workload(a.n, a.m)
+eng = cgpcm_b200.Engine(a.m, a.m)
+eng.set_option('cull', a.cull)
+eng.set_option('chunk', a.chunk)
+eng.set_data(wl['t'], wl['y'], wl['th'], wl['tx'])
+if a.mode == 0:
+    eng.precompute(*wl['hyp'], reg=wl['reg'])
+for _ in range(a.warmup):
+    eng.elbo_grad(wl['params'], mode=a.mode, reg=wl['reg'])
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+e, terms, g = eng.elbo_grad(wl['params'], mode=a.mode, reg=wl['reg'])
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print('elbo', e, eng.last_timing())
