@@ -71,16 +71,14 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 // single buffer every LDS has to wait for the in-flight DMMA that still reads its destination register.
 // The cp.async source pointers / shared offsets are computed once per CTA and only advanced per k-tile.
 template <int MB, bool A_KC, bool B_KC, bool C_TR>
-__global__ void __launch_bounds__(G_THREADS, G_CTAS_PER_SM) dgemm_dmma_kernel(const GemmArgs g) {
-  extern __shared__ __align__(16) double smem[];
+__device__ __forceinline__ void dgemm_body(const GemmArgs& g, double* smem, const int m0, const int tile_rows) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = lane >> 2, tig = lane & 3;
   const int nw = warp * 16;
   constexpr int STAGE = G_AS + G_BS;
   constexpr int TROWS = MB * 8;
-  const int m0 = blockIdx.y * TROWS;
   const int n0 = blockIdx.x * G_BN;
-  if (g.lower_only && n0 > m0 + TROWS - 1) return;
+  if (g.lower_only && n0 > m0 + tile_rows - 1) return;
   const int rows = g.M - m0, cols = g.N - n0;     // valid rows / columns from the tile origin (may exceed tile)
   const int kbeg = blockIdx.z * g.k_per_split;
   const int kend = min(g.K, kbeg + g.k_per_split);
@@ -189,15 +187,18 @@ __global__ void __launch_bounds__(G_THREADS, G_CTAS_PER_SM) dgemm_dmma_kernel(co
     if (warp_live) {
       const double* Ap = smem + stage * STAGE + a_off;
       const double* Bp = smem + stage * STAGE + b_off;
+      const int k4n = (kend - kbeg - kt * G_BK + 3) >> 2;      // k4 steps with data in this k-tile (last one may be short)
       double fa[2][MB], fb[2][2];
       load_frags(Ap, Bp, 0, fa[0], fb[0]);
 #pragma unroll
       for (int k4 = 0; k4 < G_BK / 4; ++k4) {
         if (k4 + 1 < G_BK / 4) load_frags(Ap, Bp, k4 + 1, fa[(k4 + 1) & 1], fb[(k4 + 1) & 1]);
+        if (k4 == 0 || k4 < k4n) {
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {
-          dmma_8x8x4(acc[mb][0][0], acc[mb][0][1], fa[k4 & 1][mb], fb[k4 & 1][0]);
-          dmma_8x8x4(acc[mb][1][0], acc[mb][1][1], fa[k4 & 1][mb], fb[k4 & 1][1]);
+          for (int mb = 0; mb < MB; ++mb) {
+            dmma_8x8x4(acc[mb][0][0], acc[mb][0][1], fa[k4 & 1][mb], fb[k4 & 1][0]);
+            dmma_8x8x4(acc[mb][1][0], acc[mb][1][1], fa[k4 & 1][mb], fb[k4 & 1][1]);
+          }
         }
       }
     }
@@ -236,6 +237,16 @@ __global__ void __launch_bounds__(G_THREADS, G_CTAS_PER_SM) dgemm_dmma_kernel(co
       }
     }
   }
+}
+
+// Row tiles are MB blocks high; the last row tile of the matrix may use the lower body MBL (M = 200: 13 + 12
+// blocks, no padded rows).
+template <int MB, int MBL, bool A_KC, bool B_KC, bool C_TR>
+__global__ void __launch_bounds__(G_THREADS, G_CTAS_PER_SM) dgemm_dmma_kernel(const GemmArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  const int m0 = blockIdx.y * (MB * 8);
+  if (MBL != MB && m0 + MBL * 8 >= g.M) dgemm_body<MBL, A_KC, B_KC, C_TR>(g, smem, m0, MB * 8);
+  else dgemm_body<MB, A_KC, B_KC, C_TR>(g, smem, m0, MB * 8);
 }
 
 // out[r][c] (+)= sum_s part[s][r][c]  (deterministic split-K reduction); optional mirroring of the
@@ -290,47 +301,46 @@ inline cudaError_t dgemm(cudaStream_t st, bool a_kc, bool b_kc, bool c_tr, int M
   g.lower_only = lower_only;
   const int rows = mb * 8;
   dim3 grid((N + G_BN - 1) / G_BN, (M + rows - 1) / rows, splits);
+  // last row tile exactly 12 blocks high (M = 200, 408, ...): use the 13 / 12 pair
+  const bool pair12 = mb == 13 && (M - (int)(grid.y - 1) * rows) == 96;
   static bool attr_done = false;
-#define CG_FOR_ALL(X) X(4) X(7) X(13)
-#define CG_SET(MBV)                                                                                              \
-  cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<MBV, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);  \
-  cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<MBV, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES); \
-  cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<MBV, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);\
-  cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<MBV, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
+#define CG_ATTR(MBV, MBLV, AK, BK, CT) \
+  cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<MBV, MBLV, AK, BK, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
+#define CG_ATTR4(MBV, MBLV) CG_ATTR(MBV, MBLV, true, true, false) CG_ATTR(MBV, MBLV, true, false, false) \
+  CG_ATTR(MBV, MBLV, false, false, false) CG_ATTR(MBV, MBLV, true, true, true)
   if (!attr_done) {
-    CG_FOR_ALL(CG_SET)
-    cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<13, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
-    cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<13, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
-    cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<13, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
-    cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<13, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
+    CG_ATTR4(4, 4) CG_ATTR4(7, 7) CG_ATTR4(13, 13) CG_ATTR4(13, 12)
+    CG_ATTR(13, 13, false, true, false) CG_ATTR(13, 13, true, false, true) CG_ATTR(13, 13, false, true, true)
+    CG_ATTR(13, 13, false, false, true)
     attr_done = true;
   }
-#undef CG_SET
-#define CG_LAUNCH(MBV, AK, BK, CT) dgemm_dmma_kernel<MBV, AK, BK, CT><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(g)
-#define CG_PICK(AK, BK, CT)                      \
-  do {                                           \
-    if (mb == 4) CG_LAUNCH(4, AK, BK, CT);       \
-    else if (mb == 7) CG_LAUNCH(7, AK, BK, CT);  \
-    else CG_LAUNCH(13, AK, BK, CT);              \
+#undef CG_ATTR4
+#undef CG_ATTR
+#define CG_LAUNCH(MBV, MBLV, AK, BK, CT) dgemm_dmma_kernel<MBV, MBLV, AK, BK, CT><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(g)
+#define CG_PICK(AK, BK, CT)                              \
+  do {                                                   \
+    if (mb == 4) CG_LAUNCH(4, 4, AK, BK, CT);            \
+    else if (mb == 7) CG_LAUNCH(7, 7, AK, BK, CT);       \
+    else if (pair12) CG_LAUNCH(13, 12, AK, BK, CT);      \
+    else CG_LAUNCH(13, 13, AK, BK, CT);                  \
   } while (0)
   // the four layouts the ELBO path uses come in every tile height; the others (C-ABI export only) in one
   if (!c_tr) {
     if (a_kc && b_kc) CG_PICK(true, true, false);
     else if (a_kc && !b_kc) CG_PICK(true, false, false);
     else if (!a_kc && !b_kc) CG_PICK(false, false, false);
-    else { grid.y = (M + 103) / 104; CG_LAUNCH(13, false, true, false); }
+    else { grid.y = (M + 103) / 104; CG_LAUNCH(13, 13, false, true, false); }
   } else {
     if (a_kc && b_kc) CG_PICK(true, true, true);
     else {
       grid.y = (M + 103) / 104;
-      if (a_kc && !b_kc) CG_LAUNCH(13, true, false, true);
-      else if (!a_kc && b_kc) CG_LAUNCH(13, false, true, true);
-      else CG_LAUNCH(13, false, false, true);
+      if (a_kc && !b_kc) CG_LAUNCH(13, 13, true, false, true);
+      else if (!a_kc && b_kc) CG_LAUNCH(13, 13, false, true, true);
+      else CG_LAUNCH(13, 13, false, false, true);
     }
   }
 #undef CG_PICK
 #undef CG_LAUNCH
-#undef CG_FOR_ALL
   return cudaGetLastError();
 }
 

@@ -1,0 +1,58 @@
+"""torchrun --nproc-per-node G tools/check_multi.py : the observation-sharded evaluation (one packed
+ncclAllReduce per sweep) against the single-GPU evaluation of the whole series, through the Python API."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, '.')
+import cgpcm_b200
+from cgpcm_b200 import VCGPCM, Data, Session, config
+from tests.workload import sweep_workload
+
+rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+n, m = int(sys.argv[1]) if len(sys.argv) > 1 else 20000, int(sys.argv[2]) if len(sys.argv) > 2 else 96
+wl = sweep_workload(n, m)
+config.reg = wl['reg']
+np.random.seed(0)
+sess = Session()                       # picks rank / world / device up from torch.distributed
+assert (sess.rank, sess.world, sess.device) == (rank, world, local)
+mod = VCGPCM.from_recipe(sess, Data(wl['t'], wl['y']), nx=m, nh=m, tau_w=.1, tau_f=.025, causal=True)
+mod.vars['s2'].value = np.array(np.log(.1))
+names = ['s2', 's2_f', 'alpha', 'gamma', 'omega', 'mu_u', 'var_u']
+for k in ['mu_u', 'var_u']:            # identical q(u) on every rank
+    t = torch.tensor(mod.vars[k].value, device='cuda')
+    dist.broadcast(t, 0)
+    mod.vars[k].value = t.cpu().numpy()
+elbo, terms = mod.elbo()
+f, g = elbo.value_and_grad([mod.vars[k] for k in names])
+mod.precompute()
+f_fr, g_fr = elbo.value_and_grad([mod.vars[k] for k in ['mu_u', 'var_u', 's2_f', 's2']])
+mod.undo_precompute()
+# every rank holds the same answer
+fs = [None] * world
+dist.all_gather_object(fs, (f, float(np.abs(g).sum()), f_fr))
+assert all(abs(x[0] - fs[0][0]) <= 1e-13 * abs(fs[0][0]) for x in fs), fs
+if rank == 0:
+    eng = cgpcm_b200.Engine(m, m, device=local)
+    eng.set_data(wl['t'], wl['y'], mod.th, mod.tx)
+    p = mod._pack()
+    e1, t1, g1 = eng.elbo_grad(p, reg=config.reg)
+    g1s = mod._slice_grad(g1, names)
+    print('world %d: sharded elbo %.12e single %.12e rel %.2e; grad rel %.2e' % (
+        world, f, e1, abs(f - e1) / abs(e1), np.abs(g - g1s).max() / np.abs(g1s).max()))
+    eng.precompute(*wl['hyp'], reg=config.reg)
+    e2, _, g2 = eng.elbo_grad(p, mode=0, reg=config.reg)
+    g2s = mod._slice_grad(g2, ['mu_u', 'var_u', 's2_f', 's2'])
+    print('frozen: sharded %.12e single %.12e rel %.2e; grad rel %.2e' % (
+        f_fr, e2, abs(f_fr - e2) / abs(e2), np.abs(g_fr - g2s).max() / np.abs(g2s).max()))
+    # two summation orders of the same sums: the ELBO noise floor here is ~5e-10 relative (cond(Kh) ~ 1/reg)
+    assert abs(f - e1) <= 2e-9 * abs(e1) and np.abs(g - g1s).max() <= 2e-9 * np.abs(g1s).max()
+    assert abs(f_fr - e2) <= 2e-9 * abs(e2) and np.abs(g_fr - g2s).max() <= 2e-9 * np.abs(g2s).max()
+    print('OK')
+dist.barrier()
+dist.destroy_process_group()
