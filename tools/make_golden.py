@@ -1,0 +1,34 @@
+"""Generates tests/golden/*.npz: seeded inputs and the CPU oracle's outputs (Psi sums, ELBO, 7 terms, gradient;
+full and frozen regime) at the named shapes.  The reference itself cannot run in this image (Python 2 +
+TensorFlow 1.x + bvn-cdf), so the vectors come from the oracle restatement, which is pinned by
+the reference's own known-answer tests (tests/test_oracle_golden.py) and by quadrature / scipy / mpmath.
+Run:  python tools/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import model as om  # noqa: E402
+from tests.cases import make_case  # noqa: E402
+
+om.PW_DISTS_EXACT = True     # exact squared distances (see oracle/model.py)
+out_dir = os.path.join(ROOT, 'tests', 'golden')
+os.makedirs(out_dir, exist_ok=True)
+for name in ['toy_test', 'ou', 'hrir', 'crude', 'sweep', 'toy_acausal_model']:
+    c = make_case(name)
+    e, terms, g = om.elbo_and_grad(c['params'], c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'])
+    fr = om.precompute(c['params'], c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'])
+    p2 = c['params'].copy()
+    p2[0] += .25
+    p2[5:] *= 1.03
+    ef, tf, gf = om.elbo_and_grad(p2, c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'], frozen=fr)
+    m = fr[0]
+    np.savez_compressed(os.path.join(out_dir, name + '.npz'), t=c['t'], y=c['y'], th=c['th'], tx=c['tx'],
+                        hyp=np.array(c['hyp']), reg=c['reg'], causal=c['causal'], params=c['params'],
+                        sum_Axx=m['sum_Axx'].numpy(), Ahh=m['Ahh'].numpy(), a=float(m['a']),
+                        sum_Ahx_y=m['sum_Ahx_y'].numpy(), elbo=e, terms=terms, grad=g,
+                        params_frozen=p2, elbo_frozen=ef, terms_frozen=tf, grad_frozen=gf)
+    print(name, e, ef)
