@@ -568,7 +568,8 @@ int backward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>&
       const int threads = std::min(256, round_up(ch.kwp, 32));
       dim3 grid(h->nhp, (ch.nc + AHX_NSUB - 1) / AHX_NSUB);
       ahx_dot_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx,
-                                                  h->nx, ch.k_lo, ch.kwp, h->wsV, h->M(M_YBAR), h->ld, h->gpart, c);
+                                                  h->nx, ch.k_lo, ch.kwp, h->wsA, h->wsV, h->M(M_YBAR), h->ld, h->gpart,
+                                                  c);
       L(h);
     }
   }

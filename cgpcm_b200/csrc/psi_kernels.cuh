@@ -213,12 +213,13 @@ __global__ void __launch_bounds__(256) ahx_gen_kernel(const double* __restrict__
 }
 
 // gpart[(blockIdx.y * gridDim.x + blockIdx.x) * 3 + theta] += sum over the block's elements of
-//   (W[i][n][k] + y_n * Ybar[i][k_lo + k]) * dA[i,n,k]/dtheta.
+//   (W[i][n][k] + y_n * Ybar[i][k_lo + k]) * dA[i,n,k]/dtheta,   A = the chunk's Ahx block (ahx_gen_kernel).
 __global__ void __launch_bounds__(256) ahx_dot_kernel(const double* __restrict__ t, const double* __restrict__ y,
                                                       int n_valid, int nc, const double* __restrict__ th, int nh,
                                                       const double* __restrict__ tx, int nx, int k_lo, int kwp,
-                                                      const double* __restrict__ W, const double* __restrict__ Ybar,
-                                                      long ldy, double* __restrict__ gpart, const PsiConst c) {
+                                                      const double* __restrict__ A, const double* __restrict__ W,
+                                                      const double* __restrict__ Ybar, long ldy,
+                                                      double* __restrict__ gpart, const PsiConst c) {
   const int i = blockIdx.x;
   const int n0 = blockIdx.y * AHX_NSUB;
   const int n1 = min(n_valid, n0 + AHX_NSUB);
@@ -230,8 +231,10 @@ __global__ void __launch_bounds__(256) ahx_dot_kernel(const double* __restrict__
       if (kg >= nx) continue;
       const double txk = tx[kg];
       const double yb = Ybar[(long)i * ldy + kg];
-      const double* src = W + ((long)i * nc + n0) * kwp + k;
-      for (int n = n0; n < n1; ++n, src += kwp) {
+      const long off = ((long)i * nc + n0) * kwp + k;
+      const double* src = W + off;
+      const double* asrc = A + off;
+      for (int n = n0; n < n1; ++n, src += kwp, asrc += kwp) {
         const double d = __ldg(t + n) - txk;
         const double E = -c.e_hh * thi * thi - c.e_dd * d * d + c.e_hd * thi * d;
         if (E < -c.cull) continue;
@@ -239,15 +242,10 @@ __global__ void __launch_bounds__(256) ahx_dot_kernel(const double* __restrict__
         const double bh = -(c.gamma * thi + c.omega * d);    // b / 2
         const double u = bh * 2.0 * c.inv_2A;                // b / (2A)
         const double z = bh * c.inv_sqrtA;
-        const double eE = exp(E);
-        double F, X;
-        if (c.causal) {
-          F = c.pref_hx * eE * erfc(z);
-          X = exp(E - z * z) * c.inv_sqrtA;
-        } else {
-          F = c.pref_hx * eE;
-          X = 0.0;
-        }
+        // F = Ahx[n,i,k] itself is still in the chunk workspace (same bits as the forward value); only the
+        // Gaussian factor of the erfc derivative is evaluated here
+        const double F = *asrc;
+        const double X = c.causal ? exp(E - z * z) * c.inv_sqrtA : 0.0;
         const double zc = z * c.inv_2A;
         const double da = F * (-thi * thi - u * u - c.inv_2A) + X * zc;
         const double dg = F * (-(thi + u) * (thi + u) - c.inv_2A) + X * (thi * c.inv_sqrtA + zc);

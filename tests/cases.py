@@ -75,3 +75,22 @@ def make_case(name, seed=0, n=None):
 
 
 CASES = ['toy_test', 'toy_small', 'toy_acausal_model', 'ou', 'hrir', 'crude', 'sweep']
+
+
+def oracle_noise_floor(params, t, y, th, tx, reg, causal=True, trials=4, seed=0):
+    """Conditioning noise of the path at ``params``: the spread of the oracle's own (elbo, grad) when every
+    input (hyper-parameters, th) is moved by at most 2 ulp.  At trained points s2 is small and cond(Kh) ~ 1/reg,
+    so two correct FP64 evaluations (the reference's TF graph on another machine, the oracle, the CUDA path)
+    differ by this much; a parity bar below it is not attainable by *any* implementation.
+    Returns (elbo_noise, grad_noise) as max-abs over the trials."""
+    rng = np.random.default_rng(seed)
+    e0, _, g0 = om.elbo_and_grad(params, t, y, th, tx, reg, causal)
+    en, gn = 0.0, 0.0
+    for _ in range(trials):
+        p2 = np.array(params, dtype=np.float64)
+        p2[:5] = p2[:5] * (1 + rng.integers(-2, 3, 5) * 1.1e-16)
+        th2 = th * (1 + rng.integers(-2, 3, th.shape[0]) * 1.1e-16)
+        e2, _, g2 = om.elbo_and_grad(p2, t, y, th2, tx, reg, causal)
+        en = max(en, abs(e2 - e0))
+        gn = max(gn, float(np.abs(g2 - g0).max()))
+    return en, gn

@@ -10,6 +10,7 @@ torch = pytest.importorskip('torch')
 import cgpcm_b200
 from cgpcm_b200 import VCGPCM, Data, Session, config, learn
 from oracle import model as om
+from tests.cases import oracle_noise_floor
 
 
 def test_train_schedule_toy():
@@ -59,7 +60,15 @@ def test_train_schedule_toy():
     assert np.abs(got_terms - want[1]).max() <= 1e-9 * scale, (got_terms, want[1])
     assert abs(want[0] - e_post) <= 1e-9 * scale
     gsel = mod._evaluate(True, ['mu_u', 'var_u', 's2_f', 's2', 'gamma', 'omega', 'alpha'])[2]
-    assert np.abs(gsel - want[2]).max() <= 1e-9 * np.abs(want[2]).max()
+    # at the trained point (s2 ~ 4e-3, cond(Kh) ~ 1/reg) the gradient is a cancellation of terms ~1e6 times
+    # larger than itself: the oracle's own gradient moves by ~1e-5 when its inputs move by 1 ulp.  The bar is
+    # 1e-9 relative or that measured conditioning noise, whichever is larger.
+    om.PW_DISTS_EXACT = True
+    try:
+        _, gnoise = oracle_noise_floor(p, t, y, mod.th, mod.tx, config.reg)
+    finally:
+        om.PW_DISTS_EXACT = False
+    assert np.abs(gsel - want[2]).max() <= 1e-9 * np.abs(want[2]).max() + 3 * gnoise, gnoise
     mats = mod.mats
     assert mats['sum_Axx'].shape == (40, 40) and mats['Ahh'].shape == (21, 21)
     config.reg = 1e-8

@@ -108,6 +108,47 @@ __global__ void k16(double* out, int iters) {
   if (s == 123.456) out[0] = s;
 }
 
+
+// V2: m8n8k4, MB x NB register tile per warp, fragments double-buffered in registers, barrier every 4 k4 steps.
+template <int MB, int NB, int BAR>
+__global__ void k884g(double* out, int iters) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 2, tig = lane & 3;
+  for (int i = threadIdx.x; i < 8192; i += blockDim.x) sm[i] = 1e-3 * i;
+  __syncthreads();
+  double acc[MB][NB][2];
+#pragma unroll
+  for (int i = 0; i < MB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const double* Ap = sm + ((warp & 3) * 8 + grp) * 20 + tig;
+  const double* Bp = sm + 4400 + ((warp >> 2) * 8 + grp) * 20 + tig;
+  double a[2][MB], b[2][NB];
+  auto ld = [&](int k4, double (&aa)[MB], double (&bb)[NB]) {
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) aa[mb] = Ap[mb * 160 + k4 * 4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) bb[nb] = Bp[nb * 160 + k4 * 4];
+  };
+  for (int it = 0; it < iters; ++it) {
+    ld(0, a[0], b[0]);
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      if (k4 + 1 < 4) ld(k4 + 1, a[(k4 + 1) & 1], b[(k4 + 1) & 1]);
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[k4 & 1][mb], b[k4 & 1][nb]);
+    }
+    if (BAR) __syncthreads();
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < MB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) s += acc[i][j][0] + acc[i][j][1];
+  if (s == 123.456) out[0] = s;
+}
+
 template <class K>
 void run(const char* name, K kern, int threads, int smem_bytes, double flop_per_thread_iter, int iters) {
   double* out; CK(cudaMalloc(&out, 8));
@@ -148,5 +189,21 @@ int main() {
   run("16816 MB3 LDS+barrier  2x256thr", k16<3, 16, 2>, 256, 100000, 3 * 2 * 1 * 128.0, it);
   run("16816 MB4 LDS+barrier  1x512thr", k16<4, 16, 2>, 512, 120000, 4 * 2 * 1 * 128.0, it);
   run("1688 MB4 LDS+barrier   1x512thr", k16<4, 8, 2>, 512, 120000, 4 * 2 * 2 * 64.0, it);
+  // generic MB x NB warp tiles, double-buffered fragments
+  run("884g 13x2 bar  2x128thr (8 warps/SM)", k884g<13, 2, 1>, 128, 100000, 13 * 2 * 4 * 16.0, it);
+  run("884g 13x2 bar  1x128thr (4 warps/SM)", k884g<13, 2, 1>, 128, 120000, 13 * 2 * 4 * 16.0, it);
+  run("884g 13x2 bar  1x256thr (8 warps/SM)", k884g<13, 2, 1>, 256, 120000, 13 * 2 * 4 * 16.0, it);
+  run("884g 13x2 nobar 2x128thr", k884g<13, 2, 0>, 128, 100000, 13 * 2 * 4 * 16.0, it);
+  run("884g 5x5 bar   1x480thr (15 warps/SM)", k884g<5, 5, 1>, 480, 120000, 5 * 5 * 4 * 16.0, it);
+  run("884g 5x5 bar   1x256thr (8 warps/SM)", k884g<5, 5, 1>, 256, 120000, 5 * 5 * 4 * 16.0, it);
+  run("884g 5x5 bar   2x256thr (16 warps/SM)", k884g<5, 5, 1>, 256, 100000, 5 * 5 * 4 * 16.0, it);
+  run("884g 5x5 nobar 1x480thr", k884g<5, 5, 0>, 480, 120000, 5 * 5 * 4 * 16.0, it);
+  run("884g 7x4 bar   1x256thr (8 warps/SM)", k884g<7, 4, 1>, 256, 120000, 7 * 4 * 4 * 16.0, it);
+  run("884g 7x4 bar   2x128thr (8 warps/SM)", k884g<7, 4, 1>, 128, 100000, 7 * 4 * 4 * 16.0, it);
+  run("884g 6x4 bar   1x256thr (8 warps/SM)", k884g<6, 4, 1>, 256, 120000, 6 * 4 * 4 * 16.0, it);
+  run("884g 6x4 bar   1x384thr (12 warps/SM)", k884g<6, 4, 1>, 384, 120000, 6 * 4 * 4 * 16.0, it);
+  run("884g 4x4 bar   1x512thr (16 warps/SM)", k884g<4, 4, 1>, 512, 120000, 4 * 4 * 4 * 16.0, it);
+  run("884g 13x1 bar  1x256thr (8 warps/SM)", k884g<13, 1, 1>, 256, 120000, 13 * 1 * 4 * 16.0, it);
+  run("884g 13x1 bar  1x512thr (16 warps/SM)", k884g<13, 1, 1>, 512, 120000, 13 * 1 * 4 * 16.0, it);
   return 0;
 }
