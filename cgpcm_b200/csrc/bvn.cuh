@@ -184,7 +184,62 @@ __device__ __forceinline__ double bvnd_tab(double h, double k, const BvnTab& T) 
   return bvn;
 }
 
+
+// ---- pair-hoisted high-correlation branch ---------------------------------------------------------
+// In the CGPCM  h - k = -(x1 - x2) = (p - q)(tx_k - tx_l)  does not depend on the observation: for a fixed
+// pair (k, l) Genz's  bs = (h - k)^2  is a constant, so of the two exp() per quadrature node of the
+// |rho| >= 0.925 branch one, exp(-bs / (2 xs_j)), is hoisted out of the loop over observations together
+// with sqrt(bs) and Phi(-b / a).  Every term carries the common factor exp(-hk / 2); Genz's skip tests
+// (asr > -100, -hk < 100) only drop terms below 4e-44 and are not needed in the factored form
+// (all factors stay finite for hk >= -600; below that the un-hoisted routine is used).
+// Valid for rho > 0 (always true here: rho = gamma / (alpha + gamma + omega)).
+// The 20 node constants live in shared memory ([node][thread], conflict-free) so that the loop over
+// observations keeps a register footprint that allows 16 warps per SM.
+struct BvnPair {
+  double bs, P0, Pb;
+};
+constexpr int BVN_PAIR_THREADS = 256;
+
+// sP: __shared__ double[20][BVN_PAIR_THREADS]; column threadIdx.x belongs to this thread.
+__device__ __forceinline__ void bvn_pair_init(double hmk, const BvnTab& T, BvnPair& R, double (*sP)[BVN_PAIR_THREADS]) {
+  const double bs = hmk * hmk;
+  R.bs = bs;
+  R.P0 = T.a_ * exp(-0.5 * bs / T.as_);
+  const double b = fabs(hmk);
+  R.Pb = CG_SQRT_TWO_PI * phid(-b / T.a_) * b;
+#pragma unroll
+  for (int j = 0; j < 20; ++j) sP[j][threadIdx.x] = T.w[j] * exp(-0.5 * bs * T.c0[j]);   // (a/2) w_j exp(-bs / (2 xs_j))
+}
+
+// Phi_2(x1, x2; rho) for the pair whose constants are R / sP  (same value as bvnd_tab(-x1, -x2, T)).
+__device__ __forceinline__ double bvn_cdf_pair(double x1, double x2, const BvnTab& T, const BvnPair& R,
+                                               const double (*sP)[BVN_PAIR_THREADS]) {
+  const double hk = x1 * x2;
+  const double tail = phid(fmin(x1, x2));
+  if (hk > 200.0) return tail;                       // every remaining term is below exp(-100) (Genz's own cut)
+  if (hk < -600.0) return bvnd_tab(-x1, -x2, T);     // exp(-hk/2) would overflow: un-hoisted routine
+  const double E1 = exp(-0.5 * hk);
+  const double c = (4.0 - hk) * 0.125, d = (12.0 - hk) * 0.0625;
+  const double bs = R.bs, as = T.as_;
+  const double t5 = 1.0 - d * bs * 0.2;
+  double s = R.P0 * (1.0 - c * (bs - as) * t5 * (1.0 / 3.0) + c * d * as * as * 0.2) -
+             R.Pb * (1.0 - c * bs * t5 * (1.0 / 3.0));
+#pragma unroll
+  for (int j = 0; j < 20; ++j) {
+    const double xs = T.c3[j];
+    s += sP[j][threadIdx.x] * (exp(-hk * T.c1[j]) * T.c2[j] - (1.0 + c * xs * (1.0 + d * xs)));
+  }
+  return tail - E1 * s * (1.0 / CG_TWO_PI);
+}
+
 // Phi_2(x1, x2; rho) and its three partial derivatives.
+__device__ __forceinline__ void bvn_partials_tab(double x1, double x2, const BvnTab& T, double& d1, double& d2,
+                                                 double& dr) {
+  const double inv_sqrt_2pi = 0.39894228040143267794;
+  d1 = inv_sqrt_2pi * exp(-0.5 * x1 * x1) * phid((x2 - T.rho * x1) * T.inv_s);
+  d2 = inv_sqrt_2pi * exp(-0.5 * x2 * x2) * phid((x1 - T.rho * x2) * T.inv_s);
+  dr = exp(-(x1 * x1 - 2.0 * T.rho * x1 * x2 + x2 * x2) * T.inv_2om) * T.inv_2pis;
+}
 __device__ __forceinline__ void bvn_cdf_grad_tab(double x1, double x2, const BvnTab& T, double& cdf,
                                                  double& d1, double& d2, double& dr) {
   cdf = bvnd_tab(-x1, -x2, T);

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "../../include/cgpcm_b200.h"
+#include "dgemm_sym.cuh"
 #include "linalg.cuh"
 #include "psi_kernels.cuh"
 
@@ -104,6 +105,7 @@ struct Chunk {
   int nc;       // padded observation count (multiple of 8)
   int k_lo;     // first inducing input of the window (multiple of 8)
   int kwp;      // padded window width (multiple of 8)
+  long off;     // element offset of this chunk's block in the sweep stores (prefix sum of nhp * nc * kwp)
 };
 
 }  // namespace
@@ -126,7 +128,8 @@ struct cgpcm_handle {
   int profile = 0;          // 1 = CUDA events around every GEMM launch (roofline measurement)
   std::vector<cudaEvent_t> pev;
   size_t pev_used = 0;
-  double gemm_flops = 0.0;  // flops of the tiles the GEMM launches of the last evaluation computed
+  double gemm_flops = 0.0;  // algorithmic flops of the GEMM launches of the last evaluation (symmetric: M(M+1)K)
+  double gemm_flops_exec = 0.0;   // flops of the CTA / warp tiles those launches computed
   long gemm_launches = 0;
   // memory
   double* mats = nullptr;
@@ -139,8 +142,18 @@ struct cgpcm_handle {
   // chunk workspaces
   long ws_elems = 0;
   double *wsA = nullptr, *wsT = nullptr, *wsV = nullptr;
+  // sweep stores (option "store", default on when they fit): the Ahx blocks of all chunks (storeA) and
+  // T1 = H A of the forward sweep (storeT) stay resident in HBM for the backward sweep instead of being
+  // regenerated / recomputed -- 8 nhp N nx bytes each (32 GB at N = 1e5, M = 200; the B200 has 180 GB).
+  int store_opt = 1;
+  double *storeA = nullptr, *storeT = nullptr;
+  long storeA_elems = 0, storeT_elems = 0;
+  bool use_store = false;      // decided per evaluation
+  bool storeA_frozen_valid = false;   // storeA holds the frozen regime's Ahx blocks (constant between evaluations)
   double* part = nullptr;      // split-K partials
   long part_elems = 0;
+  double* symacc[2] = {nullptr, nullptr};   // per-K-slice private accumulators of the symmetric contractions
+  int sym_used[2] = {0, 0};                 // slices touched since sym_begin
   double* axx_part = nullptr;
   long axx_part_elems = 0;
   int axx_slices = 0;
@@ -338,7 +351,8 @@ int gemm(cgpcm_handle* h, bool a_kc, bool b_kc, bool c_tr, int Mr, int Nr, int K
          long lda, const double* B, long ldb, double beta, double* C, long ldc, int splits = 1, long stride = 0,
          int lower = 0) {
   {
-    // flops of the CTA tiles this launch computes (tiles strictly above the diagonal are skipped when lower)
+    // executed: the CTA tiles this launch computes (tiles strictly above the diagonal are skipped when lower);
+    // algorithmic: M x N cells, or the M (M + 1) / 2 cells of the lower triangle of a symmetric result
     const int bm = pick_bm(Mr);
     double cells = 0.0;
     for (int m0 = 0; m0 < Mr; m0 += bm)
@@ -346,7 +360,8 @@ int gemm(cgpcm_handle* h, bool a_kc, bool b_kc, bool c_tr, int Mr, int Nr, int K
         if (lower && n0 > m0 + bm - 1) continue;
         cells += (double)std::min(bm, Mr - m0) * std::min(G_BN, Nr - n0);
       }
-    h->gemm_flops += 2.0 * cells * K;
+    h->gemm_flops_exec += 2.0 * cells * K;
+    h->gemm_flops += 2.0 * K * ((lower && Mr == Nr) ? 0.5 * Mr * (Mr + 1.0) : (double)Mr * Nr);
     h->gemm_launches++;
   }
   if (h->profile) cudaEventRecord(prof_event(h), h->st);
@@ -425,9 +440,33 @@ void plan_chunks(cgpcm_handle* h, const PsiConst& c, std::vector<Chunk>& out) {
     }
     Chunk ch;
     ch.n0 = n0; ch.nv = nc; ch.nc = round_up(nc, 8); ch.k_lo = k_lo; ch.kwp = kwp;
+    ch.off = out.empty() ? 0 : out.back().off + (long)h->nhp * out.back().nc * out.back().kwp;
     out.push_back(ch);
     n0 += nc;
   }
+}
+
+// Decide whether this evaluation keeps the Ahx blocks (and T1 when `need_t`) of all chunks resident, and
+// size the stores.  Falls back to regenerate / recompute when the device does not have the room.
+int plan_store(cgpcm_handle* h, const std::vector<Chunk>& chunks, bool need_t) {
+  h->use_store = false;
+  if (!h->store_opt || chunks.empty()) return 0;
+  const Chunk& last = chunks.back();
+  const long total = last.off + (long)h->nhp * last.nc * last.kwp;
+  auto grow = [&](double*& buf, long& have) -> int {
+    if (have >= total) return 0;
+    if (buf) { cudaFree(buf); buf = nullptr; have = 0; h->storeA_frozen_valid = false; }
+    size_t free_b = 0, tot_b = 0;
+    if (cudaMemGetInfo(&free_b, &tot_b) != cudaSuccess) { cudaGetLastError(); return 1; }
+    if ((double)total * sizeof(double) > 0.45 * (double)free_b) return 1;    // leave room for the other store + scratch
+    if (cudaMalloc(&buf, total * sizeof(double)) != cudaSuccess) { cudaGetLastError(); buf = nullptr; return 1; }
+    have = total;
+    return 0;
+  };
+  if (grow(h->storeA, h->storeA_elems)) return 0;
+  if (need_t && grow(h->storeT, h->storeT_elems)) return 0;
+  h->use_store = true;
+  return 0;
 }
 
 int ensure_ws(cgpcm_handle* h) {
@@ -452,12 +491,14 @@ int axx_sweep(cgpcm_handle* h, const PsiConst& c, const BvnTab& T, bool tangents
   int slices = h->axx_slices;
   dim3 grid(ntiles, slices);
   if (h->n_local > 0) {
-    if (tangents)
-      axx_sum_kernel<true><<<grid, 256, 0, h->st>>>(h->t, (int)h->n_local, h->t_sorted ? 1 : 0, h->tx, h->nx,
-                                                     h->axx_part, h->ld, c, T);
-    else
-      axx_sum_kernel<false><<<grid, 256, 0, h->st>>>(h->t, (int)h->n_local, h->t_sorted ? 1 : 0, h->tx, h->nx,
-                                                      h->axx_part, h->ld, c, T);
+    // pair-hoisted Genz branch: causal model, rho >= 0.925 (rho = gamma / A is always positive here)
+    const bool hoist = c.causal && T.high && T.rho > 0.0 && T.as_ > 0.0 && T.ng == 20;
+#define CG_AXX(TG, HO)                                                                                         \
+  axx_sum_kernel<TG, HO><<<grid, 256, 0, h->st>>>(h->t, (int)h->n_local, h->t_sorted ? 1 : 0, h->tx, h->nx,    \
+                                                   h->axx_part, h->ld, c, T)
+    if (tangents) { if (hoist) CG_AXX(true, true); else CG_AXX(true, false); }
+    else { if (hoist) CG_AXX(false, true); else CG_AXX(false, false); }
+#undef CG_AXX
     L(h);
     axx_reduce_kernel<<<148 * 4, 256, 0, h->st>>>(h->axx_part, slices, tangents ? 4 : 1, h->ld, h->nx, out4);
     L(h);
@@ -468,32 +509,64 @@ int axx_sweep(cgpcm_handle* h, const PsiConst& c, const BvnTab& T, bool tangents
   return 0;
 }
 
-int gen_chunk(cgpcm_handle* h, const PsiConst& c, const Chunk& ch, bool with_y) {
+int gen_chunk(cgpcm_handle* h, const PsiConst& c, const Chunk& ch, bool with_y, double* dstA = nullptr) {
+  if (!dstA) dstA = h->wsA;
   const int threads = std::min(256, round_up(ch.kwp, 32));
   dim3 grid(h->nhp, (ch.nc + AHX_NSUB - 1) / AHX_NSUB);
   if ((int)grid.y > h->y_slices) { h->err = "internal: y_slices too small"; return -1; }
   ahx_gen_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx, h->nx,
-                                              ch.k_lo, ch.kwp, h->wsA, with_y ? h->ypart : nullptr, h->ld,
+                                              ch.k_lo, ch.kwp, dstA, with_y ? h->ypart : nullptr, h->ld,
                                               (long)h->nhp * h->ld, c);
   L(h);
   return 0;
 }
 
-// C (kwp x kwp window of an ld x ld matrix) += sum over splits of a K-split GEMM; symmetric result.
+// Symmetric contractions, accumulated per K-slice over a whole sweep (dgemm_sym.cuh):
+//   sym_begin(slot)            zero the slot's private slice buffers
+//   gemm_splitk_sym(.., slot, win)   slice z of this launch adds its Mr x Mr lower triangle into buffer z at window
+//                              offset win (= k_lo * ld + k_lo for a window of the full matrix)
+//   sym_finish(slot, n, out)   out = sum over slices (fixed order), mirrored to the full symmetric n x n matrix
+int sym_begin(cgpcm_handle* h, int slot) {
+  CK(cudaMemsetAsync(h->symacc[slot], 0, (size_t)SY_MAX_SPLITS * h->ld * h->ld * sizeof(double), h->st));
+  h->sym_used[slot] = 0;
+  return 0;
+}
+
 int gemm_splitk_sym(cgpcm_handle* h, bool a_kc, bool b_kc, int Mr, int K, const double* A, long lda, const double* B,
-                    long ldb, double* Cwin) {
-  int splits = pick_splits(Mr, Mr, K, true);
-  long stride = (long)Mr * Mr;
-  if (splits * stride > h->part_elems) splits = (int)(h->part_elems / stride);
-  if (splits < 1) { h->err = "internal: split-K buffer too small"; return -1; }
+                    long ldb, int slot, long win) {
+  const long l2 = h->ld * h->ld;
+  double* C = h->symacc[slot] + win;
+  if (a_kc == b_kc && dgemm_sym_supported(Mr)) {
+    const int splits = dgemm_sym_splits(K);
+    h->gemm_flops_exec += 2.0 * K * (double)SY_NW * SY_BLK * SY_BLK;
+    h->gemm_flops += 2.0 * K * 0.5 * Mr * (Mr + 1.0);
+    h->gemm_launches++;
+    if (h->profile) cudaEventRecord(prof_event(h), h->st);
+    cudaError_t e = dgemm_sym(h->st, a_kc, Mr, K, A, lda, B, ldb, C, h->ld, l2, 1);
+    if (h->profile) cudaEventRecord(prof_event(h), h->st);
+    L(h);
+    if (e != cudaSuccess) {
+      h->err = std::string("dgemm_sym launch failed: ") + cudaGetErrorString(e);
+      return -2;
+    }
+    h->sym_used[slot] = std::max(h->sym_used[slot], splits);
+    return 0;
+  }
+  int splits = std::min(pick_splits(Mr, Mr, K, true), SY_MAX_SPLITS);
   // number of splits actually used by dgemm (it rounds the k range per split up to whole tiles)
   int kt = (K + G_BK - 1) / G_BK;
   int kt_per = (kt + splits - 1) / splits;
   splits = (kt + kt_per - 1) / kt_per;
-  if (gemm(h, a_kc, b_kc, false, Mr, Mr, K, 1.0, A, lda, B, ldb, 0.0, h->part, Mr, splits, stride, 1)) return -2;
-  long total = (long)Mr * Mr;
-  reduce_partials_kernel<<<(int)((total + 255) / 256), 256, 0, h->st>>>(h->part, stride, splits, Cwin, Mr, Mr, Mr,
-                                                                        h->ld, 1.0, 1);
+  if (gemm(h, a_kc, b_kc, false, Mr, Mr, K, 1.0, A, lda, B, ldb, 1.0, C, h->ld, splits, l2, 1)) return -2;
+  h->sym_used[slot] = std::max(h->sym_used[slot], splits);
+  return 0;
+}
+
+int sym_finish(cgpcm_handle* h, int slot, int n, double* out) {
+  const long total = (long)n * n;
+  reduce_partials_kernel<<<(int)((total + 255) / 256), 256, 0, h->st>>>(h->symacc[slot], h->ld * h->ld,
+                                                                        std::max(1, h->sym_used[slot]), out, n, n, h->ld,
+                                                                        h->ld, 0.0, 1);
   L(h);
   return 0;
 }
@@ -508,29 +581,40 @@ int right_mul_sym(cgpcm_handle* h, const double* X, const double* W, const Chunk
 
 // Forward sweep over chunks: C1 += A^T (H A), and when `full`: Q += A iKx A^T, Y += sum y A.
 int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& chunks, const double* Hm,
-                  const double* iKx, bool full) {
+                  const double* iKx, bool full, bool keep_t) {
   zero(h, h->M(M_C1), h->ld * h->ld);
+  if (sym_begin(h, 0)) return -2;
   if (full) {
     zero(h, h->M(M_Q), h->ld * h->ld);
+    if (sym_begin(h, 1)) return -2;
     zero(h, h->ypart, (long)h->y_slices * h->nhp * h->ld);
   }
+  // with the sweep stores the Ahx block (and T1 when the backward sweep will need it) go straight to their
+  // resident slots; the frozen regime's blocks do not change between evaluations and are generated once
+  const bool st = h->use_store;
+  const bool have_a = st && !full && h->storeA_frozen_valid;
   for (const Chunk& ch : chunks) {
-    if (gen_chunk(h, c, ch, full)) return -2;
+    double* Ab = st ? h->storeA + ch.off : h->wsA;
+    double* Tb = (st && keep_t) ? h->storeT + ch.off : h->wsT;
+    if (!have_a && gen_chunk(h, c, ch, full, Ab)) return -2;
     const long cols = (long)ch.nc * ch.kwp;
     // T1[i][(n,k)] = sum_j H[i][j] A[j][(n,k)]
-    if (gemm(h, true, false, false, h->nhp, (int)cols, h->nhp, 1.0, Hm, h->ld, h->wsA, cols, 0.0, h->wsT, cols)) return -2;
+    if (gemm(h, true, false, false, h->nhp, (int)cols, h->nhp, 1.0, Hm, h->ld, Ab, cols, 0.0, Tb, cols)) return -2;
     // C1[k][l] += sum_(i,n) A[(i,n)][k] T1[(i,n)][l]
-    if (gemm_splitk_sym(h, false, false, ch.kwp, h->nhp * ch.nc, h->wsA, ch.kwp, h->wsT, ch.kwp,
-                        h->M(M_C1) + (long)ch.k_lo * h->ld + ch.k_lo)) return -2;
+    if (gemm_splitk_sym(h, false, false, ch.kwp, h->nhp * ch.nc, Ab, ch.kwp, Tb, ch.kwp, 0,
+                        (long)ch.k_lo * h->ld + ch.k_lo)) return -2;
     if (full) {
       // V[(i,n)][l] = sum_k A[(i,n)][k] iKx[k][l]   (window block of iKx)
       // (computed as V^T = iKx A2^T with the transposed store: 200-row tiles split 104 + 96 instead of 128 + 72)
-      if (right_mul_sym(h, h->wsA, iKx, ch, h->wsV)) return -2;
+      if (right_mul_sym(h, Ab, iKx, ch, h->wsV)) return -2;
       // Q[i][j] += sum_(n,k) A[i][(n,k)] V[j][(n,k)]
-      if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsA, cols, h->wsV, cols, h->M(M_Q))) return -2;
+      if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, Ab, cols, h->wsV, cols, 1, 0)) return -2;
     }
   }
+  if (st && !full) h->storeA_frozen_valid = true;
+  if (sym_finish(h, 0, h->nxp, h->M(M_C1))) return -2;
   if (full) {
+    if (sym_finish(h, 1, h->nhp, h->M(M_Q))) return -2;
     long total = (long)h->nhp * h->ld;
     ypart_reduce_kernel<<<148, 256, 0, h->st>>>(h->ypart, h->y_slices, total, total, h->M(M_Y));
     L(h);
@@ -543,6 +627,7 @@ int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& 
 int backward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& chunks, const double* Hm,
                    bool full, double* g3) {
   zero(h, h->M(M_HBAR), h->ld * h->ld);
+  if (sym_begin(h, 0)) return -2;
   long gneed = 0;
   for (const Chunk& ch : chunks) gneed = std::max<long>(gneed, (long)h->nhp * ((ch.nc + AHX_NSUB - 1) / AHX_NSUB));
   if (full) {
@@ -554,25 +639,29 @@ int backward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>&
     }
     zero(h, h->gpart, h->gpart_elems);
   }
+  const bool st = h->use_store;
   for (const Chunk& ch : chunks) {
-    if (gen_chunk(h, c, ch, false)) return -2;
+    const double* Ab = st ? h->storeA + ch.off : h->wsA;
+    if (!st && gen_chunk(h, c, ch, false)) return -2;
     const long cols = (long)ch.nc * ch.kwp;
     // U1[(i,n)][l] = sum_k A[(i,n)][k] C1bar[k][l]
-    if (right_mul_sym(h, h->wsA, h->M(M_C1BAR), ch, h->wsV)) return -2;
+    if (right_mul_sym(h, Ab, h->M(M_C1BAR), ch, h->wsV)) return -2;
     // Hbar[i][j] += sum_(n,l) U1[i][(n,l)] A[j][(n,l)]
-    if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsV, cols, h->wsA, cols, h->M(M_HBAR))) return -2;
+    if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsV, cols, Ab, cols, 0, 0)) return -2;
     if (full) {
-      // T1 = H A ;  Abar = T1 Wx  (window block)
-      if (gemm(h, true, false, false, h->nhp, (int)cols, h->nhp, 1.0, Hm, h->ld, h->wsA, cols, 0.0, h->wsT, cols)) return -2;
-      if (right_mul_sym(h, h->wsT, h->M(M_WX), ch, h->wsV)) return -2;
+      // T1 = H A (kept from the forward sweep when stored) ;  Abar = T1 Wx  (window block)
+      const double* Tb = st ? h->storeT + ch.off : h->wsT;
+      if (!st && gemm(h, true, false, false, h->nhp, (int)cols, h->nhp, 1.0, Hm, h->ld, Ab, cols, 0.0, h->wsT, cols)) return -2;
+      if (right_mul_sym(h, Tb, h->M(M_WX), ch, h->wsV)) return -2;
       const int threads = std::min(256, round_up(ch.kwp, 32));
       dim3 grid(h->nhp, (ch.nc + AHX_NSUB - 1) / AHX_NSUB);
       ahx_dot_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx,
-                                                  h->nx, ch.k_lo, ch.kwp, h->wsA, h->wsV, h->M(M_YBAR), h->ld, h->gpart,
+                                                  h->nx, ch.k_lo, ch.kwp, Ab, h->wsV, h->M(M_YBAR), h->ld, h->gpart,
                                                   c);
       L(h);
     }
   }
+  if (sym_finish(h, 0, h->nhp, h->M(M_HBAR))) return -2;
   if (full) {
     sum3_kernel<<<1, 1024, 0, h->st>>>(h->gpart, gneed, g3);
     L(h);
@@ -652,6 +741,8 @@ int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int
   if (cudaMalloc(&h->gvar_d, np * sizeof(double)) != cudaSuccess) return fail(-2);
   h->part_elems = std::max<long>(320 * 64 * 64, 100 * l2);
   if (cudaMalloc(&h->part, h->part_elems * sizeof(double)) != cudaSuccess) return fail(-2);
+  for (int k = 0; k < 2; ++k)
+    if (cudaMalloc(&h->symacc[k], (size_t)SY_MAX_SPLITS * l2 * sizeof(double)) != cudaSuccess) return fail(-2);
   h->axx_slices = 32;
   h->axx_part_elems = (long)h->axx_slices * 4 * l2;
   if (cudaMalloc(&h->axx_part, h->axx_part_elems * sizeof(double)) != cudaSuccess) return fail(-2);
@@ -669,7 +760,7 @@ int cgpcm_destroy(cgpcm_handle* h) {
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->comm && h->own_comm && nccl().ok) nccl().CommDestroy(h->comm);
   double* ptrs[] = {h->t, h->y, h->th, h->tx, h->mats, h->vecs, h->sc, h->params_d, h->gvar_d, h->wsA, h->wsT,
-                    h->wsV, h->part, h->axx_part, h->ypart, h->gpart};
+                    h->wsV, h->part, h->axx_part, h->ypart, h->gpart, h->symacc[0], h->symacc[1], h->storeA, h->storeT};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   if (h->info) cudaFree(h->info);
@@ -718,6 +809,7 @@ int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
   if (!strcmp(key, "chunk")) {
     if (value < 8 || value > (1 << 20)) { h->err = "chunk out of range"; return -1; }
     h->chunk = round_up((int)value, 32);
+    h->storeA_frozen_valid = false;
     return 0;
   }
   if (!strcmp(key, "profile")) {
@@ -727,6 +819,18 @@ int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
   if (!strcmp(key, "cull")) {
     if (value < 0) { h->err = "cull must be >= 0"; return -1; }
     h->cull = value;
+    h->storeA_frozen_valid = false;
+    return 0;
+  }
+  if (!strcmp(key, "store")) {
+    h->store_opt = value != 0.0;
+    h->storeA_frozen_valid = false;
+    if (!h->store_opt) {
+      if (h->storeA) cudaFree(h->storeA);
+      if (h->storeT) cudaFree(h->storeT);
+      h->storeA = h->storeT = nullptr;
+      h->storeA_elems = h->storeT_elems = 0;
+    }
     return 0;
   }
   h->err = std::string("unknown option ") + key;
@@ -745,6 +849,7 @@ int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_
   if (!h->tx) CK(cudaMalloc(&h->tx, h->ld * sizeof(double)));
   h->n_local = n_local;
   h->frozen = false;
+  h->storeA_frozen_valid = false;
   const long na = std::max<long>(n_local, 1);
   CK(cudaMalloc(&h->t, na * sizeof(double)));
   CK(cudaMalloc(&h->y, na * sizeof(double)));
@@ -915,6 +1020,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   h->launches = 0;
   h->pev_used = 0;
   h->gemm_flops = 0.0;
+  h->gemm_flops_exec = 0.0;
   h->gemm_launches = 0;
 
   PsiConst c;
@@ -975,7 +1081,10 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     if (axx_sweep(h, c, T, !freeze, h->M(M_AXX0))) return -2;
   }
   CK(cudaEventRecord(h->ev[2], st));
-  if (forward_sweep(h, ca, chunks, Hm, h->M(M_IKX), full)) return -2;
+  const bool want_hyp = full && !freeze && grad && (grad_mask & (CGPCM_GRAD_ALPHA | CGPCM_GRAD_GAMMA | CGPCM_GRAD_OMEGA));
+  if (plan_store(h, chunks, want_hyp)) return -2;
+  if (full) h->storeA_frozen_valid = false;      // a full-regime sweep overwrites the resident Ahx blocks
+  if (forward_sweep(h, ca, chunks, Hm, h->M(M_IKX), full, want_hyp)) return -2;
   // tail scalars [n, sum_y2]
   {
     double tail[2] = {(double)h->n_local, h->sum_y2_local};
@@ -1029,6 +1138,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     h->f_sum_b = Ng * a - Ng * hs[S_TR_IKH_AHH] - hs[S_TR_IKX_AXX] + hs[S_TR_IKH_Q];
     h->fc = c;
     h->frozen = true;
+    h->storeA_frozen_valid = h->use_store;       // the blocks just generated are the frozen regime's
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     return 0;
@@ -1100,7 +1210,6 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   CK(cudaEventRecord(h->ev[4], st));
 
   // ---- 5. backward sweep
-  const bool want_hyp = full && (grad_mask & (CGPCM_GRAD_ALPHA | CGPCM_GRAD_GAMMA | CGPCM_GRAD_OMEGA));
   const bool want_q = grad_mask & (CGPCM_GRAD_MU_U | CGPCM_GRAD_VAR_U);
   const bool want_grad = grad && grad_mask;
   if (want_grad && (want_hyp || want_q)) {
@@ -1370,6 +1479,7 @@ int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_
     h->timing[6] = (double)h->launches;
     h->timing[7] = h->gemm_flops;
     h->timing[8] = (double)h->gemm_launches;
+    h->timing[9] = h->gemm_flops_exec;
     if (is_device_ptr(elbo)) cudaMemcpy(elbo, &e, sizeof e, cudaMemcpyHostToDevice); else *elbo = e;
     if (terms) { if (is_device_ptr(terms)) cudaMemcpy(terms, tm, sizeof tm, cudaMemcpyHostToDevice); else memcpy(terms, tm, sizeof tm); }
   }
@@ -1421,6 +1531,26 @@ int cgpcm_dgemm(int a_kc, int b_kc, int c_tr, int M, int N, int K, double alpha,
                         c_split_stride, lower_only);
   if (e != cudaSuccess) return -2;
   return cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess ? 0 : -2;
+}
+
+int cgpcm_dgemm_sym(int kc, int M, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                    int64_t ldc, double* work, void* stream) {
+  if (!A || !B || !C || K < 0 || (K % 2) || (lda % 2) || (ldb % 2) || ldc < M) return -1;
+  if (!dgemm_sym_supported(M)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = dgemm_sym_splits(K);
+  double* acc = work;
+  const long l2 = (long)M * M;
+  if (!acc && cudaMalloc(&acc, (size_t)splits * l2 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return -2; }
+  int rc = 0;
+  if (dgemm_sym(st, kc != 0, M, K, A, lda, B, ldb, acc, M, l2, 0) != cudaSuccess) rc = -2;
+  if (!rc) {
+    reduce_partials_kernel<<<(int)((l2 + 255) / 256), 256, 0, st>>>(acc, l2, splits, C, M, M, M, ldc, 0.0, 1);
+    if (cudaGetLastError() != cudaSuccess) rc = -2;
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess) rc = -2;
+  if (!work) cudaFree(acc);
+  return rc;
 }
 
 int cgpcm_cholinv(double* A, double* Ainv, double* logdet, int n, int64_t ld, int* info_host) {

@@ -1,0 +1,239 @@
+// Symmetric-output split-K contraction on the FP64 tensor path (DMMA m8n8k4) for sm_100a:
+//
+//     C[z] (+)= op(A)[M x Kz] * op(B)[Kz x M]      lower triangle only, one K-slice z per CTA
+//
+// This is the shape of three of the per-chunk contractions of the VCGPCM path, whose results are symmetric
+// M x M matrices (M = nh or nx = 200 at the target) summed over an enormous K (= nh * n_chunk or
+// n_chunk * nx ~ 1e5):  C1 = sum_n A_n^T (H A_n),  Q = sum_n A_n (iKx A_n^T),  Hbar = sum_n (A_n C1bar) A_n^T
+// (src/core/cgpcm.py:255-267,473-475 and the adjoint of SURVEY.md App. D).
+//
+// Tiling: the output is cut into 40 x 40 warp blocks (5 x 5 DMMA tiles: 10 fragment loads feed 25 DMMAs);
+// only the 15 blocks of the lower triangle exist, one warp each => one CTA owns the whole output for its
+// K-slice, and the grid is the K-split (one CTA per SM, one wave).  Both operand panels (M x 16 k each) are
+// staged in shared memory by a 3-stage cp.async pipeline (3 x 64 KB) fed by a 16th, producer warp and shared
+// by the 15 consumer warps.  Strides are == 4 (mod 8) doubles: every fragment load is bank-conflict free.
+// Each K-slice accumulates into its own private M x M buffer across all launches of a sweep (C[z] += ...),
+// and one fixed-order reduction at the end of the sweep adds the slices: deterministic, and the per-launch
+// split-K reduction disappears.
+#pragma once
+#include "dgemm_dmma.cuh"
+
+namespace cg {
+
+constexpr int SY_BLK = 40;                 // rows / columns per warp block
+constexpr int SY_G = 5;                    // warp-block rows
+constexpr int SY_NW = SY_G * (SY_G + 1) / 2;
+constexpr int SY_NT = (SY_NW + 1) * 32;    // 512: 15 consumer warps + 1 producer warp
+constexpr int SY_MP = SY_G * SY_BLK;       // 200: largest supported order
+constexpr int SY_BK = 16;
+constexpr int SY_STAGES = 3;
+constexpr int SY_PANEL = SY_MP * (SY_BK + 4);   // doubles (>= SY_BK * (SY_MP + 4))
+constexpr int SY_STAGE = 2 * SY_PANEL;
+constexpr int SY_SMEM_BYTES = SY_STAGES * SY_STAGE * 8;
+constexpr int SY_MAX_SPLITS = 148;
+
+struct SymArgs {
+  const double* A;
+  const double* B;
+  double* C;             // slice z writes C + z * c_split_stride (leading dimension ldc)
+  int M, K;
+  long lda, ldb, ldc;
+  long c_split_stride;
+  int k_per_split;       // multiple of SY_BK
+  int accumulate;        // 1: C[z] += result, 0: C[z] = result
+};
+
+// KC = true : A(m,k) at A[m*lda + k], B(n,k) at B[n*ldb + k]   (k contiguous)
+// KC = false: A(m,k) at A[k*lda + m], B(n,k) at B[k*ldb + n]   (m / n contiguous)
+//
+// Warp roles: warps 0..14 are consumers (one 40 x 40 output block each: 25 accumulator pairs + 10 fragments,
+// no loader state, so they fit the 128-register budget of a 512-thread CTA); warp 15 is the producer and
+// issues every cp.async of both panels.  One __syncthreads per k-tile hands a filled stage to the consumers
+// and a drained one back to the producer.
+template <bool KC>
+__global__ void __launch_bounds__(SY_NT, 1) dgemm_sym_kernel(const SymArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kbeg = blockIdx.x * g.k_per_split;
+  const int kend = min(g.K, kbeg + g.k_per_split);
+  if (kend <= kbeg) return;
+  const int ktiles = (kend - kbeg + SY_BK - 1) / SY_BK;
+
+  if (warp == SY_NW) {
+    // ------------------------------------------------------------------ producer warp
+    const double* srcA;
+    const double* srcB;
+    int dst, kofs;
+    if (KC) {            // one instruction = 4 panel rows x 128 B
+      const int r0 = lane >> 3, kc = (lane & 7) * 2;
+      srcA = g.A + (long)r0 * g.lda + kbeg + kc;
+      srcB = g.B + (long)r0 * g.ldb + kbeg + kc;
+      dst = r0 * (SY_BK + 4) + kc;
+      kofs = kc;
+    } else {             // one instruction = 32 chunks (64 columns) of one k row
+      srcA = g.A + (long)kbeg * g.lda + lane * 2;
+      srcB = g.B + (long)kbeg * g.ldb + lane * 2;
+      dst = lane * 2;
+      kofs = 0;
+    }
+    int kleft = kend - kbeg;
+    auto issue = [&](int stage) {
+      double* base = smem + stage * SY_STAGE + dst;
+      if (KC) {
+        const bool kok = kofs < kleft;
+        const int r0 = lane >> 3;
+#pragma unroll 10
+        for (int r = 0; r < SY_MP / 4; ++r) {
+          const bool v = kok && r * 4 + r0 < g.M;
+          cp_async16(base + r * 4 * (SY_BK + 4), v ? srcA + (long)r * 4 * g.lda : g.A, v);
+          cp_async16(base + SY_PANEL + r * 4 * (SY_BK + 4), v ? srcB + (long)r * 4 * g.ldb : g.B, v);
+        }
+        srcA += SY_BK;
+        srcB += SY_BK;
+      } else {
+#pragma unroll 4
+        for (int kk = 0; kk < SY_BK; ++kk) {
+          const bool kok = kk < kleft;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int m = (q * 32 + lane) * 2;
+            if (m < SY_MP) {
+              const bool v = kok && m < g.M;
+              cp_async16(base + kk * (SY_MP + 4) + q * 64, v ? srcA + (long)kk * g.lda + q * 64 : g.A, v);
+              cp_async16(base + SY_PANEL + kk * (SY_MP + 4) + q * 64, v ? srcB + (long)kk * g.ldb + q * 64 : g.B, v);
+            }
+          }
+        }
+        srcA += (long)SY_BK * g.lda;
+        srcB += (long)SY_BK * g.ldb;
+      }
+      kleft -= SY_BK;
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < SY_STAGES - 1; ++s0) {
+      if (s0 < ktiles) issue(s0);
+      cp_async_commit();
+    }
+    int stage = 0;
+    for (int kt = 0; kt < ktiles; ++kt) {
+      cp_async_wait<SY_STAGES - 2>();
+      __syncthreads();
+      int st2 = stage + SY_STAGES - 1;
+      if (st2 >= SY_STAGES) st2 -= SY_STAGES;
+      if (kt + SY_STAGES - 1 < ktiles) issue(st2);
+      cp_async_commit();
+      if (++stage == SY_STAGES) stage = 0;
+    }
+    cp_async_wait<0>();
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer warps
+  const int grp = lane >> 2, tig = lane & 3;
+  const int gi = warp >= 10 ? 4 : warp >= 6 ? 3 : warp >= 3 ? 2 : warp >= 1 ? 1 : 0;
+  const int gj = warp - gi * (gi + 1) / 2;
+  const int a_off = KC ? (gi * SY_BLK + grp) * (SY_BK + 4) + tig : tig * (SY_MP + 4) + gi * SY_BLK + grp;
+  const int b_off = SY_PANEL + (KC ? (gj * SY_BLK + grp) * (SY_BK + 4) + tig : tig * (SY_MP + 4) + gj * SY_BLK + grp);
+
+  double acc[5][5][2];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // Fragments are single-buffered (25 accumulator pairs leave no room for a second set).  The 5 x 5 DMMA block
+  // is walked row-major on even k4 steps and column-major on odd ones, and every fragment of the next step is
+  // loaded as soon as its register dies: each load then has at least four DMMAs of this warp (and all the
+  // DMMAs of the SMSP's other warps) between issue and first use.
+  auto ldf = [&](const double* P, int k4, int x) {
+    return KC ? P[x * 8 * (SY_BK + 4) + k4 * 4] : P[k4 * 4 * (SY_MP + 4) + x * 8];
+  };
+
+  int stage = 0;
+  for (int kt = 0; kt < ktiles; ++kt) {
+    __syncthreads();
+    const double* Ap = smem + stage * SY_STAGE + a_off;
+    const double* Bp = smem + stage * SY_STAGE + b_off;
+    double fa[5], fb[5];
+#pragma unroll
+    for (int x = 0; x < 5; ++x) { fa[x] = ldf(Ap, 0, x); fb[x] = ldf(Bp, 0, x); }
+#pragma unroll
+    for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
+      const bool more = k4 + 1 < SY_BK / 4;
+      if ((k4 & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            if (more && i == 4) fb[j] = ldf(Bp, k4 + 1, j);
+          }
+          if (more) fa[i] = ldf(Ap, k4 + 1, i);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            if (more && j == 4) fa[i] = ldf(Ap, k4 + 1, i);
+          }
+          if (more) fb[j] = ldf(Bp, k4 + 1, j);
+        }
+      }
+    }
+    if (++stage == SY_STAGES) stage = 0;
+  }
+
+  double* C = g.C + (long)blockIdx.x * g.c_split_stride;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int row = gi * SY_BLK + i * 8 + grp;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int col = gj * SY_BLK + j * 8 + tig * 2;
+      if (col >= g.M) continue;
+      double2* p = reinterpret_cast<double2*>(C + (long)row * g.ldc + col);
+      double v0 = acc[i][j][0], v1 = acc[i][j][1];
+      if (g.accumulate) {
+        const double2 o = *p;
+        v0 += o.x;
+        v1 += o.y;
+      }
+      *p = make_double2(v0, v1);
+    }
+  }
+}
+
+inline bool dgemm_sym_supported(int M) { return M > 160 && M <= SY_MP && (M % 8) == 0; }
+
+// Number of K-slices a launch with this K uses (<= SY_MAX_SPLITS).
+inline int dgemm_sym_splits(int K, int* k_per_split = nullptr) {
+  const int kt = (K + SY_BK - 1) / SY_BK;
+  int splits = kt < SY_MAX_SPLITS ? kt : SY_MAX_SPLITS;
+  if (splits < 1) splits = 1;
+  const int kt_per = (kt + splits - 1) / splits;
+  if (k_per_split) *k_per_split = kt_per * SY_BK;
+  return (kt + kt_per - 1) / kt_per;
+}
+
+inline cudaError_t dgemm_sym(cudaStream_t st, bool kc, int M, int K, const double* A, long lda, const double* B,
+                             long ldb, double* C, long ldc, long c_split_stride, int accumulate) {
+  if (M <= 0 || K <= 0) return cudaSuccess;
+  SymArgs g;
+  g.A = A; g.B = B; g.C = C; g.M = M; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.c_split_stride = c_split_stride; g.accumulate = accumulate;
+  const int splits = dgemm_sym_splits(K, &g.k_per_split);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute((const void*)dgemm_sym_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES);
+    cudaFuncSetAttribute((const void*)dgemm_sym_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES);
+    attr_done = true;
+  }
+  if (kc) dgemm_sym_kernel<true><<<splits, SY_NT, SY_SMEM_BYTES, st>>>(g);
+  else dgemm_sym_kernel<false><<<splits, SY_NT, SY_SMEM_BYTES, st>>>(g);
+  return cudaGetLastError();
+}
+
+}  // namespace cg

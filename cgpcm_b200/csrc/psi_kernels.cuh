@@ -83,8 +83,8 @@ constexpr int AXX_TILE = 16;
 // of the tile's observation range and *stores* its lower-triangle partial sums (no zero-init needed).
 // When t is sorted the observation range of a (k, l) tile is cut down by binary search to the
 // observations within r_xx of both the tile's tx_k and tx_l ranges; everything outside is culled anyway.
-template <bool TANGENTS>
-__global__ void __launch_bounds__(256) axx_sum_kernel(const double* __restrict__ t, int n_obs, int sorted,
+template <bool TANGENTS, bool HOIST>
+__global__ void __launch_bounds__(256, HOIST ? 2 : 3) axx_sum_kernel(const double* __restrict__ t, int n_obs, int sorted,
                                                       const double* __restrict__ tx, int nx,
                                                       double* __restrict__ part, long ld, const PsiConst c,
                                                       const BvnTab T) {
@@ -115,6 +115,10 @@ __global__ void __launch_bounds__(256) axx_sum_kernel(const double* __restrict__
   }
   const double txk = tx[k], txl = tx[l];
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  // HOIST (causal, rho >= 0.925): the pair constants of the Genz high-correlation branch (bvn.cuh)
+  __shared__ double sP[HOIST ? 20 : 1][BVN_PAIR_THREADS];
+  BvnPair R;
+  if (HOIST) bvn_pair_init((c.p - c.q) * (txk - txl), T, R, sP);
   for (int n = n_lo + blockIdx.y; n < n_hi; n += gridDim.y) {
     const double tn = __ldg(t + n);
     const double dk = tn - txk, dl = tn - txl;
@@ -133,10 +137,15 @@ __global__ void __launch_bounds__(256) axx_sum_kernel(const double* __restrict__
     }
     const double x1 = c.p * dk + c.q * dl, x2 = c.q * dk + c.p * dl;
     if (!TANGENTS) {
-      s0 += env * bvnd_tab(-x1, -x2, T);
+      s0 += env * (HOIST ? bvn_cdf_pair(x1, x2, T, R, sP) : bvnd_tab(-x1, -x2, T));
     } else {
       double cdf, d1, d2, dr;
-      bvn_cdf_grad_tab(x1, x2, T, cdf, d1, d2, dr);
+      if (HOIST) {
+        cdf = bvn_cdf_pair(x1, x2, T, R, sP);
+        bvn_partials_tab(x1, x2, T, d1, d2, dr);
+      } else {
+        bvn_cdf_grad_tab(x1, x2, T, cdf, d1, d2, dr);
+      }
       const double V = env * cdf;
       s0 += V;
       s1 += V * (-c.dg1[0] * q2 + c.dg2[0] * pr - c.dhalf_logdet[0]) +

@@ -67,7 +67,9 @@ int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_
 
 /* Tuning knobs: "chunk" (observations per contraction chunk), "cull" (0 = dense; e > 0 = Psi entries whose
  * Gaussian envelope is below exp(-e) are exactly 0 and whole windows of them are skipped; default 80),
- * "profile" (1 = CUDA events around every GEMM launch so that cgpcm_last_timing reports their sum). */
+ * "profile" (1 = CUDA events around every GEMM launch so that cgpcm_last_timing reports their sum),
+ * "store" (1 = default: keep the Ahx blocks and H*Ahx of the forward sweep resident in HBM for the backward sweep
+ * when they fit -- 2 x 8 nh N nx bytes; 0 = always regenerate / recompute per chunk). */
 int cgpcm_set_option(cgpcm_handle* h, const char* key, double value);
 
 /* Psi statistics at hyper-parameters hyp = {alpha, gamma, omega}: what `sess.run(mats[...])` returns
@@ -89,8 +91,9 @@ int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_
 /* Timing of the last cgpcm_elbo_grad / cgpcm_psi on the handle's stream (CUDA events, ms):
  * out[0] total device time, out[1] forward sweep, out[2] backward sweep, out[3] M x M algebra,
  * out[4] Axx kernel, out[5] contraction GEMM kernels (exact sum with option "profile", else the sweeps
- * minus the Axx kernel), out[6] number of kernel launches, out[7] FP64 flops of the CTA tiles those GEMM
- * launches computed, out[8] number of GEMM launches; out[9..11] reserved. */
+ * minus the Axx kernel), out[6] number of kernel launches, out[7] algorithmic FP64 flops of those GEMM
+ * launches (2 K M N; symmetric results K M (M + 1)), out[8] number of GEMM launches, out[9] flops of the CTA /
+ * warp tiles the launches actually computed; out[10..11] reserved. */
 int cgpcm_last_timing(cgpcm_handle* h, double out[12]);
 
 /* The reference's native op: Phi_2(x1, x2; rho) element-wise on three FP64 vectors of length n
@@ -103,6 +106,12 @@ int cgpcm_bvn_cdf(const double* x1, const double* x2, const double* rho, double*
 int cgpcm_dgemm(int a_kc, int b_kc, int c_tr, int M, int N, int K, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int splits,
                 int64_t c_split_stride, int lower_only, void* stream);
+/* cgpcm_dgemm_sym: the symmetric-output split-K contraction of dgemm_sym.cuh, C = op(A) op(B)^T (M x M, full
+ * symmetric matrix written; 160 < M <= 200, M % 8 == 0).  kc = 1: A[m*lda + k], B[n*ldb + k]; kc = 0: A[k*lda + m],
+ * B[k*ldb + n].  The result is only meaningful when the product is symmetric (the lower triangle is mirrored).
+ * work: NULL or a device buffer of 148 * M * M doubles for the K-slice partial results. */
+int cgpcm_dgemm_sym(int kc, int M, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                    int64_t ldc, double* work, void* stream);
 int cgpcm_cholinv(double* A, double* Ainv, double* logdet, int n, int64_t ld, int* info_host);
 
 #ifdef __cplusplus

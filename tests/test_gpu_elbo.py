@@ -96,6 +96,32 @@ def test_chunking_and_culling_do_not_change_the_result(name):
         assert np.abs(got[2] - ref[2]).max() <= 1e-10 * np.abs(ref[2]).max(), opts
 
 
+@pytest.mark.parametrize('name', ['toy_small', 'sweep_wide'])
+def test_sweep_stores_do_not_change_the_result(name):
+    """Option "store" (Ahx blocks and H*Ahx kept resident for the backward sweep; the frozen regime's blocks kept
+    between evaluations) against regenerate / recompute: the same bits."""
+    c = make_case(name)
+    outs = []
+    for store in (1, 0):
+        eng = _engine(c, chunk=64)
+        eng.set_option('store', store)
+        full = eng.elbo_grad(c['params'], reg=c['reg'])
+        eng.precompute(*c['hyp'], reg=c['reg'])
+        p = c['params'].copy()
+        p[5:] *= 1.02
+        fr1 = eng.elbo_grad(p, mode=MODE_FROZEN, reg=c['reg'])
+        fr2 = eng.elbo_grad(p, mode=MODE_FROZEN, reg=c['reg'])          # second call reuses the resident blocks
+        again = eng.elbo_grad(c['params'], reg=c['reg'])                 # full regime overwrites them
+        fr3 = eng.elbo_grad(p, mode=MODE_FROZEN, reg=c['reg'])          # ... and the frozen regime regenerates
+        assert fr1[0] == fr2[0] == fr3[0] and np.array_equal(fr1[2], fr2[2]) and np.array_equal(fr1[2], fr3[2])
+        assert again[0] == full[0] and np.array_equal(again[2], full[2])
+        outs.append((full, fr1))
+    for a, b in zip(outs[0], outs[1]):
+        assert a[0] == b[0]
+        np.testing.assert_array_equal(a[1], b[1])
+        np.testing.assert_array_equal(a[2], b[2])
+
+
 def test_device_resident_buffers():
     c = make_case('toy_small')
     dev = lambda x: torch.tensor(x, dtype=torch.float64, device='cuda')

@@ -86,6 +86,30 @@ def test_dgemm_split_k_and_lower_only():
     np.testing.assert_allclose(np.tril(low), np.tril(A @ A.T), atol=1e-10)
 
 
+@pytest.mark.parametrize('kc', [1, 0])
+@pytest.mark.parametrize('M,K', [(200, 4096), (200, 50), (168, 1234), (184, 16 * 148 * 3 + 6)])
+def test_dgemm_sym(kc, M, K):
+    """Symmetric-output split-K DMMA kernel (dgemm_sym.cuh): C = X S X^T with S symmetric, computed as A B^T with
+    A = X, B = X S, against numpy; ragged K, orders below the 200-row panel, both operand layouts."""
+    rng = np.random.default_rng(M + K + kc)
+    X = rng.standard_normal((M, K))
+    d = rng.uniform(.5, 2., K)
+    Bm = X * d                                   # (X D)  ->  X (X D)^T = X D X^T is symmetric
+    want = X @ Bm.T
+    dev = lambda x: torch.tensor(np.ascontiguousarray(x), dtype=torch.float64, device='cuda')
+    if kc:
+        As, Bs, lda = dev(X), dev(Bm), K
+    else:
+        As, Bs, lda = dev(X.T), dev(Bm.T), M
+    C = torch.full((M, M), np.nan, dtype=torch.float64, device='cuda')
+    rc = _lib.lib().cgpcm_dgemm_sym(kc, M, K, As.data_ptr(), lda, Bs.data_ptr(), lda, C.data_ptr(), M, None, None)
+    assert rc == 0
+    got = C.cpu().numpy()
+    scale = np.abs(X) @ np.abs(Bm).T
+    assert np.all(np.abs(got - want) <= 4e-15 * scale + 1e-300)
+    assert np.array_equal(got, got.T)
+
+
 @pytest.mark.parametrize('n', [1, 5, 32, 33, 41, 150, 200, 301])
 def test_cholinv(n):
     rng = np.random.default_rng(n)

@@ -37,3 +37,23 @@ for name, (akc, bkc, ctr, M, N, K, a, lda, b, ldb, c, ldc, splits, stride, lower
         best = min(best, ev0.elapsed_time(ev1))
     flops = 2.0 * M * N * K * (0.75 if lower else 1.0)
     print('%-52s %8.3f ms  %6.2f TFLOP/s' % (name, best, flops / best / 1e9), flush=True)
+
+# the symmetric-output kernel (dgemm_sym.cuh) on the same two contractions
+C = torch.empty(nh, nh, dtype=torch.float64, device=dev)
+work = torch.empty(148, nh, nh, dtype=torch.float64, device=dev)
+for name, kc, K, lda in [('Q   sym kernel (k contiguous), 200 x 200, K = nc*200', 1, cols, cols),
+                         ('C1  sym kernel (m contiguous), 200 x 200, K = 200*nc', 0, nh * nc, nx)]:
+    def run():
+        rc = L.cgpcm_dgemm_sym(kc, nh, K, A.data_ptr(), lda, T.data_ptr(), lda, C.data_ptr(), nh, work.data_ptr(), None)
+        assert rc == 0
+    run()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(reps):
+        ev0.record()
+        run()
+        ev1.record()
+        torch.cuda.synchronize()
+        best = min(best, ev0.elapsed_time(ev1))
+    flops = 2.0 * K * nh * (nh + 1) / 2
+    print('%-52s %8.3f ms  %6.2f TFLOP/s (lower triangle; incl. the reduction of the 148 K-slices)' % (name, best, flops / best / 1e9), flush=True)
