@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "../../include/cgpcm_b200.h"
+#include "dgemm_sl.cuh"
 #include "dgemm_sym.cuh"
 #include "linalg.cuh"
 #include "psi_kernels.cuh"
@@ -145,6 +146,8 @@ struct cgpcm_handle {
   // sweep stores (option "store", default on when they fit): the Ahx blocks of all chunks (storeA) and
   // T1 = H A of the forward sweep (storeT) stay resident in HBM for the backward sweep instead of being
   // regenerated / recomputed -- 8 nhp N nx bytes each (32 GB at N = 1e5, M = 200; the B200 has 180 GB).
+  int sl_opt = 1;              // 1: contractions with a small left operand run on the persistent kernel (dgemm_sl.cuh)
+  int sms = 148;
   int store_opt = 1;
   double *storeA = nullptr, *storeT = nullptr;
   long storeA_elems = 0, storeT_elems = 0;
@@ -365,7 +368,14 @@ int gemm(cgpcm_handle* h, bool a_kc, bool b_kc, bool c_tr, int Mr, int Nr, int K
     h->gemm_launches++;
   }
   if (h->profile) cudaEventRecord(prof_event(h), h->st);
-  cudaError_t e = dgemm(h->st, a_kc, b_kc, c_tr, Mr, Nr, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, stride, lower);
+  cudaError_t e;
+  // (the k-contiguous / transposed layout of dgemm_sl needs 64 bulk copies of 128 B per stage and is slower than the
+  // tiled kernel: only option sl = 2 routes it there)
+  if (h->sl_opt && a_kc && b_kc == c_tr && (!b_kc || h->sl_opt == 2) && splits <= 1 && !lower && beta == 0.0 &&
+      dgemm_sl_supported(Mr, Nr, K))
+    e = dgemm_sl(h->st, b_kc, Mr, Nr, K, alpha, A, lda, B, ldb, C, ldc, h->sms);
+  else
+    e = dgemm(h->st, a_kc, b_kc, c_tr, Mr, Nr, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, stride, lower);
   if (h->profile) cudaEventRecord(prof_event(h), h->st);
   L(h);
   if (e != cudaSuccess) {
@@ -722,6 +732,7 @@ int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int
   if (causal_id) { delete h; return -1; }   // never enabled by any task
   auto fail = [&](int code) { cgpcm_destroy(h); return code; };
   if (cudaSetDevice(device) != cudaSuccess) return fail(-2);
+  if (cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->sms < 2) h->sms = 148;
   if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) return fail(-2);
   const long l2 = h->ld * h->ld;
   // forward all-reduce buffer: M_AXX0 .. M_Y contiguous + 2 scalars directly behind M_Y requires M_Y to
@@ -820,6 +831,10 @@ int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
     if (value < 0) { h->err = "cull must be >= 0"; return -1; }
     h->cull = value;
     h->storeA_frozen_valid = false;
+    return 0;
+  }
+  if (!strcmp(key, "sl")) {
+    h->sl_opt = (int)value;
     return 0;
   }
   if (!strcmp(key, "store")) {
@@ -1527,8 +1542,16 @@ int cgpcm_dgemm(int a_kc, int b_kc, int c_tr, int M, int N, int K, double alpha,
                 int lower_only, void* stream) {
   if (M < 0 || N < 0 || K < 0 || (M % 8) || (N % 8) || (K % 2) || (lda % 2) || (ldb % 2) || (ldc % 2)) return -1;
   if (!A || !B || !C) return -1;
-  cudaError_t e = dgemm((cudaStream_t)stream, a_kc, b_kc, c_tr, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splits,
-                        c_split_stride, lower_only);
+  cudaError_t e;
+  if (a_kc && (b_kc != 0) == (c_tr != 0) && splits <= 1 && !lower_only && beta == 0.0 && dgemm_sl_supported(M, N, K)) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2) sms = 148;
+    e = dgemm_sl((cudaStream_t)stream, b_kc != 0, M, N, K, alpha, A, lda, B, ldb, C, ldc, sms);
+  } else {
+    e = dgemm((cudaStream_t)stream, a_kc, b_kc, c_tr, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splits,
+              c_split_stride, lower_only);
+  }
   if (e != cudaSuccess) return -2;
   return cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess ? 0 : -2;
 }

@@ -1,0 +1,268 @@
+// "Small-left" FP64 tensor-core GEMM for sm_100a:  C[M x N] = alpha * S[M x K] * B[K x N]  with a small left
+// operand (M, K <= 200: H = m2 - iKh, iKx, C1bar, Wx of the VCGPCM path) and an enormous N (= observations of
+// the chunk x inducing inputs ~ 1e5).  Four of the seven per-chunk contractions have this shape
+// (src/core/cgpcm.py:255-267,473-475: T1 = H A, V = A iKx; adjoint: U1 = A C1bar, Abar = T1 Wx).
+//
+// Persistent, warp-specialised design (one CTA per SM, 10 warps):
+//   * the CTA's half of S (<= 104 rows x K) is loaded into shared memory once and stays resident; only B streams;
+//   * two consumer groups of 4 warps each own a 104 x 64 output tile at a time (13 x 2 DMMA m8n8k4 blocks per
+//     warp) and work on alternate tiles of the CTA's list, so one group's epilogue overlaps the other's main loop;
+//   * two producer warps (one per group) stream the B tiles through a 3-stage ring with 1-D bulk copies
+//     (cp.async.bulk, SASS UBLKCP) that complete on mbarriers; consumers hand stages back through mbarriers.
+//     No __syncthreads in the main loop.
+// Layouts (S always k-contiguous: S[m*lds + k]):
+//   B_KC = false: B(k,n) at B[k*ldb + n], C(m,n) at C[m*ldc + n]               (left multiply,  T1 = H A)
+//   B_KC = true : B(k,n) at B[n*ldb + k], C(m,n) at C[n*ldc + m]  (transposed)  (right multiply, out^T = W X^T)
+// Requirements: M, N, K multiples of 8; K <= 200; M <= 208; lds, ldb, ldc even; 16-byte aligned pointers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dgemm_dmma.cuh"
+
+namespace cg {
+
+constexpr int SL_BN = 64;          // output columns per consumer group tile (4 warps x 16)
+constexpr int SL_BK = 16;
+constexpr int SL_STAGES = 3;
+constexpr int SL_MB = 13;          // 8-row blocks of the resident half (104 rows)
+constexpr int SL_KMAX = 200;
+constexpr int SL_SK = SL_KMAX + 4;   // row stride of the resident operand: == 4 (mod 8), conflict-free fragment loads
+constexpr int SL_NT = 320;         // 8 consumer warps + 2 producer warps
+constexpr int SL_TILE_N = SL_BK * (SL_BN + 4);   // doubles per stage, B n-contiguous
+constexpr int SL_TILE_K = SL_BN * (SL_BK + 4);   // doubles per stage, B k-contiguous
+
+struct SlArgs {
+  const double* S;
+  const double* B;
+  double* C;
+  int M, N, K;
+  long lds, ldb, ldc;
+  double alpha;
+  int ctas0;      // CTAs [0, ctas0) own rows [0, 104), the rest rows [104, M)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 1-D bulk copy global -> shared, completion (bytes) signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// One consumer warp's work on one output tile: MB x 2 blocks, K in k-tiles streamed through the ring.
+template <int MB, bool B_KC>
+__device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* Ssm, const double* ring,
+                                                uint64_t* full, uint64_t* empty, int& stage, uint32_t& phase,
+                                                int nkt, int m_base, int rows, int n0, int lane, int wq) {
+  const int grp = lane >> 2, tig = lane & 3;
+  const int nw = wq * 16;
+  constexpr int TILE = B_KC ? SL_TILE_K : SL_TILE_N;
+  double acc[MB][2][2];
+#pragma unroll
+  for (int i = 0; i < MB; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+  constexpr int sk = SL_SK;
+  const double* Sp = Ssm + grp * sk + tig;
+  const int b_off = B_KC ? (nw + grp) * (SL_BK + 4) + tig : tig * (SL_BN + 4) + nw + grp;
+
+  // B fragments are double-buffered; the 13 S fragments are single-buffered and each is reloaded for the next
+  // k4 step right after its two DMMAs have issued (24 DMMAs of slack before its next use).
+  auto load_b = [&](const double* Bp, int k4, double (&b)[2]) {
+    b[0] = B_KC ? Bp[k4 * 4] : Bp[k4 * 4 * (SL_BN + 4)];
+    b[1] = B_KC ? Bp[8 * (SL_BK + 4) + k4 * 4] : Bp[k4 * 4 * (SL_BN + 4) + 8];
+  };
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const double* Sk = Sp + kt * SL_BK;
+    const int k4n = min(SL_BK / 4, (g.K - kt * SL_BK) >> 2);   // the last k-tile may be short (K % 16 == 8)
+    double fa[MB], fb[2][2];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) fa[mb] = Sk[mb * 8 * sk];   // resident operand: no need to wait for the stage
+    mbar_wait(full + stage, phase);
+    const double* Bp = ring + stage * TILE + b_off;
+    load_b(Bp, 0, fb[0]);
+#pragma unroll
+    for (int k4 = 0; k4 < SL_BK / 4; ++k4) {
+      const bool more = k4 + 1 < SL_BK / 4 && k4 + 1 < k4n;
+      if (more) load_b(Bp, k4 + 1, fb[(k4 + 1) & 1]);
+      if (k4 < k4n) {
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          dmma_8x8x4(acc[mb][0][0], acc[mb][0][1], fa[mb], fb[k4 & 1][0]);
+          dmma_8x8x4(acc[mb][1][0], acc[mb][1][1], fa[mb], fb[k4 & 1][1]);
+          if (more) fa[mb] = Sk[mb * 8 * sk + (k4 + 1) * 4];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + stage);
+    if (++stage == SL_STAGES) { stage = 0; phase ^= 1u; }
+  }
+
+  // epilogue
+  const int cols = g.N - n0;
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb) {
+    if (mb * 8 >= rows) continue;
+    const int row = m_base + mb * 8 + grp;
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) {
+      if (nw + nb * 8 >= cols) continue;
+      const int col = n0 + nw + nb * 8 + tig * 2;
+      const double v0 = g.alpha * acc[mb][nb][0], v1 = g.alpha * acc[mb][nb][1];
+      if (!B_KC) {
+        *reinterpret_cast<double2*>(g.C + (long)row * g.ldc + col) = make_double2(v0, v1);
+      } else {
+        double* p0 = g.C + (long)col * g.ldc + row;
+        p0[0] = v0;
+        p0[g.ldc] = v1;
+      }
+    }
+  }
+}
+
+template <int MB0, int MB1, bool B_KC>
+__global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
+  extern __shared__ __align__(128) unsigned char sl_smem_raw[];
+  constexpr int TILE = B_KC ? SL_TILE_K : SL_TILE_N;
+  constexpr int sk = SL_SK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sl_smem_raw);          // [2 groups][full 3 | empty 3]
+  double* rings = reinterpret_cast<double*>(sl_smem_raw + 128);      // [2][SL_STAGES][TILE]
+  double* Ssm = rings + 2 * SL_STAGES * TILE;                         // [104][sk]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = (int)blockIdx.x >= g.ctas0 ? 1 : 0;
+  const int m_base = half ? SL_MB * 8 : 0;
+  const int rows = min(SL_MB * 8, g.M - m_base);          // valid rows of this half
+  const int q = half ? blockIdx.x - g.ctas0 : blockIdx.x; // index among the CTAs of this half
+  const int cq = half ? gridDim.x - g.ctas0 : g.ctas0;
+  const int ntiles = (g.N + SL_BN - 1) / SL_BN;
+  const int nkt = (g.K + SL_BK - 1) / SL_BK;
+
+  // ---- resident half of S (rows beyond the matrix zero-filled), barriers
+  for (int e = tid; e < SL_MB * 8 * (g.K / 2); e += SL_NT) {
+    const int r = e / (g.K / 2), c2 = (e - r * (g.K / 2)) * 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (r < rows) v = *reinterpret_cast<const double2*>(g.S + (long)(m_base + r) * g.lds + c2);
+    *reinterpret_cast<double2*>(Ssm + r * sk + c2) = v;
+  }
+  if (tid == 0) {
+    for (int gq = 0; gq < 2; ++gq)
+      for (int s = 0; s < SL_STAGES; ++s) {
+        mbar_init(bars + gq * 2 * SL_STAGES + s, 1);                  // full: the producer's expect_tx arrival
+        mbar_init(bars + gq * 2 * SL_STAGES + SL_STAGES + s, 4);      // empty: one arrival per consumer warp
+      }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  const int grpid = warp < 8 ? (warp >> 2) : warp - 8;    // consumer group / producer's group
+  uint64_t* full = bars + grpid * 2 * SL_STAGES;
+  uint64_t* empty = full + SL_STAGES;
+  double* ring = rings + grpid * SL_STAGES * TILE;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  if (warp >= 8) {
+    // ---------------------------------------------------------------- producer warp of group grpid
+    for (int it = grpid; q + (long)it * cq < ntiles; it += 2) {
+      const int n0 = (q + it * cq) * SL_BN;
+      const int cols = min(SL_BN, g.N - n0);
+      for (int kt = 0; kt < nkt; ++kt) {
+        const int kk = min(SL_BK, g.K - kt * SL_BK);      // valid k of this k-tile
+        if (lane == 0) {
+          mbar_wait(empty + stage, phase ^ 1u);
+          mbar_expect_tx(full + stage, (uint32_t)(kk * cols * 8));
+        }
+        __syncwarp();
+        double* dst = ring + stage * TILE;
+        if (!B_KC) {
+          // kk rows of `cols` contiguous doubles
+          if (lane < kk)
+            bulk_g2s(dst + lane * (SL_BN + 4), g.B + (long)(kt * SL_BK + lane) * g.ldb + n0, (uint32_t)(cols * 8),
+                     full + stage);
+        } else {
+          // `cols` rows of kk contiguous doubles
+          for (int r = lane; r < cols; r += 32)
+            bulk_g2s(dst + r * (SL_BK + 4), g.B + (long)(n0 + r) * g.ldb + kt * SL_BK, (uint32_t)(kk * 8), full + stage);
+        }
+        if (++stage == SL_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumer warps
+  const int wq = warp & 3;
+  for (int it = grpid; q + (long)it * cq < ntiles; it += 2) {
+    const int n0 = (q + it * cq) * SL_BN;
+    if (half == 0 || MB1 == MB0)
+      sl_consume_tile<MB0, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq);
+    else
+      sl_consume_tile<MB1, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq);
+  }
+}
+
+inline size_t dgemm_sl_smem(int K, bool b_kc) {
+  const int tile = b_kc ? SL_TILE_K : SL_TILE_N;
+  (void)K;
+  return 128 + (size_t)2 * SL_STAGES * tile * 8 + (size_t)SL_MB * 8 * SL_SK * 8;
+}
+
+inline bool dgemm_sl_supported(int M, int N, int K) {
+  return M > 104 && M <= 2 * SL_MB * 8 && K >= 16 && K <= SL_KMAX && (M % 8) == 0 && (N % 8) == 0 && (K % 8) == 0 &&
+         N >= 64 * 148;
+}
+
+// b_kc = false: C[m*ldc + n] = alpha sum_k S[m*lds + k] B[k*ldb + n];  b_kc = true: C[n*ldc + m] = alpha sum_k S[m*lds + k] B[n*ldb + k]
+inline cudaError_t dgemm_sl(cudaStream_t st, bool b_kc, int M, int N, int K, double alpha, const double* S, long lds,
+                            const double* B, long ldb, double* C, long ldc, int sms = 148) {
+  SlArgs g;
+  g.S = S; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lds = lds; g.ldb = ldb; g.ldc = ldc; g.alpha = alpha;
+  const int rows1 = M - SL_MB * 8;
+  // CTAs are shared between the two halves in proportion to their rows
+  int ctas0 = (int)((double)sms * (SL_MB * 8) / M + 0.5);
+  if (ctas0 >= sms) ctas0 = sms - 1;
+  g.ctas0 = ctas0;
+  const size_t smem = dgemm_sl_smem(K, b_kc);
+  const bool pair12 = rows1 == 96;
+  static bool attr_done = false;
+  if (!attr_done) {
+    const int mx = 232448;
+    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<13, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<13, 12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<13, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<13, 13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    attr_done = true;
+  }
+  if (pair12) {
+    if (b_kc) dgemm_sl_kernel<13, 12, true><<<sms, SL_NT, smem, st>>>(g);
+    else dgemm_sl_kernel<13, 12, false><<<sms, SL_NT, smem, st>>>(g);
+  } else {
+    if (b_kc) dgemm_sl_kernel<13, 13, true><<<sms, SL_NT, smem, st>>>(g);
+    else dgemm_sl_kernel<13, 13, false><<<sms, SL_NT, smem, st>>>(g);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace cg

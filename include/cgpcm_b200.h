@@ -69,7 +69,8 @@ int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_
  * Gaussian envelope is below exp(-e) are exactly 0 and whole windows of them are skipped; default 80),
  * "profile" (1 = CUDA events around every GEMM launch so that cgpcm_last_timing reports their sum),
  * "store" (1 = default: keep the Ahx blocks and H*Ahx of the forward sweep resident in HBM for the backward sweep
- * when they fit -- 2 x 8 nh N nx bytes; 0 = always regenerate / recompute per chunk). */
+ * when they fit -- 2 x 8 nh N nx bytes; 0 = always regenerate / recompute per chunk),
+ * "sl" (1 = default: products with a small left operand run on the persistent bulk-copy kernel; 0 = tiled kernel). */
 int cgpcm_set_option(cgpcm_handle* h, const char* key, double value);
 
 /* Psi statistics at hyper-parameters hyp = {alpha, gamma, omega}: what `sess.run(mats[...])` returns
@@ -101,7 +102,8 @@ int cgpcm_last_timing(cgpcm_handle* h, double out[12]);
 int cgpcm_bvn_cdf(const double* x1, const double* x2, const double* rho, double* out, size_t n, void* stream);
 
 /* Building blocks exported for tests and micro-benchmarks (device pointers only).
- * cgpcm_dgemm: C = alpha op(A) op(B) + beta C on the DMMA kernel; a_kc/b_kc/c_tr as in dgemm_dmma.cuh.
+ * cgpcm_dgemm: C = alpha op(A) op(B) + beta C on the DMMA kernels; a_kc/b_kc/c_tr as in dgemm_dmma.cuh
+ * (shapes with a small k-contiguous left operand, 104 < M <= 208, K <= 200, N >= 9472, go to dgemm_sl.cuh).
  * cgpcm_cholinv: A (n x n, ld) -> L in place, Ainv, logdet (each may be NULL). */
 int cgpcm_dgemm(int a_kc, int b_kc, int c_tr, int M, int N, int K, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int splits,

@@ -86,6 +86,36 @@ def test_dgemm_split_k_and_lower_only():
     np.testing.assert_allclose(np.tril(low), np.tril(A @ A.T), atol=1e-10)
 
 
+@pytest.mark.parametrize('b_kc', [0, 1])
+@pytest.mark.parametrize('M,K,N', [(200, 200, 64 * 148 + 64 * 37), (200, 184, 64 * 150 + 8), (168, 200, 64 * 148),
+                                   (208, 24, 64 * 149 + 40)])
+def test_dgemm_small_left(b_kc, M, K, N):
+    """Persistent small-left-operand kernel (dgemm_sl.cuh: resident S, bulk-copy ring, mbarriers) against numpy,
+    both layouts (left multiply / transposed right multiply), ragged N tiles, short last k-tile, M = 104 + 96
+    and the zero-padded generic halves."""
+    rng = np.random.default_rng(M + K + N + b_kc)
+    S = rng.standard_normal((M, K))
+    B = rng.standard_normal((K, N))
+    want = 1.5 * (S @ B)
+    dev = lambda x: torch.tensor(np.ascontiguousarray(x), dtype=torch.float64, device='cuda')
+    Sd = dev(S)
+    if b_kc:
+        Bd = dev(B.T)                                   # B(k, n) at Bd[n * K + k]
+        C = torch.full((N, M), np.nan, dtype=torch.float64, device='cuda')
+        rc = _lib.lib().cgpcm_dgemm(1, 1, 1, M, N, K, 1.5, Sd.data_ptr(), K, Bd.data_ptr(), K, 0.0, C.data_ptr(), M,
+                                    1, 0, 0, None)
+        got = C.cpu().numpy().T
+    else:
+        Bd = dev(B)
+        C = torch.full((M, N), np.nan, dtype=torch.float64, device='cuda')
+        rc = _lib.lib().cgpcm_dgemm(1, 0, 0, M, N, K, 1.5, Sd.data_ptr(), K, Bd.data_ptr(), N, 0.0, C.data_ptr(), N,
+                                    1, 0, 0, None)
+        got = C.cpu().numpy()
+    assert rc == 0
+    scale = 1.5 * (np.abs(S) @ np.abs(B))
+    assert np.all(np.abs(got - want) <= 4e-15 * scale)
+
+
 @pytest.mark.parametrize('kc', [1, 0])
 @pytest.mark.parametrize('M,K', [(200, 4096), (200, 50), (168, 1234), (184, 16 * 148 * 3 + 6)])
 def test_dgemm_sym(kc, M, K):
