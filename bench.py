@@ -32,6 +32,7 @@ from tests.workload import sweep_workload  # noqa: E402
 METRIC = 'VCGPCM ELBO+grad evals/sec (N=1e5, M=200)'
 UNIT = 'evals/s'
 FP64_PEAK_FALLBACK_TFLOPS = 37.16     # tools/fp64_peaks.cu on this pool's B200 (profiles/fp64_peaks_r01.json)
+TRAFFIC_SL_BYTES = 290.7e6            # dram__bytes_read + write of one dgemm_sl_kernel launch (profiles/r01_ncu_dgemm_sl.txt)
 
 
 def parse():
@@ -214,7 +215,7 @@ def run_ours(args):
     sampler.start()
     barrier()
     wall0 = time.perf_counter()
-    dev_ms, gemm_ms, gemm_flops, gemm_launches, launches, axx_ms = [], 0.0, 0.0, 0, 0, 0.0
+    dev_ms, gemm_ms, gemm_flops, gemm_launches, launches, axx_ms, gemm_flops_exec = [], 0.0, 0.0, 0, 0, 0.0, 0.0
     last = None
     for _ in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (not inside the event bracket)
@@ -224,6 +225,7 @@ def run_ours(args):
         dev_ms.append(tm['total_ms'])
         gemm_ms += tm['gemm_ms']
         gemm_flops += tm['gemm_flops']
+        gemm_flops_exec += tm['gemm_flops_executed']
         gemm_launches += tm['gemm_launches']
         launches += tm['launches']
         axx_ms += tm['axx_ms']
@@ -300,22 +302,32 @@ def run_ours(args):
         'config': {'workload': 'scaling sweep N=%d observations, nh=nx=%d, causal VCGPCM, full regime (Psi rebuilt '
                                'and differentiated), grad w.r.t. all %d variables' % (n, m, npar),
                    'n': n, 'nh': m, 'nx': m, 'cull': args.cull, 'chunk': args.chunk,
-                   'l2': 'flushed between timed steps (512 MB write); chunk workspaces (3 x %.0f MB) exceed L2'
-                         % (8e-6 * m * (args.chunk + 32) * m),
+                   'l2': 'flushed between timed steps (512 MB write); every chunk streams 3 x %.0f MB of operands '
+                         '(> 126 MB L2) and the sweep stores hold 2 x %.1f GB' % (8e-6 * m * args.chunk * m,
+                                                                                   8e-9 * m * (hi - lo) * m),
                    'parallelism': 'observations sharded over %d GPU(s), one packed ncclAllReduce per sweep' % world},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'how': 'wall clock of set_data(host t, y, th, tx) + cgpcm_elbo_grad(host params) -> host gradient'},
         'gpu_launches': int(launches),
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': 'dgemm_dmma_kernel (FP64 DMMA m8n8k4 contraction GEMMs)',
+        'roofline': {'bound': 'tensor',
+                     'kernel': 'FP64 DMMA (mma.sync m8n8k4.f64) contraction kernels: dgemm_sl_kernel (4 per chunk, '
+                               'dominant), dgemm_sym_kernel (3 per chunk), dgemm_dmma_kernel (M x M algebra)',
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
-                     'traffic': None, 'peak_source': peak_src,
+                     'traffic': TRAFFIC_SL_BYTES if (args.n == 100000 and args.m == 200 and args.chunk == 512) else None,
+                     'traffic_note': 'dram read + write bytes of one dgemm_sl_kernel launch (200 x 200 times '
+                                     '200 x 102400) from the ncu --set full capture in profiles/; algorithmic bytes '
+                                     'of that launch: 328 MB',
+                     'peak_source': peak_src,
                      'launches_per_step': gemm_launches / args.steps,
                      'flops_per_step': gemm_flops / args.steps,
                      'avg_launch_ms': gemm_ms / max(1, gemm_launches),
                      'share_of_step': gemm_ms / total_ms if total_ms else None,
+                     'flops_executed_per_step': gemm_flops_exec / args.steps,
                      'note': 'MEASURED_PEAKS.json has no FP64 figure; peak = FP64 tensor (DMMA) rate measured by '
-                             'tools/fp64_peaks.cu; flops = 2*K*(cells of the CTA tiles computed)'},
+                             'tools/fp64_peaks.cu; flops are algorithmic: 2 K M N per launch, K M (M + 1) for the '
+                             'symmetric M x M results (only the lower triangle is needed); launch durations from '
+                             'CUDA events around every GEMM launch on the library stream'},
         'breakdown_ms_per_step': {'axx_kernel': axx_ms / args.steps, 'gemm_kernels': gemm_ms / args.steps},
         'elbo': last[0],
         'other_cull_setting': other,

@@ -124,7 +124,7 @@ struct cgpcm_handle {
   bool t_sorted = false;
   double sum_y2_local = 0.0;
   // options
-  int chunk = 256;          // observations per chunk at full window width
+  int chunk = 512;          // observations per chunk at full window width
   double cull = 80.0;       // 0 = dense
   int profile = 0;          // 1 = CUDA events around every GEMM launch (roofline measurement)
   std::vector<cudaEvent_t> pev;
@@ -369,10 +369,7 @@ int gemm(cgpcm_handle* h, bool a_kc, bool b_kc, bool c_tr, int Mr, int Nr, int K
   }
   if (h->profile) cudaEventRecord(prof_event(h), h->st);
   cudaError_t e;
-  // (the k-contiguous / transposed layout of dgemm_sl needs 64 bulk copies of 128 B per stage and is slower than the
-  // tiled kernel: only option sl = 2 routes it there)
-  if (h->sl_opt && a_kc && b_kc == c_tr && (!b_kc || h->sl_opt == 2) && splits <= 1 && !lower && beta == 0.0 &&
-      dgemm_sl_supported(Mr, Nr, K))
+  if (h->sl_opt && a_kc && b_kc == c_tr && splits <= 1 && !lower && beta == 0.0 && dgemm_sl_supported(Mr, Nr, K))
     e = dgemm_sl(h->st, b_kc, Mr, Nr, K, alpha, A, lda, B, ldb, C, ldc, h->sms);
   else
     e = dgemm(h->st, a_kc, b_kc, c_tr, Mr, Nr, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, stride, lower);

@@ -7,8 +7,9 @@
 //   * the CTA's half of S (<= 104 rows x K) is loaded into shared memory once and stays resident; only B streams;
 //   * two consumer groups of 4 warps each own a 104 x 64 output tile at a time (13 x 2 DMMA m8n8k4 blocks per
 //     warp) and work on alternate tiles of the CTA's list, so one group's epilogue overlaps the other's main loop;
-//   * two producer warps (one per group) stream the B tiles through a 3-stage ring with 1-D bulk copies
-//     (cp.async.bulk, SASS UBLKCP) that complete on mbarriers; consumers hand stages back through mbarriers.
+//   * two producer warps (one per group) stream the B tiles through a 3-stage ring -- 1-D bulk copies
+//     (cp.async.bulk, SASS UBLKCP) for n-contiguous B, 16-byte cp.async for k-contiguous B -- that complete on
+//     mbarriers; consumers hand stages back through mbarriers.
 //     No __syncthreads in the main loop.
 // Layouts (S always k-contiguous: S[m*lds + k]):
 //   B_KC = false: B(k,n) at B[k*ldb + n], C(m,n) at C[m*ldc + n]               (left multiply,  T1 = H A)
@@ -74,7 +75,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 template <int MB, bool B_KC>
 __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* Ssm, const double* ring,
                                                 uint64_t* full, uint64_t* empty, int& stage, uint32_t& phase,
-                                                int nkt, int m_base, int rows, int n0, int lane, int wq) {
+                                                int nkt, int m_base, int rows, int n0, int lane, int wq,
+                                                uint64_t* stagger) {
   const int grp = lane >> 2, tig = lane & 3;
   const int nw = wq * 16;
   constexpr int TILE = B_KC ? SL_TILE_K : SL_TILE_N;
@@ -105,6 +107,10 @@ __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* S
     for (int k4 = 0; k4 < SL_BK / 4; ++k4) {
       const bool more = k4 + 1 < SL_BK / 4 && k4 + 1 < k4n;
       if (more) load_b(Bp, k4 + 1, fb[(k4 + 1) & 1]);
+      if (k4 == 1 && stagger && kt == min(6, nkt - 1)) {      // group 0, first tile: release group 1 (see kernel)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(stagger);
+      }
       if (k4 < k4n) {
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb) {
@@ -169,9 +175,10 @@ __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
   if (tid == 0) {
     for (int gq = 0; gq < 2; ++gq)
       for (int s = 0; s < SL_STAGES; ++s) {
-        mbar_init(bars + gq * 2 * SL_STAGES + s, 1);                  // full: the producer's expect_tx arrival
+        mbar_init(bars + gq * 2 * SL_STAGES + s, B_KC ? 32 : 1);      // full: expect_tx arrival | 32 cp.async lanes
         mbar_init(bars + gq * 2 * SL_STAGES + SL_STAGES + s, 4);      // empty: one arrival per consumer warp
       }
+    mbar_init(bars + 4 * SL_STAGES, 4);                               // stagger: group 0's four warps
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -183,8 +190,17 @@ __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
   int stage = 0;
   uint32_t phase = 0;
 
+  // Group 1 starts half a tile (and half a k-tile) after group 0: its producer holds the first copy back until
+  // group 0 is in the middle of k-tile 6 of its first tile.  From then on one group's epilogue and k-tile
+  // hand-overs fall into the other's DMMA stream instead of coinciding with them.
+  uint64_t* stagger = bars + 4 * SL_STAGES;
+
   if (warp >= 8) {
     // ---------------------------------------------------------------- producer warp of group grpid
+    if (grpid == 1) {
+      if (lane == 0) mbar_wait(stagger, 0u);
+      __syncwarp();
+    }
     for (int it = grpid; q + (long)it * cq < ntiles; it += 2) {
       const int n0 = (q + it * cq) * SL_BN;
       const int cols = min(SL_BN, g.N - n0);
@@ -192,19 +208,28 @@ __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
         const int kk = min(SL_BK, g.K - kt * SL_BK);      // valid k of this k-tile
         if (lane == 0) {
           mbar_wait(empty + stage, phase ^ 1u);
-          mbar_expect_tx(full + stage, (uint32_t)(kk * cols * 8));
+          if (!B_KC) mbar_expect_tx(full + stage, (uint32_t)(kk * cols * 8));
         }
         __syncwarp();
         double* dst = ring + stage * TILE;
         if (!B_KC) {
-          // kk rows of `cols` contiguous doubles
+          // kk rows of `cols` contiguous doubles: one bulk copy per row
           if (lane < kk)
             bulk_g2s(dst + lane * (SL_BN + 4), g.B + (long)(kt * SL_BK + lane) * g.ldb + n0, (uint32_t)(cols * 8),
                      full + stage);
         } else {
-          // `cols` rows of kk contiguous doubles
-          for (int r = lane; r < cols; r += 32)
-            bulk_g2s(dst + r * (SL_BK + 4), g.B + (long)(n0 + r) * g.ldb + kt * SL_BK, (uint32_t)(kk * 8), full + stage);
+          // `cols` rows of kk contiguous doubles (128 B): too small for bulk copies -- 16-byte cp.async, 16 per lane,
+          // whose completion arrives on the stage's mbarrier (count 32, one arrival per lane)
+          const int r0 = lane >> 3, kc = (lane & 7) * 2;
+          const double* src = g.B + (long)(n0 + r0) * g.ldb + kt * SL_BK + kc;
+          double* d = dst + r0 * (SL_BK + 4) + kc;
+          const bool kok = kc < kk;
+#pragma unroll
+          for (int j = 0; j < SL_BN / 4; ++j) {
+            const bool v = kok && r0 + 4 * j < cols;
+            cp_async16(d + j * 4 * (SL_BK + 4), v ? src + (long)j * 4 * g.ldb : g.B, v);
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(full + stage)) : "memory");
         }
         if (++stage == SL_STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -216,10 +241,11 @@ __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
   const int wq = warp & 3;
   for (int it = grpid; q + (long)it * cq < ntiles; it += 2) {
     const int n0 = (q + it * cq) * SL_BN;
+    uint64_t* sg = it == 0 ? stagger : nullptr;
     if (half == 0 || MB1 == MB0)
-      sl_consume_tile<MB0, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq);
+      sl_consume_tile<MB0, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
     else
-      sl_consume_tile<MB1, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq);
+      sl_consume_tile<MB1, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
   }
 }
 
