@@ -187,48 +187,110 @@ __device__ __forceinline__ double bvnd_tab(double h, double k, const BvnTab& T) 
 
 // ---- pair-hoisted high-correlation branch ---------------------------------------------------------
 // In the CGPCM  h - k = -(x1 - x2) = (p - q)(tx_k - tx_l)  does not depend on the observation: for a fixed
-// pair (k, l) Genz's  bs = (h - k)^2  is a constant, so of the two exp() per quadrature node of the
-// |rho| >= 0.925 branch one, exp(-bs / (2 xs_j)), is hoisted out of the loop over observations together
-// with sqrt(bs) and Phi(-b / a).  Every term carries the common factor exp(-hk / 2); Genz's skip tests
-// (asr > -100, -hk < 100) only drop terms below 4e-44 and are not needed in the factored form
-// (all factors stay finite for hk >= -600; below that the un-hoisted routine is used).
+// pair (k, l) Genz's  bs = (h - k)^2  is a constant.  Of the two exp() per quadrature node of the
+// |rho| >= 0.925 branch one, exp(-bs / (2 xs_j)), is therefore hoisted out of the loop over observations
+// (together with sqrt(bs) and Phi(-b / a)), and every term carries the common factor exp(-hk / 2).
+// What remains of the 20-node sum is a function of the single scalar u = hk,
+//
+//     f(u) = sum_j P_j / rs_j * exp(-c1_j u)  -  (K0 + c K1 + c d K2),      P_j = (a/2) w_j exp(-bs / (2 xs_j)),
+//
+// a positive combination of 20 slowly varying exponentials (c1_j u stays inside +-4 on the interval
+// |u| <= 200 that Genz's own cut-offs leave).  It is evaluated as a Chebyshev series in u / 200 whose
+// coefficients are per-pair linear combinations a_m = sum_j (P_j / rs_j) B[m][j] of the exact Chebyshev
+// coefficients B[m][j] = (2 - [m = 0]) (-1)^m I_m(200 c1_j) of the node exponentials (host, Bessel series):
+// ~2 FMAs per degree (18 at rho = 0.97) in place of 20 exp().  Truncation: coefficients below 1e-18 of the
+// leading one are dropped -- the series reproduces the node sum to rounding (tests/test_gpu_psi.py).
+// Genz's skip tests (asr > -100, -hk < 100) only drop terms below 4e-44 and are not needed in the factored
+// form; outside |hk| <= 200 the tail term alone (hk > 200) or the un-hoisted routine (hk < -200) is used.
 // Valid for rho > 0 (always true here: rho = gamma / (alpha + gamma + omega)).
-// The 20 node constants live in shared memory ([node][thread], conflict-free) so that the loop over
-// observations keeps a register footprint that allows 16 warps per SM.
-struct BvnPair {
-  double bs, P0, Pb;
-};
 constexpr int BVN_PAIR_THREADS = 256;
+constexpr int BVN_CHEB_MAXDEG = 40;
+constexpr double BVN_CHEB_U = 200.0;
 
-// sP: __shared__ double[20][BVN_PAIR_THREADS]; column threadIdx.x belongs to this thread.
-__device__ __forceinline__ void bvn_pair_init(double hmk, const BvnTab& T, BvnPair& R, double (*sP)[BVN_PAIR_THREADS]) {
+struct BvnPair {
+  double bs, P0, Pb, K0, K1, K2;
+};
+
+// Host: B[m][j] for m = 0..deg (row-major, 20 per row) and the degree.  I_m by its power series (200 c1_j < 5).
+inline int bvn_make_cheb(const BvnTab& T, double* B /* (BVN_CHEB_MAXDEG + 1) * 20 */) {
+  double mx[BVN_CHEB_MAXDEG + 1];
+  for (int m = 0; m <= BVN_CHEB_MAXDEG; ++m) {
+    mx[m] = 0.0;
+    for (int j = 0; j < 20; ++j) {
+      const long double half = 0.5L * (long double)(BVN_CHEB_U * T.c1[j]);
+      // I_m(2 half) = sum_k half^(2k + m) / (k! (k + m)!)
+      long double term = 1.0L;
+      for (int i = 1; i <= m; ++i) term *= half / i;
+      long double sum = term;
+      for (int k = 1; k < 80; ++k) {
+        term *= half * half / ((long double)k * (k + m));
+        sum += term;
+        if (term < 1e-25L * sum) break;
+      }
+      double v = (double)((m == 0 ? 1.0L : 2.0L) * ((m & 1) ? -sum : sum));
+      B[m * 20 + j] = v;
+      mx[m] = fmax(mx[m], fabs(v));
+    }
+  }
+  int deg = 0;
+  for (int m = 0; m <= BVN_CHEB_MAXDEG; ++m)
+    if (mx[m] > 1e-18 * mx[0]) deg = m;
+  return deg;
+}
+
+// Per-pair set-up.  sA: shared [deg + 1][BVN_PAIR_THREADS] (column threadIdx.x belongs to this thread);
+// sB: shared copy of B (already filled, (deg + 1) * 20).
+__device__ __forceinline__ void bvn_pair_init(double hmk, const BvnTab& T, BvnPair& R, double* sA, const double* sB,
+                                              int deg) {
   const double bs = hmk * hmk;
   R.bs = bs;
   R.P0 = T.a_ * exp(-0.5 * bs / T.as_);
   const double b = fabs(hmk);
   R.Pb = CG_SQRT_TWO_PI * phid(-b / T.a_) * b;
+  double pc[20];
+  double k0 = 0.0, k1 = 0.0, k2 = 0.0;
 #pragma unroll
-  for (int j = 0; j < 20; ++j) sP[j][threadIdx.x] = T.w[j] * exp(-0.5 * bs * T.c0[j]);   // (a/2) w_j exp(-bs / (2 xs_j))
+  for (int j = 0; j < 20; ++j) {
+    const double P = T.w[j] * exp(-0.5 * bs * T.c0[j]);     // (a/2) w_j exp(-bs / (2 xs_j))
+    const double xs = T.c3[j];
+    k0 += P;
+    k1 += P * xs;
+    k2 += P * xs * xs;
+    pc[j] = P * T.c2[j];
+  }
+  R.K0 = k0; R.K1 = k1; R.K2 = k2;
+  for (int m = 0; m <= deg; ++m) {
+    double a = 0.0;
+#pragma unroll
+    for (int j = 0; j < 20; ++j) a += pc[j] * sB[m * 20 + j];
+    sA[m * BVN_PAIR_THREADS + threadIdx.x] = a;
+  }
 }
 
-// Phi_2(x1, x2; rho) for the pair whose constants are R / sP  (same value as bvnd_tab(-x1, -x2, T)).
+// Phi_2(x1, x2; rho) for the pair whose constants are R / sA  (same value as bvnd_tab(-x1, -x2, T)).
 __device__ __forceinline__ double bvn_cdf_pair(double x1, double x2, const BvnTab& T, const BvnPair& R,
-                                               const double (*sP)[BVN_PAIR_THREADS]) {
+                                               const double* sA, int deg) {
   const double hk = x1 * x2;
   const double tail = phid(fmin(x1, x2));
-  if (hk > 200.0) return tail;                       // every remaining term is below exp(-100) (Genz's own cut)
-  if (hk < -600.0) return bvnd_tab(-x1, -x2, T);     // exp(-hk/2) would overflow: un-hoisted routine
+  if (hk > BVN_CHEB_U) return tail;                      // every remaining term is below exp(-100) (Genz's own cut)
+  if (hk < -BVN_CHEB_U) return bvnd_tab(-x1, -x2, T);    // outside the Chebyshev interval: un-hoisted routine
   const double E1 = exp(-0.5 * hk);
   const double c = (4.0 - hk) * 0.125, d = (12.0 - hk) * 0.0625;
   const double bs = R.bs, as = T.as_;
   const double t5 = 1.0 - d * bs * 0.2;
   double s = R.P0 * (1.0 - c * (bs - as) * t5 * (1.0 / 3.0) + c * d * as * as * 0.2) -
-             R.Pb * (1.0 - c * bs * t5 * (1.0 / 3.0));
-#pragma unroll
-  for (int j = 0; j < 20; ++j) {
-    const double xs = T.c3[j];
-    s += sP[j][threadIdx.x] * (exp(-hk * T.c1[j]) * T.c2[j] - (1.0 + c * xs * (1.0 + d * xs)));
+             R.Pb * (1.0 - c * bs * t5 * (1.0 / 3.0)) - (R.K0 + c * (R.K1 + d * R.K2));
+  // Clenshaw:  sum_m a_m T_m(u / U)
+  const double ut = hk * (1.0 / BVN_CHEB_U), t2 = ut + ut;
+  const double* a = sA + threadIdx.x;
+  double b1 = 0.0, b2 = 0.0;
+#pragma unroll 4
+  for (int m = deg; m >= 1; --m) {
+    const double b0 = fma(t2, b1, a[m * BVN_PAIR_THREADS]) - b2;
+    b2 = b1;
+    b1 = b0;
   }
+  s += fma(ut, b1, a[0]) - b2;
   return tail - E1 * s * (1.0 / CG_TWO_PI);
 }
 

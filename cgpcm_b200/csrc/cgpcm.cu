@@ -159,6 +159,7 @@ struct cgpcm_handle {
   int sym_used[2] = {0, 0};                 // slices touched since sym_begin
   double* axx_part = nullptr;
   long axx_part_elems = 0;
+  double* cheb_d = nullptr;    // Chebyshev table of the pair-hoisted BVN branch (bvn.cuh)
   int axx_slices = 0;
   double* ypart = nullptr;     // [slices][nhp][ld] private Y accumulators
   int y_slices = 0;
@@ -500,9 +501,24 @@ int axx_sweep(cgpcm_handle* h, const PsiConst& c, const BvnTab& T, bool tangents
   if (h->n_local > 0) {
     // pair-hoisted Genz branch: causal model, rho >= 0.925 (rho = gamma / A is always positive here)
     const bool hoist = c.causal && T.high && T.rho > 0.0 && T.as_ > 0.0 && T.ng == 20;
-#define CG_AXX(TG, HO)                                                                                         \
-  axx_sum_kernel<TG, HO><<<grid, 256, 0, h->st>>>(h->t, (int)h->n_local, h->t_sorted ? 1 : 0, h->tx, h->nx,    \
-                                                   h->axx_part, h->ld, c, T)
+    int deg = 0;
+    size_t smem = 0;
+    if (hoist) {
+      double B[(BVN_CHEB_MAXDEG + 1) * 20];
+      deg = bvn_make_cheb(T, B);
+      CK(cudaMemcpyAsync(h->cheb_d, B, (size_t)(deg + 1) * 20 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+      smem = (size_t)(deg + 1) * (20 + BVN_PAIR_THREADS) * sizeof(double);
+      static bool attr_done = false;
+      if (!attr_done) {
+        const int mx = (BVN_CHEB_MAXDEG + 1) * (20 + BVN_PAIR_THREADS) * 8;
+        cudaFuncSetAttribute((const void*)axx_sum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute((const void*)axx_sum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        attr_done = true;
+      }
+    }
+#define CG_AXX(TG, HO)                                                                                            \
+  axx_sum_kernel<TG, HO><<<grid, 256, smem, h->st>>>(h->t, (int)h->n_local, h->t_sorted ? 1 : 0, h->tx, h->nx,    \
+                                                      h->axx_part, h->ld, c, T, h->cheb_d, deg)
     if (tangents) { if (hoist) CG_AXX(true, true); else CG_AXX(true, false); }
     else { if (hoist) CG_AXX(false, true); else CG_AXX(false, false); }
 #undef CG_AXX
@@ -751,6 +767,7 @@ int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int
   if (cudaMalloc(&h->part, h->part_elems * sizeof(double)) != cudaSuccess) return fail(-2);
   for (int k = 0; k < 2; ++k)
     if (cudaMalloc(&h->symacc[k], (size_t)SY_MAX_SPLITS * l2 * sizeof(double)) != cudaSuccess) return fail(-2);
+  if (cudaMalloc(&h->cheb_d, (BVN_CHEB_MAXDEG + 1) * 20 * sizeof(double)) != cudaSuccess) return fail(-2);
   h->axx_slices = 32;
   h->axx_part_elems = (long)h->axx_slices * 4 * l2;
   if (cudaMalloc(&h->axx_part, h->axx_part_elems * sizeof(double)) != cudaSuccess) return fail(-2);
@@ -768,7 +785,7 @@ int cgpcm_destroy(cgpcm_handle* h) {
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->comm && h->own_comm && nccl().ok) nccl().CommDestroy(h->comm);
   double* ptrs[] = {h->t, h->y, h->th, h->tx, h->mats, h->vecs, h->sc, h->params_d, h->gvar_d, h->wsA, h->wsT,
-                    h->wsV, h->part, h->axx_part, h->ypart, h->gpart, h->symacc[0], h->symacc[1], h->storeA, h->storeT};
+                    h->wsV, h->part, h->axx_part, h->ypart, h->gpart, h->symacc[0], h->symacc[1], h->storeA, h->storeT, h->cheb_d};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   if (h->info) cudaFree(h->info);

@@ -87,7 +87,15 @@ template <bool TANGENTS, bool HOIST>
 __global__ void __launch_bounds__(256, HOIST ? 2 : 3) axx_sum_kernel(const double* __restrict__ t, int n_obs, int sorted,
                                                       const double* __restrict__ tx, int nx,
                                                       double* __restrict__ part, long ld, const PsiConst c,
-                                                      const BvnTab T) {
+                                                      const BvnTab T, const double* __restrict__ cheb, int deg) {
+  // HOIST: dynamic shared memory = B table [(deg + 1) * 20] followed by the per-thread Chebyshev coefficients
+  extern __shared__ double axx_smem[];
+  double* sB = axx_smem;
+  double* sA = axx_smem + (HOIST ? (deg + 1) * 20 : 0);
+  if (HOIST) {
+    for (int e = threadIdx.x; e < (deg + 1) * 20; e += blockDim.x) sB[e] = cheb[e];
+    __syncthreads();
+  }
   // decode lower-triangular tile index
   int tidx = blockIdx.x;
   int tk = (int)((sqrt(8.0 * tidx + 1.0) - 1.0) * 0.5);
@@ -116,9 +124,8 @@ __global__ void __launch_bounds__(256, HOIST ? 2 : 3) axx_sum_kernel(const doubl
   const double txk = tx[k], txl = tx[l];
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   // HOIST (causal, rho >= 0.925): the pair constants of the Genz high-correlation branch (bvn.cuh)
-  __shared__ double sP[HOIST ? 20 : 1][BVN_PAIR_THREADS];
   BvnPair R;
-  if (HOIST) bvn_pair_init((c.p - c.q) * (txk - txl), T, R, sP);
+  if (HOIST) bvn_pair_init((c.p - c.q) * (txk - txl), T, R, sA, sB, deg);
   for (int n = n_lo + blockIdx.y; n < n_hi; n += gridDim.y) {
     const double tn = __ldg(t + n);
     const double dk = tn - txk, dl = tn - txl;
@@ -137,11 +144,11 @@ __global__ void __launch_bounds__(256, HOIST ? 2 : 3) axx_sum_kernel(const doubl
     }
     const double x1 = c.p * dk + c.q * dl, x2 = c.q * dk + c.p * dl;
     if (!TANGENTS) {
-      s0 += env * (HOIST ? bvn_cdf_pair(x1, x2, T, R, sP) : bvnd_tab(-x1, -x2, T));
+      s0 += env * (HOIST ? bvn_cdf_pair(x1, x2, T, R, sA, deg) : bvnd_tab(-x1, -x2, T));
     } else {
       double cdf, d1, d2, dr;
       if (HOIST) {
-        cdf = bvn_cdf_pair(x1, x2, T, R, sP);
+        cdf = bvn_cdf_pair(x1, x2, T, R, sA, deg);
         bvn_partials_tab(x1, x2, T, d1, d2, dr);
       } else {
         bvn_cdf_grad_tab(x1, x2, T, cdf, d1, d2, dr);

@@ -57,6 +57,13 @@ def make_case(name, seed=0, n=None):
         w = np.exp(-40 * np.linspace(-.3, .3, 61) ** 2)
         y = _unit(np.convolve(rng.standard_normal(n + 60), w, mode='valid'))
         reg = 1e-6
+    elif name == 'sweep_hi':        # the bench's correlation: rho = 0.967 -> Genz's |rho| >= 0.925 branch (pair-hoisted
+        n = n or 600                #   Chebyshev path of bvn.cuh), observations on both sides of every inducing input
+        t = np.linspace(0, 6., n)
+        rec = om.recipe(t, nx=16, nh=12, tau_w=.1, tau_f=.025, causal=True)
+        w = np.exp(-40 * np.linspace(-.3, .3, 61) ** 2)
+        y = _unit(np.convolve(rng.standard_normal(n + 60), w, mode='valid'))
+        reg = 1e-6
     elif name == 'sweep_wide':      # long series, few inducing inputs per unit time -> narrow windows
         n = n or 3000
         t = np.linspace(0, n / 100., n)
@@ -74,7 +81,7 @@ def make_case(name, seed=0, n=None):
                 hyp=hyp, reg=reg, causal=causal, params=params, nh=len(rec['th']), nx=len(rec['tx']))
 
 
-CASES = ['toy_test', 'toy_small', 'toy_acausal_model', 'ou', 'hrir', 'crude', 'sweep']
+CASES = ['toy_test', 'toy_small', 'toy_acausal_model', 'ou', 'hrir', 'crude', 'sweep', 'sweep_hi']
 
 
 def oracle_noise_floor(params, t, y, th, tx, reg, causal=True, trials=4, seed=0):

@@ -17,7 +17,7 @@ from tests.cases import make_case  # noqa: E402
 om.PW_DISTS_EXACT = True     # exact squared distances (see oracle/model.py)
 out_dir = os.path.join(ROOT, 'tests', 'golden')
 os.makedirs(out_dir, exist_ok=True)
-for name in ['toy_test', 'ou', 'hrir', 'crude', 'sweep', 'toy_acausal_model']:
+for name in ['toy_test', 'ou', 'hrir', 'crude', 'sweep', 'sweep_hi', 'toy_acausal_model']:
     c = make_case(name)
     e, terms, g = om.elbo_and_grad(c['params'], c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'])
     fr = om.precompute(c['params'], c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'])
