@@ -561,7 +561,7 @@ int gemm_splitk_sym(cgpcm_handle* h, bool a_kc, bool b_kc, int Mr, int K, const 
   double* C = h->symacc[slot] + win;
   if (a_kc == b_kc && dgemm_sym_supported(Mr)) {
     const int splits = dgemm_sym_splits(K);
-    h->gemm_flops_exec += 2.0 * K * (double)SY_NW * SY_BLK * SY_BLK;
+    h->gemm_flops_exec += 2.0 * K * (10.0 * SY_BLK * SY_BLK + 5.0 * 15 * 64);   // 10 full + 5 diagonal warp blocks
     h->gemm_flops += 2.0 * K * 0.5 * Mr * (Mr + 1.0);
     h->gemm_launches++;
     if (h->profile) cudaEventRecord(prof_event(h), h->st);

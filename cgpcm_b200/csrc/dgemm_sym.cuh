@@ -8,7 +8,8 @@
 // (src/core/cgpcm.py:255-267,473-475 and the adjoint of SURVEY.md App. D).
 //
 // Tiling: the output is cut into 40 x 40 warp blocks (5 x 5 DMMA tiles: 10 fragment loads feed 25 DMMAs);
-// only the 15 blocks of the lower triangle exist, one warp each => one CTA owns the whole output for its
+// only the 15 blocks of the lower triangle exist (the 5 diagonal ones compute 15 of their 25 tiles), one warp
+// each => one CTA owns the whole output for its
 // K-slice, and the grid is the K-split (one CTA per SM, one wave).  Both operand panels (M x 16 k each) are
 // staged in shared memory by a 3-stage cp.async pipeline (3 x 64 KB) fed by a 16th, producer warp and shared
 // by the 15 consumer warps.  Strides are == 4 (mod 8) doubles: every fragment load is bank-conflict free.
@@ -42,6 +43,84 @@ struct SymArgs {
   int k_per_split;       // multiple of SY_BK
   int accumulate;        // 1: C[z] += result, 0: C[z] = result
 };
+
+// One consumer warp: block (gi, gj) of the lower triangle.  DIAG: gi == gj, only the DMMA tiles i >= j are computed.
+template <bool KC, bool DIAG>
+__device__ __forceinline__ void sym_consume(const SymArgs& g, const double* smem, int ktiles, int gi, int gj, int lane) {
+  const int grp = lane >> 2, tig = lane & 3;
+  const int a_off = KC ? (gi * SY_BLK + grp) * (SY_BK + 4) + tig : tig * (SY_MP + 4) + gi * SY_BLK + grp;
+  const int b_off = SY_PANEL + (KC ? (gj * SY_BLK + grp) * (SY_BK + 4) + tig : tig * (SY_MP + 4) + gj * SY_BLK + grp);
+
+  double acc[5][5][2];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // Fragments are single-buffered (25 accumulator pairs leave no room for a second set).  The 5 x 5 DMMA block
+  // is walked row-major on even k4 steps and column-major on odd ones, and every fragment of the next step is
+  // loaded as soon as its register dies: each load then has at least four DMMAs of this warp (and all the
+  // DMMAs of the SMSP's other warps) between issue and first use.
+  auto ldf = [&](const double* P, int k4, int x) {
+    return KC ? P[x * 8 * (SY_BK + 4) + k4 * 4] : P[k4 * 4 * (SY_MP + 4) + x * 8];
+  };
+
+  int stage = 0;
+  for (int kt = 0; kt < ktiles; ++kt) {
+    __syncthreads();
+    const double* Ap = smem + stage * SY_STAGE + a_off;
+    const double* Bp = smem + stage * SY_STAGE + b_off;
+    double fa[5], fb[5];
+#pragma unroll
+    for (int x = 0; x < 5; ++x) { fa[x] = ldf(Ap, 0, x); fb[x] = ldf(Bp, 0, x); }
+#pragma unroll
+    for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
+      const bool more = k4 + 1 < SY_BK / 4;
+      if ((k4 & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            if (!DIAG || i >= j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            if (more && i == 4) fb[j] = ldf(Bp, k4 + 1, j);
+          }
+          if (more) fa[i] = ldf(Ap, k4 + 1, i);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            if (!DIAG || i >= j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            if (more && j == 4) fa[i] = ldf(Ap, k4 + 1, i);
+          }
+          if (more) fb[j] = ldf(Bp, k4 + 1, j);
+        }
+      }
+    }
+    if (++stage == SY_STAGES) stage = 0;
+  }
+
+  double* C = g.C + (long)blockIdx.x * g.c_split_stride;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int row = gi * SY_BLK + i * 8 + grp;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int col = gj * SY_BLK + j * 8 + tig * 2;
+      if (col >= g.M || (DIAG && j > i)) continue;
+      double2* p = reinterpret_cast<double2*>(C + (long)row * g.ldc + col);
+      double v0 = acc[i][j][0], v1 = acc[i][j][1];
+      if (g.accumulate) {
+        const double2 o = *p;
+        v0 += o.x;
+        v1 += o.y;
+      }
+      *p = make_double2(v0, v1);
+    }
+  }
+}
 
 // KC = true : A(m,k) at A[m*lda + k], B(n,k) at B[n*ldb + k]   (k contiguous)
 // KC = false: A(m,k) at A[k*lda + m], B(n,k) at B[k*ldb + n]   (m / n contiguous)
@@ -129,81 +208,14 @@ __global__ void __launch_bounds__(SY_NT, 1) dgemm_sym_kernel(const SymArgs g) {
   }
 
   // -------------------------------------------------------------------- consumer warps
-  const int grp = lane >> 2, tig = lane & 3;
-  const int gi = warp >= 10 ? 4 : warp >= 6 ? 3 : warp >= 3 ? 2 : warp >= 1 ? 1 : 0;
-  const int gj = warp - gi * (gi + 1) / 2;
-  const int a_off = KC ? (gi * SY_BLK + grp) * (SY_BK + 4) + tig : tig * (SY_MP + 4) + gi * SY_BLK + grp;
-  const int b_off = SY_PANEL + (KC ? (gj * SY_BLK + grp) * (SY_BK + 4) + tig : tig * (SY_MP + 4) + gj * SY_BLK + grp);
-
-  double acc[5][5][2];
-#pragma unroll
-  for (int i = 0; i < 5; ++i)
-#pragma unroll
-    for (int j = 0; j < 5; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  // Fragments are single-buffered (25 accumulator pairs leave no room for a second set).  The 5 x 5 DMMA block
-  // is walked row-major on even k4 steps and column-major on odd ones, and every fragment of the next step is
-  // loaded as soon as its register dies: each load then has at least four DMMAs of this warp (and all the
-  // DMMAs of the SMSP's other warps) between issue and first use.
-  auto ldf = [&](const double* P, int k4, int x) {
-    return KC ? P[x * 8 * (SY_BK + 4) + k4 * 4] : P[k4 * 4 * (SY_MP + 4) + x * 8];
-  };
-
-  int stage = 0;
-  for (int kt = 0; kt < ktiles; ++kt) {
-    __syncthreads();
-    const double* Ap = smem + stage * SY_STAGE + a_off;
-    const double* Bp = smem + stage * SY_STAGE + b_off;
-    double fa[5], fb[5];
-#pragma unroll
-    for (int x = 0; x < 5; ++x) { fa[x] = ldf(Ap, 0, x); fb[x] = ldf(Bp, 0, x); }
-#pragma unroll
-    for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
-      const bool more = k4 + 1 < SY_BK / 4;
-      if ((k4 & 1) == 0) {
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-            if (more && i == 4) fb[j] = ldf(Bp, k4 + 1, j);
-          }
-          if (more) fa[i] = ldf(Ap, k4 + 1, i);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-#pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-            if (more && j == 4) fa[i] = ldf(Ap, k4 + 1, i);
-          }
-          if (more) fb[j] = ldf(Bp, k4 + 1, j);
-        }
-      }
-    }
-    if (++stage == SY_STAGES) stage = 0;
-  }
-
-  double* C = g.C + (long)blockIdx.x * g.c_split_stride;
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int row = gi * SY_BLK + i * 8 + grp;
-    if (row >= g.M) continue;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const int col = gj * SY_BLK + j * 8 + tig * 2;
-      if (col >= g.M) continue;
-      double2* p = reinterpret_cast<double2*>(C + (long)row * g.ldc + col);
-      double v0 = acc[i][j][0], v1 = acc[i][j][1];
-      if (g.accumulate) {
-        const double2 o = *p;
-        v0 += o.x;
-        v1 += o.y;
-      }
-      *p = make_double2(v0, v1);
-    }
-  }
+  // Block of this warp.  The five diagonal blocks only need their lower 15 of 25 DMMA tiles; blocks are dealt to
+  // warps so that every SM sub-partition (warp % 4) carries about the same number of DMMAs per k-step:
+  // {F,F,D,D} = 80, {F,F,D,D} = 80, {F,F,F,D} = 90, {F,F,F + producer} = 75   (F = 25, D = 15).
+  const int blk = (int)((0xE92DA50C863B741ull >> (4 * warp)) & 15);   // warp -> block {1,4,7,11,3,6,8,12,0,5,10,13,2,9,14}
+  const int gi = blk >= 10 ? 4 : blk >= 6 ? 3 : blk >= 3 ? 2 : blk >= 1 ? 1 : 0;
+  const int gj = blk - gi * (gi + 1) / 2;
+  if (gi == gj) sym_consume<KC, true>(g, smem, ktiles, gi, gj, lane);
+  else sym_consume<KC, false>(g, smem, ktiles, gi, gj, lane);
 }
 
 inline bool dgemm_sym_supported(int M) { return M > 160 && M <= SY_MP && (M % 8) == 0; }

@@ -250,23 +250,40 @@ __global__ void __launch_bounds__(256) ahx_dot_kernel(const double* __restrict__
       const long off = ((long)i * nc + n0) * kwp + k;
       const double* src = W + off;
       const double* asrc = A + off;
-      for (int n = n0; n < n1; ++n, src += kwp, asrc += kwp) {
-        const double d = __ldg(t + n) - txk;
-        const double E = -c.e_hh * thi * thi - c.e_dd * d * d + c.e_hd * thi * d;
-        if (E < -c.cull) continue;
-        const double w = *src + __ldg(y + n) * yb;
-        const double bh = -(c.gamma * thi + c.omega * d);    // b / 2
-        const double u = bh * 2.0 * c.inv_2A;                // b / (2A)
-        const double z = bh * c.inv_sqrtA;
-        // F = Ahx[n,i,k] itself is still in the chunk workspace (same bits as the forward value); only the
-        // Gaussian factor of the erfc derivative is evaluated here
-        const double F = *asrc;
-        const double X = c.causal ? exp(E - z * z) * c.inv_sqrtA : 0.0;
-        const double zc = z * c.inv_2A;
-        const double da = F * (-thi * thi - u * u - c.inv_2A) + X * zc;
-        const double dg = F * (-(thi + u) * (thi + u) - c.inv_2A) + X * (thi * c.inv_sqrtA + zc);
-        const double dw = F * (-(d + u) * (d + u) - c.inv_2A) + X * (d * c.inv_sqrtA + zc);
-        g0 += w * da; g1 += w * dg; g2 += w * dw;
+      // four observations per step: all eight loads are issued before the first exp() so that enough bytes
+      // are in flight per SM (the kernel streams 16 B per element and is latency-bound otherwise)
+      for (int nb = n0; nb < n1; nb += 4) {
+        double wv[4], av[4], tv[4], yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = nb + u < n1;
+          wv[u] = ok ? src[(long)u * kwp] : 0.0;
+          av[u] = ok ? asrc[(long)u * kwp] : 0.0;
+          tv[u] = ok ? __ldg(t + nb + u) : 0.0;
+          yv[u] = ok ? __ldg(y + nb + u) : 0.0;
+        }
+        src += 4L * kwp;
+        asrc += 4L * kwp;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (nb + u >= n1) break;
+          const double d = tv[u] - txk;
+          const double E = -c.e_hh * thi * thi - c.e_dd * d * d + c.e_hd * thi * d;
+          if (E < -c.cull) continue;
+          const double w = wv[u] + yv[u] * yb;
+          const double bh = -(c.gamma * thi + c.omega * d);    // b / 2
+          const double uu = bh * 2.0 * c.inv_2A;               // b / (2A)
+          const double z = bh * c.inv_sqrtA;
+          // F = Ahx[n,i,k] itself is still in the chunk's block (same bits as the forward value); only the
+          // Gaussian factor of the erfc derivative is evaluated here
+          const double F = av[u];
+          const double X = c.causal ? exp(E - z * z) * c.inv_sqrtA : 0.0;
+          const double zc = z * c.inv_2A;
+          const double da = F * (-thi * thi - uu * uu - c.inv_2A) + X * zc;
+          const double dg = F * (-(thi + uu) * (thi + uu) - c.inv_2A) + X * (thi * c.inv_sqrtA + zc);
+          const double dw = F * (-(d + uu) * (d + uu) - c.inv_2A) + X * (d * c.inv_sqrtA + zc);
+          g0 += w * da; g1 += w * dg; g2 += w * dw;
+        }
       }
     }
   }
