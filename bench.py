@@ -216,6 +216,7 @@ def run_ours(args):
     barrier()
     wall0 = time.perf_counter()
     dev_ms, gemm_ms, gemm_flops, gemm_launches, launches, axx_ms, gemm_flops_exec = [], 0.0, 0.0, 0, 0, 0.0, 0.0
+    gen_ms = 0.0
     last = None
     for _ in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (not inside the event bracket)
@@ -229,6 +230,7 @@ def run_ours(args):
         gemm_launches += tm['gemm_launches']
         launches += tm['launches']
         axx_ms += tm['axx_ms']
+        gen_ms += tm['ahx_gen_ms']
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
@@ -328,7 +330,16 @@ def run_ours(args):
                              'tools/fp64_peaks.cu; flops are algorithmic: 2 K M N per launch, K M (M + 1) for the '
                              'symmetric M x M results (only the lower triangle is needed); launch durations from '
                              'CUDA events around every GEMM launch on the library stream'},
-        'breakdown_ms_per_step': {'axx_kernel': axx_ms / args.steps, 'gemm_kernels': gemm_ms / args.steps},
+        'breakdown_ms_per_step': {'axx_kernel': axx_ms / args.steps, 'ahx_gen_kernels': gen_ms / args.steps,
+                                  'gemm_kernels': gemm_ms / args.steps},
+        # BASELINE.json's second figure: logical bytes of the Psi statistics the reference materialises
+        # (8 (N nx^2 + N nh nx)) over the time of the kernels that construct (and reduce) them
+        'psi_stat': {'value': 8e-9 * n * m * (m + m) / (1e-3 * (axx_ms + gen_ms) / args.steps)
+                     if (axx_ms + gen_ms) > 0 else None,
+                     'unit': 'GB/s (logical Psi-statistic bytes of the whole job / Axx + Ahx kernel time of rank 0)',
+                     'logical_bytes_per_eval': 8.0 * n * m * (m + m),
+                     'note': 'the statistics are never materialised: Axx is reduced in registers, Ahx is written once '
+                             '(8 N nh nx bytes) for the contractions'},
         'elbo': last[0],
         'other_cull_setting': other,
         'frozen_regime': {'value': frozen_value, 'unit': UNIT,

@@ -129,6 +129,7 @@ struct cgpcm_handle {
   int profile = 0;          // 1 = CUDA events around every GEMM launch (roofline measurement)
   std::vector<cudaEvent_t> pev;
   size_t pev_used = 0;
+  std::vector<char> pev_kind;  // per event pair: 0 = contraction GEMM, 1 = Ahx generation
   double gemm_flops = 0.0;  // algorithmic flops of the GEMM launches of the last evaluation (symmetric: M(M+1)K)
   double gemm_flops_exec = 0.0;   // flops of the CTA / warp tiles those launches computed
   long gemm_launches = 0;
@@ -342,7 +343,11 @@ void dot(cgpcm_handle* h, const double* a, const double* b, int n, double* out) 
 
 void zero(cgpcm_handle* h, double* p, long n) { cudaMemsetAsync(p, 0, n * sizeof(double), h->st); }
 
-cudaEvent_t prof_event(cgpcm_handle* h) {
+cudaEvent_t prof_event(cgpcm_handle* h, int kind = 0) {
+  if ((h->pev_used & 1) == 0) {
+    if (h->pev_kind.size() <= h->pev_used / 2) h->pev_kind.resize(h->pev_used / 2 + 1);
+    h->pev_kind[h->pev_used / 2] = (char)kind;
+  }
   if (h->pev_used == h->pev.size()) {
     cudaEvent_t e;
     cudaEventCreate(&e);
@@ -537,9 +542,11 @@ int gen_chunk(cgpcm_handle* h, const PsiConst& c, const Chunk& ch, bool with_y, 
   const int threads = std::min(256, round_up(ch.kwp, 32));
   dim3 grid(h->nhp, (ch.nc + AHX_NSUB - 1) / AHX_NSUB);
   if ((int)grid.y > h->y_slices) { h->err = "internal: y_slices too small"; return -1; }
+  if (h->profile) cudaEventRecord(prof_event(h, 1), h->st);
   ahx_gen_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx, h->nx,
                                               ch.k_lo, ch.kwp, dstA, with_y ? h->ypart : nullptr, h->ld,
                                               (long)h->nhp * h->ld, c);
+  if (h->profile) cudaEventRecord(prof_event(h, 1), h->st);
   L(h);
   return 0;
 }
@@ -1497,13 +1504,14 @@ int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_
     h->timing[0] = ms[0]; h->timing[1] = ms[1]; h->timing[2] = ms[2]; h->timing[3] = ms[3]; h->timing[4] = ms[4];
     h->timing[5] = ms[1] - ms[4] + ms[2];
     if (h->profile) {
-      double tot = 0.0;
+      double tot = 0.0, tot_gen = 0.0;
       for (size_t i = 0; i + 1 < h->pev_used; i += 2) {
         float g = 0;
         cudaEventElapsedTime(&g, h->pev[i], h->pev[i + 1]);
-        tot += g;
+        if (h->pev_kind[i / 2]) tot_gen += g; else tot += g;
       }
       h->timing[5] = tot;
+      h->timing[10] = tot_gen;
     }
     h->timing[6] = (double)h->launches;
     h->timing[7] = h->gemm_flops;

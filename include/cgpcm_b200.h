@@ -94,7 +94,8 @@ int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_
  * out[4] Axx kernel, out[5] contraction GEMM kernels (exact sum with option "profile", else the sweeps
  * minus the Axx kernel), out[6] number of kernel launches, out[7] algorithmic FP64 flops of those GEMM
  * launches (2 K M N; symmetric results K M (M + 1)), out[8] number of GEMM launches, out[9] flops of the CTA /
- * warp tiles the launches actually computed; out[10..11] reserved. */
+ * warp tiles the launches actually computed, out[10] Ahx generation kernels (option "profile" only);
+ * out[11] reserved. */
 int cgpcm_last_timing(cgpcm_handle* h, double out[12]);
 
 /* The reference's native op: Phi_2(x1, x2; rho) element-wise on three FP64 vectors of length n
