@@ -319,6 +319,34 @@ class VCGPCM(CGPCM):
         terms = [{'name': nm, 'tensor': Term(obj, i), 'modifier': '.2e'} for i, nm in enumerate(TERM_NAMES)]
         return obj, terms
 
+    def _fpi(self, num, high_reg):
+        temporary = not self._precomputed
+        if temporary:                      # symbolic mats in the reference = statistics at the current hyper-parameters
+            self.precompute()
+        try:
+            return self.engine.fpi(self._pack(), num, high_reg=high_reg, reg=config.reg)
+        finally:
+            if temporary:
+                self.undo_precompute()
+
+    def fpi(self, num=50, z=True, high_reg=False):
+        """Fixed-point iteration on q(u) (``src/core/cgpcm.py:479-516``): ``num`` rounds of optimal q(z) given q(u),
+        optimal q(u) given q(z); assigns ``mu_u`` and ``var_u``."""
+        if not z:
+            raise NotImplementedError('fpi on q(z) (z=False) is not on the accelerated path')
+        mu_u, var_u, _, _ = self._fpi(num, high_reg)
+        self.vars['mu_u'].value = mu_u.reshape(self.vars['mu_u'].value.shape)
+        self.vars['var_u'].value = var_u
+        self._cache = None
+
+    def convert(self, z=True):
+        """Assign q(z) after optimising q(u) (``src/core/cgpcm.py:577-592``): ``vars['mu_z']``, ``vars['var_z']``."""
+        if not z:
+            raise NotImplementedError('convert(z=False) is not on the accelerated path')
+        _, _, mu_z, var_z = self._fpi(0, False)
+        self.vars['mu_z'] = Var('mu_z', mu_z.reshape(-1, 1))
+        self.vars['var_z'] = Var('var_z', var_z)
+
     @property
     def mats(self):
         """Psi statistics at the current (or frozen) hyper-parameters as numpy arrays."""

@@ -91,7 +91,7 @@ enum Mat {
 };
 
 // vector slots (each ld doubles)
-enum Vec { V_MU, V_YTMU, V_LAM, V_LBAR, V_ISOMU, V_MUBAR, V_YLBAR, V_M2BMU, V_COUNT };
+enum Vec { V_MU, V_YTMU, V_LAM, V_LBAR, V_ISOMU, V_MUBAR, V_YLBAR, V_M2BMU, V_MUZ, V_COUNT };
 
 // device scalars
 enum Sc {
@@ -700,6 +700,26 @@ int backward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>&
   return 0;
 }
 
+// Q-type sweep with an arbitrary symmetric ld x ld matrix W in place of iKx:  M_Q = sum_n A_n W A_n^T  over the
+// frozen regime's Ahx blocks (the z = False contraction of _optimal_q, src/core/cgpcm.py:473-475).
+int q_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& chunks, const double* W) {
+  zero(h, h->M(M_Q), h->ld * h->ld);
+  if (sym_begin(h, 1)) return -2;
+  const bool st = h->use_store;
+  const bool have_a = st && h->storeA_frozen_valid;
+  for (const Chunk& ch : chunks) {
+    double* Ab = st ? h->storeA + ch.off : h->wsA;
+    if (!have_a && gen_chunk(h, c, ch, false, Ab)) return -2;
+    const long cols = (long)ch.nc * ch.kwp;
+    if (right_mul_sym(h, Ab, W, ch, h->wsV)) return -2;
+    if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, Ab, cols, h->wsV, cols, 1, 0)) return -2;
+  }
+  if (st) h->storeA_frozen_valid = true;
+  if (sym_finish(h, 1, h->nhp, h->M(M_Q))) return -2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int allreduce(cgpcm_handle* h, double* buf, long count) {
   if (h->world <= 1 || !h->comm) return 0;
   ncclResult_t r = nccl().AllReduce(buf, buf, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->comm, h->st);
@@ -769,7 +789,8 @@ int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int
   cudaMemsetAsync(h->info, 0, 4 * sizeof(int), h->st);
   const long np = 5 + nh + (long)nh * (nh + 1) / 2;
   if (cudaMalloc(&h->params_d, np * sizeof(double)) != cudaSuccess) return fail(-2);
-  if (cudaMalloc(&h->gvar_d, np * sizeof(double)) != cudaSuccess) return fail(-2);
+  // packed gradient of the variables; also the packed Cholesky factor of q(z) in cgpcm_fpi (nx (nx + 1) / 2)
+  if (cudaMalloc(&h->gvar_d, std::max<long>(np, (long)nx * (nx + 1) / 2) * sizeof(double)) != cudaSuccess) return fail(-2);
   h->part_elems = std::max<long>(320 * 64 * 64, 100 * l2);
   if (cudaMalloc(&h->part, h->part_elems * sizeof(double)) != cudaSuccess) return fail(-2);
   for (int k = 0; k < 2; ++k)
@@ -1460,6 +1481,156 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   return 0;
 }
 
+// VCGPCM.fpi(num, z=True, high_reg) followed by convert(z=True) (src/core/cgpcm.py:479-516,577-592) on the frozen
+// Psi statistics: num rounds of  q(u) -> optimal q(z) -> optimal q(u)  (Normal.from_natural,
+// src/core/distribution.py:20-33), then the optimal q(z) of the final q(u).  Per round one C1-type sweep
+// (sum_n A_n^T m2_u A_n) and one Q-type sweep (sum_n A_n m2_z A_n^T) over the resident Ahx blocks.
+int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, double reg, double* mu_u, double* var_u,
+            double* mu_z, double* var_z) {
+  const int nh = h->nh, nx = h->nx, nhp = h->nhp, nxp = h->nxp;
+  const long ld = h->ld, l2 = ld * ld;
+  const long nvar = (long)nh * (nh + 1) / 2;
+  const long np = 5 + nh + nvar;
+  for (long i = 0; i < np; ++i)
+    if (!std::isfinite(params_host[i])) { h->err = "non-finite parameter"; return -4; }
+  if (!h->frozen) { h->err = "cgpcm_fpi requires cgpcm_precompute"; return -1; }
+  const double s2 = exp(params_host[0]), s2f = exp(params_host[1]);
+  const double alpha = exp(params_host[2]), gamma = exp(params_host[3]), omega = exp(params_host[4]);
+  const double r = s2f / s2, c0 = sqrt(s2f) / s2;
+  const double hr = high_reg ? 1e-4 : 0.0;
+  if (ensure_sweep_buffers(h)) return -2;
+  h->launches = 0;
+  h->pev_used = 0;
+  h->gemm_flops = h->gemm_flops_exec = 0.0;
+  h->gemm_launches = 0;
+  PsiConst c;
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
+  std::vector<Chunk> chunks;
+  plan_chunks(h, h->fc, chunks);
+  cudaStream_t st = h->st;
+  CK(cudaEventRecord(h->ev[0], st));
+  CK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
+  CK(cudaMemcpyAsync(h->params_d, params_host, np * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (prior_stage(h, c, reg)) return -2;
+  if (plan_store(h, chunks, false)) return -2;
+  double* Lq = h->M(M_LQ);
+  double* mu = h->V(V_MU);
+  double* muz = h->V(V_MUZ);
+  double* var = h->M(M_VAR);
+  double* Hm = h->M(M_H);
+  {
+    const double* pd = h->params_d;
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      Lq[idx] = (i < nh && j <= i) ? pd[5 + nh + (long)i * (i + 1) / 2 + j] : 0.0;
+      if (idx < ld) mu[idx] = idx < nh ? pd[5 + idx] : 0.0;
+    });
+    L(h);
+    if (mm(h, Lq, false, Lq, true, var, nhp, nhp, nhp)) return -2;
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      if (i == j && i < nh) var[idx] += reg;      // self.h = Normal(reg(L L^T), mu_u)  (cgpcm.py:444-445)
+    });
+    L(h);
+  }
+  for (int it = 0; it <= num; ++it) {
+    // optimal q(z) given q(u)
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      Hm[idx] = var[idx] + mu[i] * mu[j];
+    });
+    L(h);
+    if (forward_sweep(h, h->fc, chunks, Hm, nullptr, false, false)) return -2;
+    if (allreduce(h, h->M(M_C1), l2)) return -2;
+    {
+      double* Pm = h->M(M_LP);
+      const double* kx = h->M(M_KX);
+      const double* fb = h->M(M_F_AXX);      // frozen sum_Bxx
+      const double* c1 = h->M(M_C1);
+      const double hrz = it < num ? hr : 0.0;      // convert() (the last half round) never uses high_reg
+      ew(st, l2, [=] __device__(long idx) {
+        int i = (int)(idx / ld), j = (int)(idx % ld);
+        Pm[idx] = kx[idx] + r * (fb[idx] + c1[idx]) + ((i == j && i < nx) ? hrz + reg : 0.0);
+      });
+      L(h);
+    }
+    if (chol_inv(h, h->M(M_LP), h->M(M_PINV), nx, nxp, nullptr, 3)) return -2;
+    matvec(h, h->M(M_F_Y), nx, nh, 1, mu, c0, h->V(V_LAM));                  // lam = c0 Y^T mean_u
+    matvec(h, h->M(M_PINV), nx, nx, 0, h->V(V_LAM), 1.0, muz);               // mean_z = var_z lam
+    if (it == num) break;
+    // optimal q(u) given q(z)
+    {
+      double* W = h->M(M_WX);
+      const double* vz = h->M(M_PINV);
+      ew(st, l2, [=] __device__(long idx) {
+        int i = (int)(idx / ld), j = (int)(idx % ld);
+        W[idx] = vz[idx] + muz[i] * muz[j];
+      });
+      L(h);
+    }
+    if (q_sweep(h, h->fc, chunks, h->M(M_WX))) return -2;
+    if (allreduce(h, h->M(M_Q), l2)) return -2;
+    {
+      double* Pu = h->M(M_SO);
+      const double* kh0 = h->M(M_KH0);
+      const double* fb = h->M(M_F_BHH);
+      const double* q = h->M(M_Q);
+      ew(st, l2, [=] __device__(long idx) {
+        int i = (int)(idx / ld), j = (int)(idx % ld);
+        Pu[idx] = kh0[idx] + r * (fb[idx] + q[idx]) + ((i == j && i < nh) ? reg + hr + reg : 0.0);   // Kh = reg(Kh0)
+      });
+      L(h);
+    }
+    if (chol_inv(h, h->M(M_SO), var, nh, nhp, nullptr, 4)) return -2;
+    matvec(h, h->M(M_F_Y), nh, nx, 0, muz, c0, h->V(V_LAM));                 // lam = c0 Y mean_z
+    matvec(h, var, nh, nh, 0, h->V(V_LAM), 1.0, mu);                         // mean_u = var_u lam (padding stays 0)
+  }
+  // outputs: means, and the Cholesky factors of the covariances in np.tril_indices order
+  auto emit = [&](const double* mean, const double* cov, int n, int npad, double* mean_out, double* chol_out, int tag) -> int {
+    if (mean_out) CK(cudaMemcpyAsync(mean_out, mean, n * sizeof(double), cudaMemcpyDefault, st));
+    if (!chol_out) return 0;
+    double* Lc = h->M(M_T1);
+    CK(cudaMemcpyAsync(Lc, cov, l2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (chol_inv(h, Lc, nullptr, n, npad, nullptr, tag)) return -2;
+    double* g = h->gvar_d;
+    const long nv = (long)n * (n + 1) / 2;
+    ew(st, nv, [=] __device__(long e) {
+      long i = (long)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+      while ((i + 1) * (i + 2) / 2 <= e) ++i;
+      while (i * (i + 1) / 2 > e) --i;
+      g[e] = Lc[i * ld + (e - i * (i + 1) / 2)];
+    });
+    L(h);
+    CK(cudaMemcpyAsync(chol_out, g, nv * sizeof(double), cudaMemcpyDefault, st));
+    return 0;
+  };
+  if (emit(mu, var, nh, nhp, mu_u, var_u, 5)) return -2;
+  if (emit(muz, h->M(M_PINV), nx, nxp, mu_z, var_z, 3)) return -2;
+  int info[4];
+  CK(cudaMemcpyAsync(info, h->info, sizeof info, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(h->ev[6], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (info[0]) {
+    static const char* names[] = {"?", "Kh", "Kx", "P of q(z)", "P of q(u)", "a q covariance"};
+    int tag = info[0] / 100000;
+    char b[160];
+    snprintf(b, sizeof b, "matrix %s is not positive definite (pivot %d)", tag >= 1 && tag <= 5 ? names[tag] : "?",
+             info[0] % 100000);
+    h->err = b;
+    return -3;
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+  memset(h->timing, 0, sizeof h->timing);
+  h->timing[0] = ms;
+  h->timing[6] = (double)h->launches;
+  h->timing[7] = h->gemm_flops;
+  h->timing[8] = (double)h->gemm_launches;
+  h->timing[9] = h->gemm_flops_exec;
+  return 0;
+}
+
 }  // namespace cgimpl
 
 extern "C" {
@@ -1480,6 +1651,18 @@ int cgpcm_precompute(cgpcm_handle* h, const double hyp[3], double reg) {
   CK(cudaSetDevice(h->device));
   double p5[5] = {0.0, 0.0, log(hyp[0]), log(hyp[1]), log(hyp[2])};
   return evaluate(h, p5, CGPCM_MODE_FULL, 0, reg, true, nullptr, nullptr, nullptr);
+}
+
+int cgpcm_fpi(cgpcm_handle* h, const double* params, int32_t num, int32_t high_reg, double reg, double* mu_u,
+              double* var_u, double* mu_z, double* var_z) {
+  if (!h || !params || num < 0) return -1;
+  if (!h->t) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  if (!std::isfinite(reg) || reg < 0) { h->err = "reg must be finite and >= 0"; return -4; }
+  CK(cudaSetDevice(h->device));
+  const long np = 5 + h->nh + (long)h->nh * (h->nh + 1) / 2;
+  std::vector<double> host;
+  if (fetch_params(h, params, np, host)) return -2;
+  return fpi_run(h, host.data(), num, high_reg, reg, mu_u, var_u, mu_z, var_z);
 }
 
 int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_t grad_mask, double reg, double* elbo,

@@ -109,6 +109,17 @@ class Engine(object):
                                              _lib.ptr(elbo), _lib.ptr(terms), _lib.ptr(grad)))
         return float(elbo[0]), terms, grad
 
+    def fpi(self, params, num, high_reg=False, reg=1e-8):
+        """``num`` rounds of the fixed-point iteration on the frozen Psi statistics, then the optimal q(z):
+        ``(mu_u[nh], var_u[nh(nh+1)/2], mu_z[nx], var_z[nx(nx+1)/2])`` (``src/core/cgpcm.py:479-516,577-592``)."""
+        if int(params.shape[0]) != n_params(self.nh):
+            raise ValueError('params must have length %d' % n_params(self.nh))
+        mu_u, var_u = np.empty(self.nh), np.empty(self.nh * (self.nh + 1) // 2)
+        mu_z, var_z = np.empty(self.nx), np.empty(self.nx * (self.nx + 1) // 2)
+        self._ck(_lib.lib().cgpcm_fpi(self._h, _lib.ptr(params), int(num), int(bool(high_reg)), float(reg),
+                                       _lib.ptr(mu_u), _lib.ptr(var_u), _lib.ptr(mu_z), _lib.ptr(var_z)))
+        return mu_u, var_u, mu_z, var_z
+
     def last_timing(self):
         t = np.zeros(12)
         self._ck(_lib.lib().cgpcm_last_timing(self._h, _lib.ptr(t)))

@@ -89,6 +89,15 @@ int cgpcm_precompute(cgpcm_handle* h, const double hyp[3], double reg);
 int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_t grad_mask, double reg,
                     double* elbo, double* terms, double* grad);
 
+/* mod.fpi(num, z=True, high_reg) followed by mod.convert(z=True) (src/core/cgpcm.py:479-516,577-592): num rounds of
+ * the fixed-point iteration q(u) -> optimal q(z) -> optimal q(u) on the Psi statistics frozen by cgpcm_precompute
+ * (Normal.from_natural, src/core/distribution.py:20-33; high_reg adds 1e-4 to both precisions), starting from the
+ * q(u) in params.  Outputs (each may be NULL; host or device): mu_u[nh], var_u[nh(nh+1)/2] = tril_to_vec(chol(cov))
+ * as the reference assigns them, and the optimal q(z) of the final q(u): mu_z[nx], var_z[nx(nx+1)/2].
+ * num = 0 is convert(z=True) alone. */
+int cgpcm_fpi(cgpcm_handle* h, const double* params, int32_t num, int32_t high_reg, double reg, double* mu_u,
+              double* var_u, double* mu_z, double* var_z);
+
 /* Timing of the last cgpcm_elbo_grad / cgpcm_psi on the handle's stream (CUDA events, ms):
  * out[0] total device time, out[1] forward sweep, out[2] backward sweep, out[3] M x M algebra,
  * out[4] Axx kernel, out[5] contraction GEMM kernels (exact sum with option "profile", else the sweeps

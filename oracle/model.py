@@ -356,3 +356,53 @@ def init_q(th, alpha, gamma, r, rng, scale=0.1):
     var_u = tril_to_vec(torch.linalg.cholesky(reg(iKh, r))).numpy()
     mu_u = scale * rng.standard_normal(len(th))
     return mu_u, var_u
+
+
+# ----------------------------------------------------------------------------- fixed-point iteration
+def optimal_q(m, k, s2, s2_f, mean, m2, z):
+    """``VCGPCM._optimal_q`` (``cgpcm.py:458-477``): natural parameters ``(lam, P)`` of the optimal q(z) given the
+    moments of q(u) (``z=True``) or of the optimal q(u) given the moments of q(z) (``z=False``)."""
+    if z:
+        lam = s2_f ** .5 / s2 * (m['sum_Ahx_y'].T @ mean)
+        S = m['sum_Bxx'] + torch.sum(m['Ahx'].transpose(-1, -2) @ (m2 @ m['Ahx']), 0)
+        K = k['Kx']
+    else:
+        lam = s2_f ** .5 / s2 * (m['sum_Ahx_y'] @ mean)
+        S = m['sum_Bhh'] + torch.sum(m['Ahx'] @ (m2 @ m['Ahx'].transpose(-1, -2)), 0)
+        K = k['Kh']
+    return lam, K + s2_f / s2 * S
+
+
+def from_natural(P, lam, r):
+    """``Normal.from_natural`` (``distribution.py:20-33``): ``(mean, var)`` of ``N(reg(P)^-1 lam, reg(P)^-1)``."""
+    L = torch.linalg.cholesky(reg(P, r))
+    return torch.cholesky_solve(lam, L), cholinv(L)
+
+
+def fpi(params, t, y, th, tx, r, num, causal=True, high_reg=False):
+    """``VCGPCM.fpi(num, z=True, high_reg)`` (``cgpcm.py:479-516``): ``num`` rounds of
+    q(u) -> optimal q(z) -> optimal q(u).  Returns ``(mu_u, var_u)`` as the reference assigns them
+    (``var_u = tril_to_vec(cholesky(var))``) plus the last q(z) as ``(mu_z, var_z)`` in the same packing (what
+    ``convert(z=True)``, ``cgpcm.py:577-592``, assigns when called with ``num = 0`` rounds before it)."""
+    with torch.no_grad():
+        nh = len(th)
+        s2, s2_f, alpha, gamma, omega, mu_u, var_u = unpack(T(np.asarray(params, np.float64)), nh)
+        k = prior_kernels(th, tx, alpha, gamma, omega, r)
+        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal)
+        m = model_matrices(y, a, Ahh, Axx, Ahx, k['iKh'], k['iKx'])
+        Lq = vec_to_tril(var_u)
+        mean, var = mu_u, reg(Lq @ Lq.T, r)                       # self.h (cgpcm.py:444-445)
+        for _ in range(num):
+            lam, P = optimal_q(m, k, s2, s2_f, mean, var + mean @ mean.T, True)
+            if high_reg:
+                P = reg(P, 1e-4)
+            mz, vz = from_natural(P, lam, r)
+            lam, P = optimal_q(m, k, s2, s2_f, mz, vz + mz @ mz.T, False)
+            if high_reg:
+                P = reg(P, 1e-4)
+            mean, var = from_natural(P, lam, r)
+        lam, P = optimal_q(m, k, s2, s2_f, mean, var + mean @ mean.T, True)   # convert(z=True)
+        mz, vz = from_natural(P, lam, r)
+        out = [mean.numpy().ravel().copy(), tril_to_vec(torch.linalg.cholesky(var)).numpy().copy(),
+               mz.numpy().ravel().copy(), tril_to_vec(torch.linalg.cholesky(vz)).numpy().copy()]
+    return out

@@ -70,3 +70,24 @@ def test_frozen_regime_matches_full_at_freeze_point():
     np.testing.assert_allclose(full[2][:2], froz[2][:2], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(full[2][5:], froz[2][5:], rtol=1e-9, atol=1e-8)
     assert np.all(froz[2][2:5] == 0)
+
+
+def test_fpi_is_coordinate_ascent():
+    """oracle.fpi (src/core/cgpcm.py:479-516): every round of the fixed-point iteration raises the saturated ELBO,
+    and convert's q(z) is the optimal q(z) of the final q(u) (its mean solves reg(P) mz = lam)."""
+    c = make_case('toy_small')
+    args = (c['t'], c['y'], c['th'], c['tx'], c['reg'])
+    e = [om.elbo_and_grad(c['params'], *args)[0]]
+    for num in (1, 2, 5):
+        mu, var, mz, vz = om.fpi(c['params'], *args, num)
+        p = c['params'].copy()
+        p[5:5 + c['nh']] = mu
+        p[5 + c['nh']:] = var
+        e.append(om.elbo_and_grad(p, *args)[0])
+    assert e[0] < e[1] < e[2] < e[3]
+    # num = 0: q(u) is returned unchanged (up to the Cholesky round trip of reg(L L^T))
+    mu0, var0, _, _ = om.fpi(c['params'], *args, 0)
+    np.testing.assert_allclose(mu0, c['params'][5:5 + c['nh']], rtol=0, atol=1e-15)
+    L = om.vec_to_tril(om.T(c['params'][5 + c['nh']:])).numpy()
+    L0 = om.vec_to_tril(om.T(var0)).numpy()
+    np.testing.assert_allclose(L0 @ L0.T, L @ L.T + c['reg'] * np.eye(c['nh']), rtol=1e-12, atol=1e-14)
