@@ -116,8 +116,10 @@ __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* S
         for (int mb = 0; mb < MB; ++mb) {
           dmma_8x8x4(acc[mb][0][0], acc[mb][0][1], fa[mb], fb[k4 & 1][0]);
           dmma_8x8x4(acc[mb][1][0], acc[mb][1][1], fa[mb], fb[k4 & 1][1]);
-          if (more) fa[mb] = Sk[mb * 8 * sk + (k4 + 1) * 4];
+          // reload one block behind: the DMMAs that still read fa[mb] have a head start on the overwriting load
+          if (more && mb >= 1) fa[mb - 1] = Sk[(mb - 1) * 8 * sk + (k4 + 1) * 4];
         }
+        if (more) fa[MB - 1] = Sk[(MB - 1) * 8 * sk + (k4 + 1) * 4];
       }
     }
     __syncwarp();
