@@ -154,8 +154,6 @@ struct cgpcm_handle {
   long storeA_elems = 0, storeT_elems = 0;
   bool use_store = false;      // decided per evaluation
   bool storeA_frozen_valid = false;   // storeA holds the frozen regime's Ahx blocks (constant between evaluations)
-  double* part = nullptr;      // split-K partials
-  long part_elems = 0;
   double* symacc[2] = {nullptr, nullptr};   // per-K-slice private accumulators of the symmetric contractions
   int sym_used[2] = {0, 0};                 // slices touched since sym_begin
   double* axx_part = nullptr;
@@ -791,8 +789,6 @@ int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int
   if (cudaMalloc(&h->params_d, np * sizeof(double)) != cudaSuccess) return fail(-2);
   // packed gradient of the variables; also the packed Cholesky factor of q(z) in cgpcm_fpi (nx (nx + 1) / 2)
   if (cudaMalloc(&h->gvar_d, std::max<long>(np, (long)nx * (nx + 1) / 2) * sizeof(double)) != cudaSuccess) return fail(-2);
-  h->part_elems = std::max<long>(320 * 64 * 64, 100 * l2);
-  if (cudaMalloc(&h->part, h->part_elems * sizeof(double)) != cudaSuccess) return fail(-2);
   for (int k = 0; k < 2; ++k)
     if (cudaMalloc(&h->symacc[k], (size_t)SY_MAX_SPLITS * l2 * sizeof(double)) != cudaSuccess) return fail(-2);
   if (cudaMalloc(&h->cheb_d, (BVN_CHEB_MAXDEG + 1) * 20 * sizeof(double)) != cudaSuccess) return fail(-2);
@@ -813,7 +809,7 @@ int cgpcm_destroy(cgpcm_handle* h) {
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->comm && h->own_comm && nccl().ok) nccl().CommDestroy(h->comm);
   double* ptrs[] = {h->t, h->y, h->th, h->tx, h->mats, h->vecs, h->sc, h->params_d, h->gvar_d, h->wsA, h->wsT,
-                    h->wsV, h->part, h->axx_part, h->ypart, h->gpart, h->symacc[0], h->symacc[1], h->storeA, h->storeT, h->cheb_d};
+                    h->wsV, h->axx_part, h->ypart, h->gpart, h->symacc[0], h->symacc[1], h->storeA, h->storeT, h->cheb_d};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   if (h->info) cudaFree(h->info);

@@ -1,14 +1,34 @@
 #!/bin/bash
-# One GPU session: parity tests, GEMM micro-bench, bench line, ncu launch lists. Outputs under gpurun_out/<tag>/.
-TAG=${1:-r01}
+# One GPU session under gpurun: `bash tools/gpu_round.sh <tag> [steps...]`, outputs under gpurun_out/<tag>/.
+#   tests    python -m pytest tests -m gpu
+#   gemm     GEMM micro-benchmark of the three DMMA kernels on the contraction shapes of one dense chunk
+#   steps    one evaluation at the bench shape: dense, culled, frozen (tools/profile_step.py)
+#   bench    bench.py (ours + reference arm)
+#   launches ncu launch lists of one dense and one culled evaluation
+#   ncu-sl / ncu-sym / ncu-axx   ncu --set full of the named kernel inside one dense evaluation
+TAG=${1:-run}; shift
+STEPS=${@:-tests gemm steps}
 O=gpurun_out/$TAG
 mkdir -p $O
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $O/smi.log 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
-timeout 300 python tools/gemm_bench.py 512 5 > $O/gemm_bench.log 2>&1
-timeout 900 python bench.py --steps 5 --warmup 3 > $O/bench_dense.json 2> $O/bench_dense.err
-timeout 600 python tools/profile_step.py --cull 0 > $O/ps_dense.log 2>&1
-timeout 600 python tools/profile_step.py --cull 80 > $O/ps_cull.log 2>&1
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/launches_dense.csv python tools/profile_step.py --cull 0 > $O/ncu_dense.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/launches_cull.csv python tools/profile_step.py --cull 80 > $O/ncu_cull.log 2>&1
-tail -3 $O/pytest_gpu.log; cat $O/gemm_bench.log; cat $O/bench_dense.json; cat $O/ps_dense.log $O/ps_cull.log
+for S in $STEPS; do
+  case $S in
+    tests) timeout 1500 python -m pytest tests -m gpu -q -x > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -4 $O/pytest_gpu.log;;
+    gemm) timeout 300 python tools/gemm_bench.py 512 5 > $O/gemm_bench.log 2>&1; cat $O/gemm_bench.log;;
+    steps) timeout 600 python tools/profile_step.py --cull 0 > $O/ps_dense.log 2>&1
+           timeout 600 python tools/profile_step.py --cull 80 > $O/ps_cull.log 2>&1
+           timeout 600 python tools/profile_step.py --cull 80 --mode 0 > $O/ps_frozen.log 2>&1
+           cat $O/ps_dense.log $O/ps_cull.log $O/ps_frozen.log;;
+    bench) timeout 900 python bench.py --steps 5 --warmup 3 > $O/bench.json 2> $O/bench.err
+           timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err
+           cat $O/bench.json $O/bench_ref.json; tail -2 $O/bench.err;;
+    launches) timeout 600 python tools/profile_step.py --cull 0 > $O/ps_dense.log 2>&1 && \
+           timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/launches_dense.csv python tools/profile_step.py --cull 0 > $O/ncu_dense.log 2>&1
+           timeout 600 python tools/profile_step.py --cull 80 > $O/ps_cull.log 2>&1 && \
+           timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/launches_cull.csv python tools/profile_step.py --cull 80 > $O/ncu_cull.log 2>&1;;
+    ncu-sl|ncu-sym|ncu-axx)
+           K=${S#ncu-}; R=dgemm_sl; [ $K = sym ] && R=dgemm_sym; [ $K = axx ] && R=axx_sum
+           SK=6; [ $K = axx ] && SK=0
+           timeout 600 python tools/profile_step.py --cull 0 > $O/ps_dense.log 2>&1 && \
+           timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$R -s $SK -c 3 -o $O/${K}_prof python tools/profile_step.py --cull 0 > $O/ncu_$K.log 2>&1; tail -2 $O/ncu_$K.log;;
+  esac
+done
