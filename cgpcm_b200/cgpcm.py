@@ -15,7 +15,7 @@ import numpy as np
 from . import config
 from .engine import (Engine, TERM_NAMES, GRAD_S2, GRAD_S2F, GRAD_ALPHA, GRAD_GAMMA, GRAD_OMEGA, GRAD_MU_U,
                      GRAD_VAR_U, MODE_FROZEN, MODE_FULL)
-from .util import length_scale, to_float, tril_to_vec
+from .util import length_scale, to_float, tril_to_vec, vec_to_tril
 
 _HEAD = ['s2', 's2_f', 'alpha', 'gamma', 'omega']
 _MASK = {'s2': GRAD_S2, 's2_f': GRAD_S2F, 'alpha': GRAD_ALPHA, 'gamma': GRAD_GAMMA, 'omega': GRAD_OMEGA,
@@ -75,6 +75,8 @@ class Term(object):
         self.objective, self.index = objective, index
 
     def eval(self):
+        if hasattr(self.objective, '_run'):
+            return self.objective._run()[1][self.index]
         return self.objective.mod._evaluate(want_grad=False)[1][self.index]
 
 
@@ -83,6 +85,7 @@ class Objective(object):
 
     def __init__(self, mod, sign=1.0):
         self.mod, self.sign = mod, sign
+        self.smf = False
 
     def __neg__(self):
         return Objective(self.mod, -self.sign)
@@ -96,6 +99,23 @@ class Objective(object):
         names = [v.name for v in var_list]
         e, _, g = self.mod._evaluate(want_grad=True, names=names)
         return self.sign * e, self.sign * self.mod._slice_grad(g, names)
+
+
+class SmfObjective(object):
+    """``elbo(smf=True, sample=...)`` (``src/core/cgpcm.py:527-531``) as a lazy scalar; no gradient."""
+
+    def __init__(self, mod, sample=None, sign=1.0):
+        self.mod, self.sample, self.sign = mod, sample, sign
+
+    def __neg__(self):
+        return SmfObjective(self.mod, self.sample, -self.sign)
+
+    def _run(self):
+        s = self.sample if self.sample is not None else self.mod.sample_q()
+        return self.mod._evaluate_smf(s)
+
+    def eval(self):
+        return self.sign * self._run()[0]
 
 
 class Session(object):
@@ -312,9 +332,14 @@ class VCGPCM(CGPCM):
 
     def elbo(self, smf=False, sample=None, z=True):
         """Construct the ELBO: ``(elbo, terms)`` with ``terms`` the 7 named fetches
-        (``src/core/cgpcm.py:518-575``)."""
-        if smf or sample is not None or not z:
-            raise NotImplementedError('only the saturated q(z) bound (smf=False, z=True) is accelerated')
+        (``src/core/cgpcm.py:518-575``).  ``smf=True``: the stochastic SMF bound at ``sample`` (a fresh draw from
+        q(u) per evaluation if ``None``); value only."""
+        if not z:
+            raise NotImplementedError('only the bound saturated for q(z) (z=True) is accelerated')
+        if smf:
+            obj = SmfObjective(self, sample)
+            terms = [{'name': nm, 'tensor': Term(obj, i), 'modifier': '.2e'} for i, nm in enumerate(TERM_NAMES)]
+            return obj, terms
         obj = Objective(self)
         terms = [{'name': nm, 'tensor': Term(obj, i), 'modifier': '.2e'} for i, nm in enumerate(TERM_NAMES)]
         return obj, terms
@@ -346,6 +371,45 @@ class VCGPCM(CGPCM):
         _, _, mu_z, var_z = self._fpi(0, False)
         self.vars['mu_z'] = Var('mu_z', mu_z.reshape(-1, 1))
         self.vars['var_z'] = Var('var_z', var_z)
+
+    # -- SMF bound and posterior samples of the filter (src/core/cgpcm.py:527-531,594-608,848-872)
+    def _evaluate_smf(self, sample):
+        mode = MODE_FROZEN if self._precomputed else MODE_FULL
+        return self.engine.elbo_smf(self._pack(), sample, mode=mode, reg=config.reg)
+
+    def _q_cov_factor(self):
+        L = vec_to_tril(self.vars['var_u'].value)
+        return np.linalg.cholesky(L @ L.T + config.reg * np.eye(self.nh))
+
+    def sample_q(self):
+        """A draw from q(u) = N(mu_u, reg(L L^T)) (``Normal.sample``, ``src/core/distribution.py:44-58``)."""
+        return self.vars['mu_u'].value.reshape(-1, 1) + self._q_cov_factor() @ np.random.randn(self.nh, 1)
+
+    def sample_prior(self):
+        """A draw from the prior of ``K_u^-1 u``: ``N(0, reg(iKh))`` (``src/core/cgpcm.py:219-220``)."""
+        alpha, gamma = self.alpha.eval(), self.gamma.eval()
+        th = self.th
+        Kh = np.exp(-alpha * (th[:, None] ** 2 + th[None, :] ** 2) - gamma * (th[:, None] - th[None, :]) ** 2)
+        Lh = np.linalg.cholesky(Kh + config.reg * np.eye(self.nh))
+        iLh = np.linalg.solve(Lh, np.eye(self.nh))
+        Lp = np.linalg.cholesky(iLh.T @ iLh + config.reg * np.eye(self.nh))
+        return Lp @ np.random.randn(self.nh, 1)
+
+    def elbo_smf(self, samples_h):
+        """Monte-Carlo estimate of the SMF bound: ``(mean, standard error)`` (``src/core/cgpcm.py:594-608``)."""
+        elbos = [self._evaluate_smf(x)[0] for x in samples_h]
+        return np.mean(elbos), np.std(elbos) / len(samples_h) ** .5
+
+    def sample(self, iters=200, burn=None):
+        """Samples from the posterior over filters by elliptical slice sampling (``src/core/cgpcm.py:848-872``)."""
+        from .sample import ESS
+        if burn is None:
+            burn = iters
+        ess = ESS(lambda x: self._evaluate_smf(x)[2], self.sample_prior)
+        ess.move(self.vars['mu_u'].value.reshape(-1, 1))
+        if burn > 0:
+            ess.sample(burn)
+        return ess.sample(iters)
 
     @property
     def mats(self):

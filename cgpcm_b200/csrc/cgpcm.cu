@@ -91,13 +91,13 @@ enum Mat {
 };
 
 // vector slots (each ld doubles)
-enum Vec { V_MU, V_YTMU, V_LAM, V_LBAR, V_ISOMU, V_MUBAR, V_YLBAR, V_M2BMU, V_MUZ, V_COUNT };
+enum Vec { V_MU, V_YTMU, V_LAM, V_LBAR, V_ISOMU, V_MUBAR, V_YLBAR, V_M2BMU, V_MUZ, V_SMP, V_COUNT };
 
 // device scalars
 enum Sc {
   S_LOGDET_KX, S_LOGDET_P, S_LOGDET_SO, S_LOGDET_VAR, S_TR_IKH_AHH, S_TR_IKX_AXX, S_TR_IKH_Q, S_TR_BHH_M2,
   S_TR_ISO_VAR, S_MU_ISO_MU, S_LAM_LBAR, S_PBAR_S, S_C0BAR, S_G_KH_A, S_G_KH_G, S_G_KX_O, S_G_AHH_A,
-  S_G_AHH_G, S_G_AXX_A, S_G_AXX_G, S_G_AXX_O, S_COUNT
+  S_G_AHH_G, S_G_AXX_A, S_G_AXX_G, S_G_AXX_O, S_LOGDET_P0, S_LAM_LBAR0, S_S_BHH_S, S_COUNT
 };
 
 struct Chunk {
@@ -1056,8 +1056,11 @@ namespace cgimpl {
 // The whole evaluation.  mode FULL: hyper-parameters from params; mode FROZEN: Psi sums from the frozen
 // state (precompute), prior kernels still from params (they stay symbolic in the reference too).
 // `freeze`: run the forward Psi sums only and store them (cgpcm_precompute).
+// `sample_host` (nh values, or NULL): the stochastic SMF bound elbo(smf=True, sample=...) (src/core/cgpcm.py:527-531):
+// the optimal q(z) is built from (sample, sample sample^T) instead of the moments of q(u); value only.  `loglik`
+// then also receives the pseudo-log-likelihood that VCGPCM.sample() hands to the slice sampler (cgpcm.py:857-866).
 int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad_mask, double reg, bool freeze,
-             double* elbo, double* terms, double* grad) {
+             double* elbo, double* terms, double* grad, const double* sample_host = nullptr, double* loglik = nullptr) {
   const int nh = h->nh, nx = h->nx, nhp = h->nhp, nxp = h->nxp;
   const long ld = h->ld, l2 = ld * ld;
   const long nvar = (long)nh * (nh + 1) / 2;
@@ -1110,6 +1113,12 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     double* var = h->M(M_VAR);
     double* lvar = h->M(M_LVAR);
     double* m2 = h->M(M_M2);
+    double* smp = h->V(V_SMP);
+    const bool smf = sample_host != nullptr;
+    if (smf) {
+      CK(cudaMemsetAsync(smp, 0, ld * sizeof(double), st));
+      CK(cudaMemcpyAsync(smp, sample_host, nh * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     ew(st, l2, [=] __device__(long idx) {
       int i = (int)(idx / ld), j = (int)(idx % ld);
       double v = var[idx] + ((i == j && i < nh) ? reg : 0.0);
@@ -1117,8 +1126,10 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
       lvar[idx] = v;
       double m = v + mu[i] * mu[j];
       m2[idx] = m;
+      // the second moment that enters the optimal q(z): q(u)'s, or sample sample^T for the SMF bound
+      const double mq = smf ? smp[i] * smp[j] : m;
       // FULL: H = m2 - iKh.  FROZEN: the frozen sum_Bxx already carries -sum A^T iKh A, so H = m2.
-      Hm[idx] = full ? m - ikh_cur[idx] : m;
+      Hm[idx] = full ? mq - ikh_cur[idx] : mq;
     });
     L(h);
   } else {
@@ -1215,7 +1226,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   }
   if (chol_inv(h, Pm, h->M(M_PINV), nx, nxp, h->sc + S_LOGDET_P, 3)) return -2;
   const double* Ym = full ? h->M(M_Y) : h->M(M_F_Y);
-  matvec(h, Ym, nx, nh, 1, h->V(V_MU), 1.0, h->V(V_YTMU));                 // Y^T mu
+  matvec(h, Ym, nx, nh, 1, sample_host ? h->V(V_SMP) : h->V(V_MU), 1.0, h->V(V_YTMU));   // Y^T mu (or Y^T sample)
   matvec(h, h->M(M_PINV), nx, nx, 0, h->V(V_YTMU), c0, h->V(V_LBAR));       // lbar = Pinv lam, lam = c0 Y^T mu
   {
     const double* ytmu = h->V(V_YTMU);
@@ -1223,6 +1234,19 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     reduce_to(st, (long)nx, [=] __device__(long i) { return c0 * ytmu[i] * lbar[i]; }, h->sc + S_LAM_LBAR);
     reduce_to(st, (long)nx, [=] __device__(long i) { return ytmu[i] * lbar[i]; }, h->sc + S_C0BAR);
     L(h, 2);
+  }
+  if (sample_host && loglik) {
+    // sample(): L = chol(P) without jitter (cgpcm.py:856), log_lik = -1/2 logdet P + 1/2 |L^-1 lam|^2 - 1/2 r s^T sum_Bhh s
+    double* P0 = h->M(M_T1);
+    const double* kx = h->M(M_KX);
+    ew(st, l2, [=] __device__(long idx) { P0[idx] = kx[idx] + r * S[idx]; });
+    L(h);
+    if (chol_inv(h, P0, h->M(M_T2), nx, nxp, h->sc + S_LOGDET_P0, 3)) return -2;
+    matvec(h, h->M(M_T2), nx, nx, 0, h->V(V_YTMU), c0, h->V(V_LAM));
+    const double* ytmu = h->V(V_YTMU);
+    const double* l0 = h->V(V_LAM);
+    reduce_to(st, (long)nx, [=] __device__(long i) { return c0 * ytmu[i] * l0[i]; }, h->sc + S_LAM_LBAR0);
+    L(h);
   }
   // adjoint seeds: Pbar = -1/2 Pinv - 1/2 lbar lbar^T ; C1bar = r Pbar ; Wx = r (2 Pbar + iKx) ; Ybar = c0 mu lbar^T
   {
@@ -1290,6 +1314,10 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     CK(cudaMemcpyAsync(bhh, h->M(M_F_BHH), l2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
   }
   frob(h, bhh, h->M(M_M2), nh, nh, h->sc + S_TR_BHH_M2);
+  if (sample_host && loglik) {
+    matvec(h, bhh, nh, nh, 0, h->V(V_SMP), 1.0, h->V(V_M2BMU));
+    dot(h, h->V(V_SMP), h->V(V_M2BMU), nh, h->sc + S_S_BHH_S);
+  }
 
   if (want_grad) {
     // m2bar = Hbar - 1/2 r sum_Bhh ; varbar = m2bar - 1/2 (iSo - ivar) ; Lbar = tril(2 varbar L)
@@ -1455,6 +1483,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   for (int i = 0; i < 7; ++i) e += tm[i];
   if (terms) memcpy(terms, tm, sizeof tm);
   if (elbo) *elbo = e;
+  if (sample_host && loglik) *loglik = -0.5 * hs[S_LOGDET_P0] + 0.5 * hs[S_LAM_LBAR0] - 0.5 * r * hs[S_S_BHH_S];
   if (want_grad) {
     const double rbar = hs[S_PBAR_S] - 0.5 * sum_b - 0.5 * tr_bhh_m2;
     const double c0bar = hs[S_C0BAR];
@@ -1647,6 +1676,34 @@ int cgpcm_precompute(cgpcm_handle* h, const double hyp[3], double reg) {
   CK(cudaSetDevice(h->device));
   double p5[5] = {0.0, 0.0, log(hyp[0]), log(hyp[1]), log(hyp[2])};
   return evaluate(h, p5, CGPCM_MODE_FULL, 0, reg, true, nullptr, nullptr, nullptr);
+}
+
+int cgpcm_elbo_smf(cgpcm_handle* h, const double* params, int32_t mode, double reg, const double* sample, double* elbo,
+                   double* terms, double* loglik) {
+  if (!h || !params || !sample || !elbo) return -1;
+  if (mode != CGPCM_MODE_FROZEN && mode != CGPCM_MODE_FULL) { h->err = "bad mode"; return -1; }
+  if (!h->t) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  if (!std::isfinite(reg) || reg < 0) { h->err = "reg must be finite and >= 0"; return -4; }
+  CK(cudaSetDevice(h->device));
+  const long np = 5 + h->nh + (long)h->nh * (h->nh + 1) / 2;
+  std::vector<double> host, smp(h->nh);
+  if (fetch_params(h, params, np, host)) return -2;
+  if (is_device_ptr(sample)) CK(cudaMemcpy(smp.data(), sample, h->nh * sizeof(double), cudaMemcpyDeviceToHost));
+  else memcpy(smp.data(), sample, h->nh * sizeof(double));
+  for (int i = 0; i < h->nh; ++i)
+    if (!std::isfinite(smp[i])) { h->err = "non-finite sample"; return -4; }
+  double e = 0.0, tm[7], ll = 0.0;
+  int rc = evaluate(h, host.data(), mode, 0u, reg, false, &e, tm, nullptr, smp.data(), &ll);
+  if (rc) return rc;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+  memset(h->timing, 0, sizeof h->timing);
+  h->timing[0] = ms;
+  h->timing[6] = (double)h->launches;
+  if (is_device_ptr(elbo)) cudaMemcpy(elbo, &e, sizeof e, cudaMemcpyHostToDevice); else *elbo = e;
+  if (terms) { if (is_device_ptr(terms)) cudaMemcpy(terms, tm, sizeof tm, cudaMemcpyHostToDevice); else memcpy(terms, tm, sizeof tm); }
+  if (loglik) { if (is_device_ptr(loglik)) cudaMemcpy(loglik, &ll, sizeof ll, cudaMemcpyHostToDevice); else *loglik = ll; }
+  return 0;
 }
 
 int cgpcm_fpi(cgpcm_handle* h, const double* params, int32_t num, int32_t high_reg, double reg, double* mu_u,

@@ -109,6 +109,17 @@ class Engine(object):
                                              _lib.ptr(elbo), _lib.ptr(terms), _lib.ptr(grad)))
         return float(elbo[0]), terms, grad
 
+    def elbo_smf(self, params, sample, mode=MODE_FULL, reg=1e-8):
+        """``elbo(smf=True, sample=sample)`` and the pseudo-log-likelihood of ``sample`` for the slice sampler:
+        ``(elbo, terms[7], log_lik)`` (``src/core/cgpcm.py:527-531,848-872``)."""
+        sample = np.ascontiguousarray(np.asarray(sample, dtype=np.float64).ravel())
+        if sample.shape[0] != self.nh or int(params.shape[0]) != n_params(self.nh):
+            raise ValueError('shape mismatch in elbo_smf')
+        elbo, terms, ll = np.empty(1), np.empty(7), np.empty(1)
+        self._ck(_lib.lib().cgpcm_elbo_smf(self._h, _lib.ptr(params), int(mode), float(reg), _lib.ptr(sample),
+                                            _lib.ptr(elbo), _lib.ptr(terms), _lib.ptr(ll)))
+        return float(elbo[0]), terms, float(ll[0])
+
     def fpi(self, params, num, high_reg=False, reg=1e-8):
         """``num`` rounds of the fixed-point iteration on the frozen Psi statistics, then the optimal q(z):
         ``(mu_u[nh], var_u[nh(nh+1)/2], mu_z[nx], var_z[nx(nx+1)/2])`` (``src/core/cgpcm.py:479-516,577-592``)."""

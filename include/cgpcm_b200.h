@@ -89,6 +89,13 @@ int cgpcm_precompute(cgpcm_handle* h, const double hyp[3], double reg);
 int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_t grad_mask, double reg,
                     double* elbo, double* terms, double* grad);
 
+/* The stochastic SMF bound `mod.elbo(smf=True, sample=h)` (src/core/cgpcm.py:527-531, used by elbo_smf :594-608): the
+ * optimal q(z) is built from (h, h h^T) instead of the moments of q(u).  sample[nh]; value only (elbo[1], terms[7]).
+ * loglik (may be NULL) receives the pseudo-log-likelihood of h that VCGPCM.sample() gives to the elliptical slice
+ * sampler (src/core/cgpcm.py:848-872; Cholesky of P without jitter, as there). */
+int cgpcm_elbo_smf(cgpcm_handle* h, const double* params, int32_t mode, double reg, const double* sample, double* elbo,
+                   double* terms, double* loglik);
+
 /* mod.fpi(num, z=True, high_reg) followed by mod.convert(z=True) (src/core/cgpcm.py:479-516,577-592): num rounds of
  * the fixed-point iteration q(u) -> optimal q(z) -> optimal q(u) on the Psi statistics frozen by cgpcm_precompute
  * (Normal.from_natural, src/core/distribution.py:20-33; high_reg adds 1e-4 to both precisions), starting from the

@@ -406,3 +406,35 @@ def fpi(params, t, y, th, tx, r, num, causal=True, high_reg=False):
         out = [mean.numpy().ravel().copy(), tril_to_vec(torch.linalg.cholesky(var)).numpy().copy(),
                mz.numpy().ravel().copy(), tril_to_vec(torch.linalg.cholesky(vz)).numpy().copy()]
     return out
+
+
+# ----------------------------------------------------------------------------- SMF bound and sampler target
+def elbo_smf(params, t, y, th, tx, r, sample, causal=True):
+    """``VCGPCM.elbo(smf=True, sample=sample)`` (``cgpcm.py:518-575``) and the pseudo-log-likelihood of
+    ``VCGPCM.sample`` (``cgpcm.py:848-866``) at ``h = sample``: ``(elbo, terms[7], log_lik)``."""
+    with torch.no_grad():
+        nh = len(th)
+        s2, s2_f, alpha, gamma, omega, mu_u, var_u = unpack(T(np.asarray(params, np.float64)), nh)
+        k = prior_kernels(th, tx, alpha, gamma, omega, r)
+        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal)
+        m = model_matrices(y, a, Ahh, Axx, Ahx, k['iKh'], k['iKx'])
+        yy = T(y)
+        n, sum_y2 = yy.shape[0], torch.sum(yy ** 2)
+        h = T(np.asarray(sample, np.float64)).reshape(-1, 1)
+        lam, P = optimal_q(m, k, s2, s2_f, h, h @ h.T, True)
+        L = torch.linalg.cholesky(reg(P, r))
+        Lq = vec_to_tril(var_u)
+        h_var = reg(Lq @ Lq.T, r)
+        h_m2 = h_var + mu_u @ mu_u.T
+        zero = torch.zeros(mu_u.shape, dtype=DT)
+        terms = [-.5 * n * torch.log(2 * math.pi * s2) - .5 * sum_y2 / s2,
+                 .5 * log_det(k['Lx']),
+                 -.5 * log_det(L),
+                 .5 * torch.sum(trisolve(L, lam) ** 2),
+                 -.5 * s2_f / s2 * m['sum_b'],
+                 -.5 * s2_f / s2 * trmul(m['sum_Bhh'], h_m2),
+                 -normal_kl(h_var, mu_u, reg(k['iKh'], r), zero)]
+        L0 = torch.linalg.cholesky(P)                                    # sample(): no jitter (cgpcm.py:856)
+        ll = (-.5 * log_det(L0) + .5 * torch.sum(trisolve(L0, lam) ** 2)
+              - .5 * s2_f / s2 * (h.T @ m['sum_Bhh'] @ h).squeeze())
+    return float(sum(terms)), np.array([float(x) for x in terms]), float(ll)

@@ -101,3 +101,18 @@ def oracle_noise_floor(params, t, y, th, tx, reg, causal=True, trials=4, seed=0)
         en = max(en, abs(e2 - e0))
         gn = max(gn, float(np.abs(g2 - g0).max()))
     return en, gn
+
+
+def ulp_noise(fn, params, th, trials=3, seed=0):
+    """Generic form of ``oracle_noise_floor``: ``fn(params, th)`` returns a tuple of scalars / arrays; the result is
+    the per-entry max-abs deviation of that tuple when ``params[:5]`` and ``th`` move by at most 2 ulp."""
+    rng = np.random.default_rng(seed)
+    base = fn(params, th)
+    noise = [0.0] * len(base)
+    for _ in range(trials):
+        p2 = np.array(params, dtype=np.float64)
+        p2[:5] = p2[:5] * (1 + rng.integers(-2, 3, 5) * 1.1e-16)
+        th2 = th * (1 + rng.integers(-2, 3, th.shape[0]) * 1.1e-16)
+        out = fn(p2, th2)
+        noise = [max(a, float(np.max(np.abs(np.asarray(x) - np.asarray(y))))) for a, x, y in zip(noise, out, base)]
+    return base, noise

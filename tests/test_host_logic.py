@@ -134,3 +134,21 @@ def test_tril_packing_matches_numpy_order():
     v = util.tril_to_vec(L)
     np.testing.assert_array_equal(v, L[np.tril_indices(4)])
     np.testing.assert_array_equal(util.vec_to_tril(v), L)
+
+
+def test_elliptical_slice_sampler_on_a_gaussian_target():
+    """cgpcm_b200.sample.ESS (interface of src/core/sample.py:8-130): prior N(0, I_2), likelihood N(x; m, s^2 I) ->
+    posterior N(m / (1 + s^2), s^2 / (1 + s^2) I); the chain's moments match within Monte-Carlo error."""
+    from cgpcm_b200.sample import ESS
+    rng = np.random.RandomState(0)
+    m, s2 = np.array([[1.5], [-0.5]]), 0.5
+    ess = ESS(lambda x: float(-.5 * np.sum((x - m) ** 2) / s2), lambda: rng.randn(2, 1), rng=rng)
+    ess.move(np.zeros((2, 1)))
+    ess.sample(200)
+    xs = np.concatenate(ess.sample(4000), 1)
+    want_mean, want_var = m.ravel() / (1 + s2), s2 / (1 + s2)
+    assert np.abs(xs.mean(1) - want_mean).max() < 0.06
+    assert np.abs(xs.var(1) - want_var).max() < 0.05
+    assert min(ess.attempts) >= 1 and np.mean(ess.attempts) < 6
+    one = ess.sample(1)
+    assert one.shape == (2, 1)
