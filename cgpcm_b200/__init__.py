@@ -6,7 +6,7 @@ FP64) behind the C-ABI of ``include/cgpcm_b200.h``.  There is no CPU fallback.
 """
 from . import config, learn, sample, util
 from .cgpcm import VCGPCM, CGPCM, Session, Var, Objective, shard_bounds
-from .data import Data
+from .data import Data, UncertainData
 from .engine import Engine, bvn_cdf, TERM_NAMES, n_params
 from ._lib import (build, lib, LIB_PATH, CgpcmError, GRAD_ALL, GRAD_S2, GRAD_S2F, GRAD_ALPHA, GRAD_GAMMA,
                    GRAD_OMEGA, GRAD_MU_U, GRAD_VAR_U, MODE_FROZEN, MODE_FULL)

@@ -411,6 +411,29 @@ class VCGPCM(CGPCM):
             ess.sample(burn)
         return ess.sample(iters)
 
+    def predict_f(self, t, samples_h=50, precompute=True):
+        """Predict the function at ``t`` (``src/core/cgpcm.py:781-846``).  ``samples_h`` numeric: that many draws
+        from q(u) with the optimal q(z) of q(u); a list of filter samples (e.g. from :meth:`sample`): the SMF
+        approximation, q(z | h) per sample.  Returns ``UncertainData(mean, lower, upper, std)`` of ``Data``."""
+        from .data import Data, UncertainData
+        t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
+        if np.isscalar(samples_h) or isinstance(samples_h, (int, np.integer)):
+            samples, smf = [self.sample_q() for _ in range(int(samples_h))], False
+        else:
+            samples, smf = list(samples_h), True
+        samples = np.stack([np.asarray(x, dtype=np.float64).ravel() for x in samples])
+        temporary = not self._precomputed
+        if temporary:
+            self.precompute()
+        try:
+            mu, var = self.engine.predict_f(self._pack(), t, samples, smf=smf, reg=config.reg)
+        finally:
+            if temporary:
+                self.undo_precompute()
+        std = np.maximum(var, 0) ** .5
+        return UncertainData(mean=Data(t, mu), lower=Data(t, mu - 2 * std), upper=Data(t, mu + 2 * std),
+                             std=Data(t, std))
+
     @property
     def mats(self):
         """Psi statistics at the current (or frozen) hyper-parameters as numpy arrays."""

@@ -31,6 +31,7 @@
 #include "dgemm_sl.cuh"
 #include "dgemm_sym.cuh"
 #include "linalg.cuh"
+#include "predict_kernels.cuh"
 #include "psi_kernels.cuh"
 
 using namespace cg;
@@ -1656,6 +1657,191 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
   return 0;
 }
 
+// VCGPCM.predict_f (src/core/cgpcm.py:781-846) for given filter samples: posterior mean and variance of the function
+// at the test inputs, averaged over the samples.  smf = 0: one optimal q(z) from the moments of q(u); smf = 1: the
+// optimal q(z | h) per sample.  Training side: the frozen regime's sweeps; test side: predict_kernels.cuh.
+int predict_run(cgpcm_handle* h, const double* params_host, double reg, const double* tstar_host, long n_star,
+                const double* samples_host, int B, int smf, double* mu_out, double* var_out) {
+  const int nh = h->nh, nx = h->nx, nhp = h->nhp, nxp = h->nxp;
+  const long ld = h->ld, l2 = ld * ld;
+  const long np = 5 + nh + (long)nh * (nh + 1) / 2;
+  for (long i = 0; i < np; ++i)
+    if (!std::isfinite(params_host[i])) { h->err = "non-finite parameter"; return -4; }
+  for (long i = 0; i < n_star; ++i)
+    if (!std::isfinite(tstar_host[i])) { h->err = "non-finite test input"; return -4; }
+  for (long i = 0; i < (long)B * nh; ++i)
+    if (!std::isfinite(samples_host[i])) { h->err = "non-finite sample"; return -4; }
+  if (!h->frozen) { h->err = "cgpcm_predict_f requires cgpcm_precompute"; return -1; }
+  const double s2 = exp(params_host[0]), s2f = exp(params_host[1]);
+  const double alpha = exp(params_host[2]), gamma = exp(params_host[3]), omega = exp(params_host[4]);
+  const double r = s2f / s2, c0 = sqrt(s2f) / s2;
+  if (ensure_sweep_buffers(h)) return -2;
+  h->launches = 0;
+  h->pev_used = 0;
+  h->gemm_flops = h->gemm_flops_exec = 0.0;
+  h->gemm_launches = 0;
+  PsiConst c;
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
+  PsiConst cd = c;                       // test-side statistics are evaluated densely (no windows)
+  cd.cull = 1e300;
+  BvnTab T;
+  bvn_make_tab(gamma / (alpha + gamma + omega), &T);
+  std::vector<Chunk> chunks;
+  plan_chunks(h, h->fc, chunks);
+  cudaStream_t st = h->st;
+  const int TC = std::min<long>(h->chunk, std::max<long>(n_star, 1));
+  const int nq = smf ? B : 1;            // distinct q(z)
+  // scratch of this call
+  double *d_t = nullptr, *d_x = nullptr, *d_mx = nullptr, *d_vec = nullptr, *d_q1 = nullptr, *d_acc = nullptr;
+  auto cleanup = [&]() {
+    double* ps[] = {d_t, d_x, d_mx, d_vec, d_q1, d_acc};
+    for (double* q : ps) if (q) cudaFree(q);
+  };
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[256]; snprintf(b_, sizeof b_, \
+    "CUDA error %s in predict_f (%s)", cudaGetErrorString(e_), #call); h->err = b_; cleanup(); return -2; } } while (0)
+#define PRC(call) do { if (call) { cleanup(); return -2; } } while (0)
+  PCK(cudaMalloc(&d_t, (size_t)std::max<long>(n_star, 1) * sizeof(double)));
+  PCK(cudaMalloc(&d_x, (size_t)TC * nx * nx * sizeof(double)));
+  PCK(cudaMalloc(&d_mx, (size_t)nq * l2 * sizeof(double)));
+  PCK(cudaMalloc(&d_vec, (size_t)(B + nq) * ld * sizeof(double)));      // samples h_b, then x_mean per q(z)
+  PCK(cudaMalloc(&d_q1, (size_t)B * sizeof(double)));
+  PCK(cudaMalloc(&d_acc, (size_t)2 * std::max<long>(n_star, 1) * sizeof(double)));
+  double* d_h = d_vec;
+  double* d_xm = d_vec + (long)B * ld;
+  PCK(cudaEventRecord(h->ev[0], st));
+  PCK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
+  PCK(cudaMemcpyAsync(h->params_d, params_host, np * sizeof(double), cudaMemcpyHostToDevice, st));
+  PCK(cudaMemcpyAsync(d_t, tstar_host, n_star * sizeof(double), cudaMemcpyHostToDevice, st));
+  PCK(cudaMemsetAsync(d_vec, 0, (size_t)(B + nq) * ld * sizeof(double), st));
+  PCK(cudaMemcpy2DAsync(d_h, ld * sizeof(double), samples_host, nh * sizeof(double), nh * sizeof(double), B,
+                        cudaMemcpyHostToDevice, st));
+  PCK(cudaMemsetAsync(d_acc, 0, (size_t)2 * std::max<long>(n_star, 1) * sizeof(double), st));
+  PRC(prior_stage(h, c, reg));
+  PRC(plan_store(h, chunks, false));
+  // q(u) moments
+  double* Lq = h->M(M_LQ);
+  double* mu = h->V(V_MU);
+  double* var = h->M(M_VAR);
+  double* Hm = h->M(M_H);
+  {
+    const double* pd = h->params_d;
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      Lq[idx] = (i < nh && j <= i) ? pd[5 + nh + (long)i * (i + 1) / 2 + j] : 0.0;
+      if (idx < ld) mu[idx] = idx < nh ? pd[5 + idx] : 0.0;
+    });
+    L(h);
+    PRC(mm(h, Lq, false, Lq, true, var, nhp, nhp, nhp));
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      if (i == j && i < nh) var[idx] += reg;
+    });
+    L(h);
+  }
+  frob(h, h->M(M_AHH), h->M(M_IKH), nh, nh, h->sc + S_TR_IKH_AHH);
+  const double a_val = (h->causal ? 0.5 : 1.0) * sqrt(3.14159265358979323846 / (2.0 * alpha));
+  // ---- training side: q(z) (once, or per sample) and the per-sample scalar q1
+  for (int b = 0; b < std::max(B, nq); ++b) {
+    const double* hb = d_h + (long)b * ld;
+    if (b < nq) {
+      const double* mvec = smf ? hb : mu;
+      const int smf_ = smf;
+      ew(st, l2, [=] __device__(long idx) {
+        int i = (int)(idx / ld), j = (int)(idx % ld);
+        Hm[idx] = smf_ ? mvec[i] * mvec[j] : var[idx] + mvec[i] * mvec[j];
+      });
+      L(h);
+      PRC(forward_sweep(h, h->fc, chunks, Hm, nullptr, false, false));
+      PRC(allreduce(h, h->M(M_C1), l2));
+      double* Pm = h->M(M_LP);
+      const double* kx = h->M(M_KX);
+      const double* fb = h->M(M_F_AXX);
+      const double* c1 = h->M(M_C1);
+      ew(st, l2, [=] __device__(long idx) {
+        int i = (int)(idx / ld), j = (int)(idx % ld);
+        Pm[idx] = kx[idx] + r * (fb[idx] + c1[idx]) + ((i == j && i < nx) ? reg : 0.0);
+      });
+      L(h);
+      PRC(chol_inv(h, Pm, h->M(M_PINV), nx, nxp, nullptr, 3));
+      double* xm = d_xm + (long)b * ld;
+      matvec(h, h->M(M_F_Y), nx, nh, 1, mvec, c0, h->V(V_LAM));
+      matvec(h, h->M(M_PINV), nx, nx, 0, h->V(V_LAM), 1.0, xm);
+      double* mxb = d_mx + (long)b * l2;
+      const double* xv = h->M(M_PINV);
+      const double* ikx = h->M(M_IKX);
+      ew(st, l2, [=] __device__(long idx) {
+        int i = (int)(idx / ld), j = (int)(idx % ld);
+        mxb[idx] = (i < nx && j < nx) ? xv[idx] + xm[i] * xm[j] - ikx[idx] : 0.0;
+      });
+      L(h);
+    }
+    if (b < B) {
+      // q1 = a + h^T Ahh h - tr(Ahh iKh)
+      matvec(h, h->M(M_AHH), nh, nh, 0, hb, 1.0, h->V(V_M2BMU));
+      dot(h, hb, h->V(V_M2BMU), nh, h->sc + S_S_BHH_S);
+      const double* scp = h->sc;
+      double* q1 = d_q1 + b;
+      ew(st, 1, [=] __device__(long) { q1[0] = a_val + scp[S_S_BHH_S] - scp[S_TR_IKH_AHH]; });
+      L(h);
+    }
+  }
+  // ---- test side, chunk by chunk
+  for (long p0 = 0; p0 < n_star; p0 += TC) {
+    const int nv = (int)std::min<long>(TC, n_star - p0);
+    const int nc = round_up(nv, 8);
+    const long cols = (long)nc * nxp;
+    const double* tc = d_t + p0;
+    {
+      const int threads = std::min(256, round_up(nxp, 32));
+      dim3 grid(nhp, (nc + AHX_NSUB - 1) / AHX_NSUB);
+      ahx_gen_kernel<<<grid, threads, 0, st>>>(tc, tc, nv, nc, h->th, nh, h->tx, nx, 0, nxp, h->wsA, nullptr, ld,
+                                               (long)nhp * ld, cd);
+      L(h);
+    }
+    PRC(gemm(h, true, false, false, nhp, (int)cols, nhp, 1.0, h->M(M_IKH), ld, h->wsA, cols, 0.0, h->wsT, cols));
+    axx_user_kernel<<<148 * 8, 256, 0, st>>>(tc, nv, h->tx, nx, d_x, cd, T);
+    L(h);
+    {
+      dim3 grid((nx + 31) / 32, (nx + 31) / 32, nv);
+      bxx_star_kernel<<<grid, 256, 0, st>>>(h->wsA, h->wsT, nh, nc, nxp, nx, d_x);
+      L(h);
+    }
+    for (int b = 0; b < B; ++b) {
+      const int qb = smf ? b : 0;
+      predict_point_kernel<<<nv, 256, nx * sizeof(double), st>>>(h->wsA, nh, nc, nxp, nx, d_h + (long)b * ld,
+                                                                 d_xm + (long)qb * ld, d_mx + (long)qb * l2, ld, d_x,
+                                                                 d_q1 + b, sqrt(s2f), s2f, 1.0 / B, d_acc + p0,
+                                                                 d_acc + n_star + p0);
+      L(h);
+    }
+  }
+  if (mu_out) PCK(cudaMemcpyAsync(mu_out, d_acc, n_star * sizeof(double), cudaMemcpyDefault, st));
+  if (var_out) PCK(cudaMemcpyAsync(var_out, d_acc + n_star, n_star * sizeof(double), cudaMemcpyDefault, st));
+  int info[4];
+  PCK(cudaMemcpyAsync(info, h->info, sizeof info, cudaMemcpyDeviceToHost, st));
+  PCK(cudaEventRecord(h->ev[6], st));
+  PCK(cudaStreamSynchronize(st));
+  PCK(cudaGetLastError());
+  cleanup();
+#undef PCK
+#undef PRC
+  if (info[0]) {
+    static const char* names[] = {"?", "Kh", "Kx", "P of q(z)", "?", "?"};
+    int tag = info[0] / 100000;
+    char b[160];
+    snprintf(b, sizeof b, "matrix %s is not positive definite (pivot %d)", tag >= 1 && tag <= 5 ? names[tag] : "?",
+             info[0] % 100000);
+    h->err = b;
+    return -3;
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+  memset(h->timing, 0, sizeof h->timing);
+  h->timing[0] = ms;
+  h->timing[6] = (double)h->launches;
+  return 0;
+}
+
 }  // namespace cgimpl
 
 extern "C" {
@@ -1704,6 +1890,23 @@ int cgpcm_elbo_smf(cgpcm_handle* h, const double* params, int32_t mode, double r
   if (terms) { if (is_device_ptr(terms)) cudaMemcpy(terms, tm, sizeof tm, cudaMemcpyHostToDevice); else memcpy(terms, tm, sizeof tm); }
   if (loglik) { if (is_device_ptr(loglik)) cudaMemcpy(loglik, &ll, sizeof ll, cudaMemcpyHostToDevice); else *loglik = ll; }
   return 0;
+}
+
+int cgpcm_predict_f(cgpcm_handle* h, const double* params, double reg, const double* t_star, int64_t n_star,
+                    const double* samples, int32_t n_samples, int32_t smf, double* mean, double* var) {
+  if (!h || !params || n_star < 0 || n_samples < 1 || !samples || (n_star > 0 && !t_star)) return -1;
+  if (!h->t) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  if (!std::isfinite(reg) || reg < 0) { h->err = "reg must be finite and >= 0"; return -4; }
+  if (n_star == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  const long np = 5 + h->nh + (long)h->nh * (h->nh + 1) / 2;
+  std::vector<double> host, ts(n_star), smp((size_t)n_samples * h->nh);
+  if (fetch_params(h, params, np, host)) return -2;
+  if (is_device_ptr(t_star)) CK(cudaMemcpy(ts.data(), t_star, n_star * sizeof(double), cudaMemcpyDeviceToHost));
+  else memcpy(ts.data(), t_star, n_star * sizeof(double));
+  if (is_device_ptr(samples)) CK(cudaMemcpy(smp.data(), samples, smp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  else memcpy(smp.data(), samples, smp.size() * sizeof(double));
+  return predict_run(h, host.data(), reg, ts.data(), n_star, smp.data(), n_samples, smf, mean, var);
 }
 
 int cgpcm_fpi(cgpcm_handle* h, const double* params, int32_t num, int32_t high_reg, double reg, double* mu_u,

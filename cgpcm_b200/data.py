@@ -1,5 +1,7 @@
 """Minimal ``Data`` container: what the hot path reads of the reference's ``core.data.Data``
 (``src/core/data.py:25-34``): observation inputs ``x`` and outputs ``y`` as float64 vectors."""
+from collections import namedtuple
+
 import numpy as np
 
 
@@ -21,3 +23,7 @@ class Data(object):
 
     def __getitem__(self, sl):
         return Data(self.x[sl], self.y[sl])
+
+
+# Named tuple for bundling predictions (``src/core/data.py:481-482``)
+UncertainData = namedtuple('UncertainData', 'mean lower upper std')

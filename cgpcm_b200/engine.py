@@ -120,6 +120,19 @@ class Engine(object):
                                             _lib.ptr(elbo), _lib.ptr(terms), _lib.ptr(ll)))
         return float(elbo[0]), terms, float(ll[0])
 
+    def predict_f(self, params, t_star, samples, smf=False, reg=1e-8):
+        """Posterior ``(mean, var)`` of the function at ``t_star`` averaged over the filter ``samples`` ([B, nh])
+        (``src/core/cgpcm.py:781-846``); needs the frozen statistics."""
+        t_star = np.ascontiguousarray(np.asarray(t_star, dtype=np.float64).ravel())
+        samples = np.ascontiguousarray(np.asarray(samples, dtype=np.float64).reshape(-1, self.nh))
+        if int(params.shape[0]) != n_params(self.nh) or samples.shape[0] < 1:
+            raise ValueError('shape mismatch in predict_f')
+        mean, var = np.empty(t_star.shape[0]), np.empty(t_star.shape[0])
+        self._ck(_lib.lib().cgpcm_predict_f(self._h, _lib.ptr(params), float(reg), _lib.ptr(t_star) if t_star.size else None,
+                                             int(t_star.shape[0]), _lib.ptr(samples), int(samples.shape[0]),
+                                             int(bool(smf)), _lib.ptr(mean), _lib.ptr(var)))
+        return mean, var
+
     def fpi(self, params, num, high_reg=False, reg=1e-8):
         """``num`` rounds of the fixed-point iteration on the frozen Psi statistics, then the optimal q(z):
         ``(mu_u[nh], var_u[nh(nh+1)/2], mu_z[nx], var_z[nx(nx+1)/2])`` (``src/core/cgpcm.py:479-516,577-592``)."""

@@ -96,6 +96,13 @@ int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_
 int cgpcm_elbo_smf(cgpcm_handle* h, const double* params, int32_t mode, double reg, const double* sample, double* elbo,
                    double* terms, double* loglik);
 
+/* mod.predict_f(t, samples_h) (src/core/cgpcm.py:781-846): posterior mean[n_star] and variance[n_star] of the function
+ * at the test inputs t_star, averaged over the filter samples samples[n_samples][nh].  smf = 0: the optimal q(z) of
+ * q(u) (the reference's numeric samples_h: draws from q(u)); smf = 1: the optimal q(z | h) of every sample (the
+ * reference's list samples_h, e.g. from mod.sample()).  Uses the Psi statistics frozen by cgpcm_precompute. */
+int cgpcm_predict_f(cgpcm_handle* h, const double* params, double reg, const double* t_star, int64_t n_star,
+                    const double* samples, int32_t n_samples, int32_t smf, double* mean, double* var);
+
 /* mod.fpi(num, z=True, high_reg) followed by mod.convert(z=True) (src/core/cgpcm.py:479-516,577-592): num rounds of
  * the fixed-point iteration q(u) -> optimal q(z) -> optimal q(u) on the Psi statistics frozen by cgpcm_precompute
  * (Normal.from_natural, src/core/distribution.py:20-33; high_reg adds 1e-4 to both precisions), starting from the

@@ -438,3 +438,38 @@ def elbo_smf(params, t, y, th, tx, r, sample, causal=True):
         ll = (-.5 * log_det(L0) + .5 * torch.sum(trisolve(L0, lam) ** 2)
               - .5 * s2_f / s2 * (h.T @ m['sum_Bhh'] @ h).squeeze())
     return float(sum(terms)), np.array([float(x) for x in terms]), float(ll)
+
+
+# ----------------------------------------------------------------------------- function prediction
+def predict_f(params, t, y, th, tx, r, t_star, samples_h, smf=False, causal=True):
+    """``VCGPCM.predict_f`` (``cgpcm.py:781-846``) for given filter samples ``samples_h`` ([B][nh]): posterior mean
+    and variance of the function at ``t_star``, averaged over the samples.  ``smf=False``: q(z) is the optimal q(z) of
+    q(u) (the reference's numeric ``samples_h``: draws from q(u)); ``smf=True``: q(z | h) per sample."""
+    with torch.no_grad():
+        nh = len(th)
+        s2, s2_f, alpha, gamma, omega, mu_u, var_u = unpack(T(np.asarray(params, np.float64)), nh)
+        k = prior_kernels(th, tx, alpha, gamma, omega, r)
+        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal)
+        m = model_matrices(y, a, Ahh, Axx, Ahx, k['iKh'], k['iKx'])
+        # test-side statistics (cgpcm.py:793: _construct_model_matrices(Data(t)))
+        a_s, Ahh_s, Axx_s, Ahx_s = psi_closed(t_star, th, tx, alpha, gamma, omega, causal)
+        Lq = vec_to_tril(var_u)
+        h_var = reg(Lq @ Lq.T, r)
+        mus, vars_ = [], []
+        for hs in samples_h:
+            h = T(np.asarray(hs, np.float64)).reshape(-1, 1)
+            if smf:
+                lam, P = optimal_q(m, k, s2, s2_f, h, h @ h.T, True)
+            else:
+                lam, P = optimal_q(m, k, s2, s2_f, mu_u, h_var + mu_u @ mu_u.T, True)
+            xm, xv = from_natural(P, lam, r)
+            mu = s2_f ** .5 * (h.T @ Ahx_s @ xm).reshape(-1)                         # [n*]
+            mh = h @ h.T - k['iKh']
+            mx = xv + xm @ xm.T - k['iKx']
+            m2 = s2_f * (a_s + trmul(Ahh_s, mh) + torch.sum(Axx_s * mx, (-1, -2))
+                         + torch.sum((mh @ Ahx_s) * (Ahx_s @ mx), (-1, -2)))
+            mus.append(mu)
+            vars_.append(m2 - mu ** 2)
+        mu = torch.mean(torch.stack(mus, 1), 1)
+        var = torch.mean(torch.stack(vars_, 1), 1)
+    return mu.numpy().copy(), var.numpy().copy()

@@ -91,3 +91,21 @@ def test_fpi_is_coordinate_ascent():
     L = om.vec_to_tril(om.T(c['params'][5 + c['nh']:])).numpy()
     L0 = om.vec_to_tril(om.T(var0)).numpy()
     np.testing.assert_allclose(L0 @ L0.T, L @ L.T + c['reg'] * np.eye(c['nh']), rtol=1e-12, atol=1e-14)
+
+
+def test_predict_f_oracle_is_a_smoother():
+    """oracle.predict_f (src/core/cgpcm.py:781-846): after a few fixed-point rounds the predictive mean follows the
+    observations, the variance is positive, and the SMF variant with the mean of q(u) as the only sample equals
+    the plug-in formulas evaluated by hand."""
+    c = make_case('toy_small')
+    args = (c['t'], c['y'], c['th'], c['tx'], c['reg'])
+    mu, var, _, _ = om.fpi(c['params'], *args, 8)
+    p = c['params'].copy()
+    p[5:5 + c['nh']] = mu
+    p[5 + c['nh']:] = var
+    m, v = om.predict_f(p, *args, c['t'], [mu], smf=False)
+    assert np.all(v > 0) and np.mean((m - c['y']) ** 2) < 0.6
+    m2, v2 = om.predict_f(p, *args, c['t'][:5], [mu, mu], smf=True)
+    m1, v1 = om.predict_f(p, *args, c['t'][:5], [mu], smf=True)
+    np.testing.assert_allclose(m2, m1, rtol=1e-13)
+    np.testing.assert_allclose(v2, v1, rtol=1e-12)
