@@ -290,6 +290,26 @@ def run_ours(args):
         dist.all_reduce(fdev, op=dist.ReduceOp.MAX)
     frozen_value = len(fms) / (float(fdev.sum().item()) * 1e-3)
 
+    # ---- the widened rows on the same frozen statistics: device time per unit of work
+    rng = np.random.default_rng(1)
+    nh = args.m
+    eng.fpi(p_h.numpy(), 1, reg=wl['reg'])
+    eng.fpi(p_h.numpy(), 2, reg=wl['reg'])
+    fpi_ms = eng.last_timing()['total_ms'] / 2.5          # 2 rounds + the convert half round
+    smp = wl['params'][5:5 + nh] + .01 * rng.standard_normal(nh)
+    eng.elbo_smf(p_h.numpy(), smp, mode=cgpcm_b200.MODE_FROZEN, reg=wl['reg'])
+    eng.elbo_smf(p_h.numpy(), smp, mode=cgpcm_b200.MODE_FROZEN, reg=wl['reg'])
+    smf_ms = eng.last_timing()['total_ms']
+    t_star = np.linspace(wl['t'][0], wl['t'][-1], 2048)
+    samples = wl['params'][5:5 + nh] + .01 * rng.standard_normal((8, nh))
+    eng.predict_f(p_h.numpy(), t_star, samples, reg=wl['reg'])
+    eng.predict_f(p_h.numpy(), t_star, samples, reg=wl['reg'])
+    pred_ms = eng.last_timing()['total_ms']
+    rows = torch.tensor([fpi_ms, smf_ms, pred_ms], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(rows, op=dist.ReduceOp.MAX)
+    fpi_ms, smf_ms, pred_ms = [float(v) for v in rows.cpu()]
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -344,6 +364,10 @@ def run_ours(args):
         'other_cull_setting': other,
         'frozen_regime': {'value': frozen_value, 'unit': UNIT,
                           'note': 'Psi sums frozen by precompute(); gradient w.r.t. log s2, log s2_f, mu_u, var_u'},
+        'next_rows': {'fpi_ms_per_round': fpi_ms, 'elbo_smf_ms_per_sample': smf_ms,
+                      'predict_f_ms': pred_ms, 'predict_f_shape': '2048 test inputs x 8 filter samples',
+                      'note': 'SURVEY.md 8f ranks 1-3 (fpi, SMF bound / sampler target, predict_f) on the frozen '
+                              'statistics at the same cull setting; device time, max over ranks'},
         'wall_s_timed_region': wall,
     }
     if not args.no_cpu_baseline:
