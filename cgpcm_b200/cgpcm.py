@@ -434,6 +434,29 @@ class VCGPCM(CGPCM):
         return UncertainData(mean=Data(t, mu), lower=Data(t, mu - 2 * std), upper=Data(t, mu + 2 * std),
                              std=Data(t, std))
 
+    def predict_k(self, t, samples_h=200, psd=False, normalise=True):
+        """Predict the kernel, or the PSD via the kernel approximation, at lags ``t``
+        (``src/core/cgpcm.py:610-661``): Monte-Carlo over filter samples (numeric ``samples_h``: draws from q(u)).
+        The kernel samples come from the GPU (``cgpcm_kernel_samples``); normalisation, the FFT and the percentile
+        band are post-processing of those samples.  Returns ``UncertainData(mean, lower, upper, std)``."""
+        from .data import Data, UncertainData
+        from .util import fft_spectrum, lower_perc, upper_perc
+        t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
+        if np.isscalar(samples_h) or isinstance(samples_h, (int, np.integer)):
+            samples = [self.sample_q() for _ in range(int(samples_h))]
+        else:
+            samples = list(samples_h)
+        samples = np.stack([np.asarray(x, dtype=np.float64).ravel() for x in samples])
+        k = self.engine.kernel_samples(self._pack(), t, samples, reg=config.reg)          # [n, B]
+        if normalise:
+            k = k / k.max(axis=0, keepdims=True)
+        x = t
+        if psd:
+            x, spec = fft_spectrum(t, k)
+            k = np.abs(spec)
+        return UncertainData(mean=Data(x, k.mean(axis=1)), lower=Data(x, np.percentile(k, lower_perc, axis=1)),
+                             upper=Data(x, np.percentile(k, upper_perc, axis=1)), std=Data(x, k.std(axis=1)))
+
     @property
     def mats(self):
         """Psi statistics at the current (or frozen) hyper-parameters as numpy arrays."""

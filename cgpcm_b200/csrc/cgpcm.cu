@@ -1842,6 +1842,85 @@ int predict_run(cgpcm_handle* h, const double* params_host, double reg, const do
   return 0;
 }
 
+// Monte-Carlo kernel samples of VCGPCM.predict_k (src/core/cgpcm.py:610-634), before normalisation:
+//   out[p][b] = s2_f (a_c(t_p) + tr((h_b h_b^T - iKh) Ahh_c(t_p)))
+// The n x nh^2 matrix of centre statistics times the nh^2 x B matrix of (h h^T - iKh) is one DMMA GEMM per chunk.
+int kernel_run(cgpcm_handle* h, const double* params_host, double reg, const double* t_host, long n,
+               const double* samples_host, int B, double* out) {
+  const int nh = h->nh;
+  const long ld = h->ld;
+  const long np = 5 + nh + (long)nh * (nh + 1) / 2;
+  for (long i = 0; i < 5; ++i)
+    if (!std::isfinite(params_host[i])) { h->err = "non-finite parameter"; return -4; }
+  for (long i = 0; i < n; ++i)
+    if (!std::isfinite(t_host[i])) { h->err = "non-finite input"; return -4; }
+  for (long i = 0; i < (long)B * nh; ++i)
+    if (!std::isfinite(samples_host[i])) { h->err = "non-finite sample"; return -4; }
+  (void)np;
+  const double s2f = exp(params_host[1]);
+  const double alpha = exp(params_host[2]), gamma = exp(params_host[3]), omega = exp(params_host[4]);
+  h->launches = 0;
+  h->gemm_flops = h->gemm_flops_exec = 0.0;
+  h->gemm_launches = 0;
+  h->pev_used = 0;
+  PsiConst c;
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
+  cudaStream_t st = h->st;
+  const int nhl = round_up(nh, 2);
+  const long K = (long)nh * nhl;
+  const int Bp = round_up(B, 8);
+  const int TC = (int)std::min<long>(round_up((int)std::min<long>(n, 1024), 8), 1024);
+  double *d_t = nullptr, *d_hs = nullptr, *d_ac = nullptr, *d_AC = nullptr, *d_HH = nullptr, *d_G = nullptr, *d_out = nullptr;
+  auto cleanup = [&]() {
+    double* ps[] = {d_t, d_hs, d_ac, d_AC, d_HH, d_G, d_out};
+    for (double* q : ps) if (q) cudaFree(q);
+  };
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[256]; snprintf(b_, sizeof b_, \
+    "CUDA error %s in kernel_samples (%s)", cudaGetErrorString(e_), #call); h->err = b_; cleanup(); return -2; } } while (0)
+#define PRC(call) do { if (call) { cleanup(); return -2; } } while (0)
+  PCK(cudaMalloc(&d_t, (size_t)n * sizeof(double)));
+  PCK(cudaMalloc(&d_hs, (size_t)B * nh * sizeof(double)));
+  PCK(cudaMalloc(&d_ac, (size_t)TC * sizeof(double)));
+  PCK(cudaMalloc(&d_AC, (size_t)TC * K * sizeof(double)));
+  PCK(cudaMalloc(&d_HH, (size_t)Bp * K * sizeof(double)));
+  PCK(cudaMalloc(&d_G, (size_t)TC * Bp * sizeof(double)));
+  PCK(cudaMalloc(&d_out, (size_t)n * B * sizeof(double)));
+  PCK(cudaEventRecord(h->ev[0], st));
+  PCK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
+  PCK(cudaMemcpyAsync(d_t, t_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  PCK(cudaMemcpyAsync(d_hs, samples_host, (size_t)B * nh * sizeof(double), cudaMemcpyHostToDevice, st));
+  PRC(prior_stage(h, c, reg));                          // Kh -> iKh (M_IKH)
+  hh_build_kernel<<<148 * 4, 256, 0, st>>>(d_hs, nh, B, Bp, h->M(M_IKH), ld, nh, nhl, d_HH);
+  L(h);
+  for (long p0 = 0; p0 < n; p0 += TC) {
+    const int nv = (int)std::min<long>(TC, n - p0);
+    const int nvp = round_up(nv, 8);
+    if (nvp > nv) PCK(cudaMemsetAsync(d_AC + (long)nv * K, 0, (size_t)(nvp - nv) * K * sizeof(double), st));
+    ahh_center_kernel<<<148 * 8, 256, 0, st>>>(d_t + p0, nv, h->th, nh, nhl, alpha, gamma, h->causal, d_AC, d_ac);
+    L(h);
+    // G[p][b] = sum_e AC[p][e] HH[b][e]
+    PRC(gemm(h, true, true, false, nvp, Bp, (int)K, 1.0, d_AC, K, d_HH, K, 0.0, d_G, Bp));
+    kernel_finish_kernel<<<148 * 2, 256, 0, st>>>(d_G, Bp, d_ac, nv, B, s2f, d_out + p0 * B);
+    L(h);
+  }
+  PCK(cudaMemcpyAsync(out, d_out, (size_t)n * B * sizeof(double), cudaMemcpyDefault, st));
+  int info[4];
+  PCK(cudaMemcpyAsync(info, h->info, sizeof info, cudaMemcpyDeviceToHost, st));
+  PCK(cudaEventRecord(h->ev[6], st));
+  PCK(cudaStreamSynchronize(st));
+  PCK(cudaGetLastError());
+  cleanup();
+#undef PCK
+#undef PRC
+  if (info[0]) { h->err = "matrix Kh is not positive definite"; return -3; }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+  memset(h->timing, 0, sizeof h->timing);
+  h->timing[0] = ms;
+  h->timing[6] = (double)h->launches;
+  return 0;
+}
+
 }  // namespace cgimpl
 
 extern "C" {
@@ -1907,6 +1986,22 @@ int cgpcm_predict_f(cgpcm_handle* h, const double* params, double reg, const dou
   if (is_device_ptr(samples)) CK(cudaMemcpy(smp.data(), samples, smp.size() * sizeof(double), cudaMemcpyDeviceToHost));
   else memcpy(smp.data(), samples, smp.size() * sizeof(double));
   return predict_run(h, host.data(), reg, ts.data(), n_star, smp.data(), n_samples, smf, mean, var);
+}
+
+int cgpcm_kernel_samples(cgpcm_handle* h, const double* params, double reg, const double* t, int64_t n,
+                         const double* samples, int32_t n_samples, double* out) {
+  if (!h || !params || n < 0 || n_samples < 1 || !samples || !out || (n > 0 && !t)) return -1;
+  if (!h->th) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  if (!std::isfinite(reg) || reg < 0) { h->err = "reg must be finite and >= 0"; return -4; }
+  if (n == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  std::vector<double> host, ts(n), smp((size_t)n_samples * h->nh);
+  if (fetch_params(h, params, 5, host)) return -2;
+  if (is_device_ptr(t)) CK(cudaMemcpy(ts.data(), t, n * sizeof(double), cudaMemcpyDeviceToHost));
+  else memcpy(ts.data(), t, n * sizeof(double));
+  if (is_device_ptr(samples)) CK(cudaMemcpy(smp.data(), samples, smp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  else memcpy(smp.data(), samples, smp.size() * sizeof(double));
+  return kernel_run(h, host.data(), reg, ts.data(), n, smp.data(), n_samples, out);
 }
 
 int cgpcm_fpi(cgpcm_handle* h, const double* params, int32_t num, int32_t high_reg, double reg, double* mu_u,

@@ -93,3 +93,69 @@ __global__ void __launch_bounds__(256) predict_point_kernel(const double* __rest
 }
 
 }  // namespace cg
+
+namespace cg {
+
+// Off-diagonal ("center") Psi statistics of predict_k (src/core/cgpcm.py:164-166,190-192): t2 = 0, upper limit
+// min(t, 0) for the causal model.  Closed forms (oracle.model.psi_center_closed):
+//   a_c(t)        = pref_a exp(-(alpha/2 + gamma) t^2) erfc(sqrt(2 alpha) |t| / 2)
+//   Ahh_c(t)[i,j] = pref_h exp(c + b^2 / 8B) erfc(sqrt(2B) (b / 4B - min(t, 0))),   B = alpha + gamma,
+//                   b = 2B t - 2 gamma (th_i + th_j),  c = -alpha (t^2 + th_i^2) - gamma (t - th_i)^2 - B th_j^2
+// (acausal: no erfc, twice the prefactor).  AC: [n][nh * nhl] (row i at stride nhl, zero padded), ac: [n].
+__global__ void ahh_center_kernel(const double* __restrict__ t, int n, const double* __restrict__ th, int nh, int nhl,
+                                  double alpha, double gamma, int causal, double* __restrict__ AC,
+                                  double* __restrict__ ac) {
+  const double PI = 3.14159265358979323846;
+  const double B = alpha + gamma;
+  const double pref_a = (causal ? 0.5 : 1.0) * sqrt(PI / (2.0 * alpha));
+  const double pref_h = (causal ? 0.5 : 1.0) * sqrt(PI / (2.0 * B));
+  const long per = (long)nh * nhl;
+  const long total = (long)n * per;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx / per);
+    const int e = (int)(idx - (long)p * per);
+    const int i = e / nhl, j = e - i * nhl;
+    const double tt = t[p];
+    if (e == 0) {
+      double v = pref_a * exp(-(0.5 * alpha + gamma) * tt * tt);
+      if (causal) v *= erfc(sqrt(2.0 * alpha) * fabs(tt) * 0.5);
+      ac[p] = v;
+    }
+    double v = 0.0;
+    if (j < nh) {
+      const double ti = th[i], tj = th[j];
+      const double b = 2.0 * B * tt - 2.0 * gamma * (ti + tj);
+      const double c = -alpha * (tt * tt + ti * ti) - gamma * (tt - ti) * (tt - ti) - B * tj * tj;
+      v = pref_h * exp(c + b * b / (8.0 * B));
+      if (causal) v *= erfc(sqrt(2.0 * B) * (b / (4.0 * B) - fmin(tt, 0.0)));
+    }
+    AC[idx] = v;
+  }
+}
+
+// HH[b][i * nhl + j] = h_b[i] h_b[j] - iKh[i][j]   (rows b >= nb and the padding are zero)
+__global__ void hh_build_kernel(const double* __restrict__ hs, long ldh, int nb, int nbp, const double* __restrict__ iKh,
+                                long ld, int nh, int nhl, double* __restrict__ HH) {
+  const long per = (long)nh * nhl;
+  const long total = (long)nbp * per;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / per);
+    const int e = (int)(idx - (long)b * per);
+    const int i = e / nhl, j = e - i * nhl;
+    double v = 0.0;
+    if (b < nb && j < nh) v = hs[(long)b * ldh + i] * hs[(long)b * ldh + j] - iKh[(long)i * ld + j];
+    HH[idx] = v;
+  }
+}
+
+// out[p][b] = s2f (ac[p] + G[p][b])
+__global__ void kernel_finish_kernel(const double* __restrict__ G, long ldg, const double* __restrict__ ac, int n, int nb,
+                                     double s2f, double* __restrict__ out) {
+  const long total = (long)n * nb;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx / nb), b = (int)(idx - (long)p * nb);
+    out[idx] = s2f * (ac[p] + G[(long)p * ldg + b]);
+  }
+}
+
+}  // namespace cg

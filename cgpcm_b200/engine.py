@@ -133,6 +133,18 @@ class Engine(object):
                                              int(bool(smf)), _lib.ptr(mean), _lib.ptr(var)))
         return mean, var
 
+    def kernel_samples(self, params, t, samples, reg=1e-8):
+        """Kernel samples ``k[n, b]`` of ``predict_k`` at lags ``t`` for filter ``samples`` ([B, nh])
+        (``src/core/cgpcm.py:610-634``), before normalisation."""
+        t = np.ascontiguousarray(np.asarray(t, dtype=np.float64).ravel())
+        samples = np.ascontiguousarray(np.asarray(samples, dtype=np.float64).reshape(-1, self.nh))
+        out = np.empty((t.shape[0], samples.shape[0]))
+        if t.shape[0]:
+            self._ck(_lib.lib().cgpcm_kernel_samples(self._h, _lib.ptr(np.ascontiguousarray(params[:5])), float(reg),
+                                                      _lib.ptr(t), int(t.shape[0]), _lib.ptr(samples),
+                                                      int(samples.shape[0]), _lib.ptr(out)))
+        return out
+
     def fpi(self, params, num, high_reg=False, reg=1e-8):
         """``num`` rounds of the fixed-point iteration on the frozen Psi statistics, then the optimal q(z):
         ``(mu_u[nh], var_u[nh(nh+1)/2], mu_z[nx], var_z[nx(nx+1)/2])`` (``src/core/cgpcm.py:479-516,577-592``)."""

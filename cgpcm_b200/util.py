@@ -31,3 +31,22 @@ def vec_to_tril(v):
     out = np.zeros((m, m), dtype=v.dtype)
     out[np.tril_indices(m)] = v
     return out
+
+
+# Percentiles of the +-2 sigma band used for Monte-Carlo predictions (``src/core/util.py:11-12``)
+lower_perc = 2.275013194817921    # 100 * Phi(-2)
+upper_perc = 97.72498680518208    # 100 * Phi(2)
+
+
+def fft_spectrum(t, y, zero_pad=2000):
+    """``Data(t, y).fft()`` of the reference (``src/core/data.py:184-209``, ``util.py:67-93,104-121``): zero pad by
+    ``zero_pad`` on both sides, FFT along axis 0, ``fftshift``, scale by the spacing.  Returns ``(freq, spectrum)``."""
+    t = np.asarray(t, dtype=np.float64)
+    d = np.diff(t)
+    if t.shape[0] < 2 or np.abs(d - d[0]).max() > 1e-8 * max(abs(d[0]), 1e-300):
+        raise AssertionError('data must be evenly spaced')
+    dx = t[1] - t[0]
+    y = np.asarray(y)
+    pad = np.zeros((zero_pad,) + y.shape[1:], dtype=y.dtype)
+    spec = dx * np.fft.fftshift(np.fft.fft(np.concatenate((pad, y, pad), axis=0), axis=0), axes=0)
+    return np.fft.fftshift(np.fft.fftfreq(spec.shape[0])) / dx, spec

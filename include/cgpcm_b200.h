@@ -103,6 +103,13 @@ int cgpcm_elbo_smf(cgpcm_handle* h, const double* params, int32_t mode, double r
 int cgpcm_predict_f(cgpcm_handle* h, const double* params, double reg, const double* t_star, int64_t n_star,
                     const double* samples, int32_t n_samples, int32_t smf, double* mean, double* var);
 
+/* The Monte-Carlo kernel samples of mod.predict_k(t, samples_h) (src/core/cgpcm.py:610-634; centre statistics
+ * _a_center / _Ahh_center :164-166,190-192), before normalisation / FFT / percentiles (host post-processing):
+ * out[p * n_samples + b] = s2_f (a_c(t_p) + tr((h_b h_b^T - iKh) Ahh_c(t_p))) for lags t[n] and filter samples
+ * samples[n_samples][nh].  Needs only the inducing inputs (cgpcm_set_data) and the hyper-parameters in params[0..4]. */
+int cgpcm_kernel_samples(cgpcm_handle* h, const double* params, double reg, const double* t, int64_t n,
+                         const double* samples, int32_t n_samples, double* out);
+
 /* mod.fpi(num, z=True, high_reg) followed by mod.convert(z=True) (src/core/cgpcm.py:479-516,577-592): num rounds of
  * the fixed-point iteration q(u) -> optimal q(z) -> optimal q(u) on the Psi statistics frozen by cgpcm_precompute
  * (Normal.from_natural, src/core/distribution.py:20-33; high_reg adds 1e-4 to both precisions), starting from the

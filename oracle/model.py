@@ -473,3 +473,62 @@ def predict_f(params, t, y, th, tx, r, t_star, samples_h, smf=False, causal=True
         mu = torch.mean(torch.stack(mus, 1), 1)
         var = torch.mean(torch.stack(vars_, 1), 1)
     return mu.numpy().copy(), var.numpy().copy()
+
+
+# ----------------------------------------------------------------------------- kernel prediction (first part)
+def psi_center_generic(t, th, alpha, gamma, causal=True):
+    """``_a_center`` / ``_Ahh_center`` (``cgpcm.py:164-166,190-192``) through the restated ``integrate_box`` on the
+    reference's integrands: ``t2 = 0``, upper limit ``min(t1, 0)`` (causal) or ``inf``.  ``a`` [n], ``Ahh`` [n,nh,nh]."""
+    t, th = T(t), T(th)
+    v = expq.var
+    tau1, t1, th1, th2 = v('tau1'), v('t1'), v('th1'), v('th2')
+    kh = lambda x, y: expq.kh(alpha, gamma, x, y)
+    zero = expq.const(0)
+    expq_a = kh(t1 - tau1, zero - tau1)
+    expq_Ahh = kh(t1 - tau1, th1) * kh(th2, zero - tau1)
+    n, nh = t.shape[0], th.shape[0]
+    vm = {'t1': t.reshape(-1, 1, 1), 'th1': th.reshape(1, -1, 1), 'th2': th.reshape(1, 1, -1)}
+    vm['min_t1_0'] = torch.minimum(vm['t1'], torch.zeros(1, dtype=DT))
+    up = v('min_t1_0') if causal else expq.inf
+    a = torch.as_tensor(expq_a.integrate_box(('tau1', -expq.inf, up), **vm))       # squeezed like tf.squeeze: [n]
+    a = a.reshape(-1) * torch.ones(n, dtype=DT)
+    Ahh = torch.as_tensor(expq_Ahh.integrate_box(('tau1', -expq.inf, up), **vm))
+    return a, Ahh.reshape(n, nh, nh)
+
+
+def psi_center_closed(t, th, alpha, gamma, causal=True):
+    """Closed forms of the same: with ``B = alpha + gamma``, ``U = min(t, 0)``,
+    ``a_c(t) = 1/2 sqrt(pi/2alpha) exp(-(alpha/2 + gamma) t^2) erfc(sqrt(2 alpha) |t| / 2)`` and
+    ``Ahh_c(t)[i,j] = 1/2 sqrt(pi/2B) exp(c + b^2/8B) erfc(sqrt(2B) (b/4B - U))``, ``b = 2B t - 2 gamma (th_i + th_j)``,
+    ``c = -alpha (t^2 + th_i^2) - gamma (t - th_i)^2 - B th_j^2``; acausal: twice the prefactor, no erfc."""
+    t, th = T(t), T(th)
+    alpha, gamma = T(alpha), T(gamma)
+    B = alpha + gamma
+    a = torch.sqrt(math.pi / (2 * alpha)) * torch.exp(-(.5 * alpha + gamma) * t ** 2)
+    tt = t.reshape(-1, 1, 1)
+    thi, thj = th.reshape(1, -1, 1), th.reshape(1, 1, -1)
+    b = 2 * B * tt - 2 * gamma * (thi + thj)
+    c = -alpha * (tt ** 2 + thi ** 2) - gamma * (tt - thi) ** 2 - B * thj ** 2
+    Ahh = torch.sqrt(math.pi / (2 * B)) * torch.exp(c + b ** 2 / (8 * B))
+    if causal:
+        U = torch.minimum(tt, torch.zeros(1, dtype=DT))
+        a = .5 * a * torch.special.erfc(torch.sqrt(2 * alpha) * torch.abs(t) / 2)
+        Ahh = .5 * Ahh * torch.special.erfc(torch.sqrt(2 * B) * (b / (4 * B) - U))
+    return a, Ahh
+
+
+def kernel_samples(params, th, r, t, samples_h, causal=True):
+    """The Monte-Carlo kernel samples of ``VCGPCM.predict_k`` (``cgpcm.py:610-634``), before normalisation:
+    ``k[n, b] = s2_f (a_c(t_n) + tr((h_b h_b^T - iKh) Ahh_c(t_n)))``."""
+    with torch.no_grad():
+        nh = len(th)
+        s2, s2_f, alpha, gamma, omega, _, _ = unpack(T(np.asarray(params, np.float64)), nh)
+        thT = T(th)
+        Kh = reg(deq(1., alpha, gamma, thT), r)
+        iKh = cholinv(torch.linalg.cholesky(Kh))
+        a, Ahh = psi_center_closed(t, th, alpha, gamma, causal)
+        cols = []
+        for hs in samples_h:
+            h = T(np.asarray(hs, np.float64)).reshape(-1, 1)
+            cols.append(s2_f * (a + torch.sum((h @ h.T - iKh) * Ahh, (-1, -2))))
+    return torch.stack(cols, 1).numpy().copy()

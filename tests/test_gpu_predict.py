@@ -81,3 +81,45 @@ def test_predict_f_api():
     pred2 = mod.predict_f(Data(c['t'][:7]), samples_h=mod.sample(iters=3, burn=2))     # SMF path, not precomputed
     assert pred2.mean.y.shape == (7,) and np.all(np.isfinite(pred2.std.y))
     config.reg = 1e-8
+
+
+@pytest.mark.parametrize('name', ['toy_small', 'hrir', 'toy_acausal_model'])
+def test_kernel_samples_match_oracle(name):
+    """predict_k's Monte-Carlo kernel samples (src/core/cgpcm.py:610-634; centre statistics :164-166,190-192)."""
+    c = make_case(name)
+    rng = np.random.default_rng(9)
+    nh = c['nh']
+    samples = c['params'][5:5 + nh] + .3 * rng.standard_normal((11, nh))
+    span = c['th'].max() - c['th'].min()
+    t = np.concatenate([np.linspace(-1.5 * span, 1.5 * span, 45), [0.0]])
+    om.PW_DISTS_EXACT = True
+    try:
+        want = om.kernel_samples(c['params'], c['th'], c['reg'], t, samples, causal=c['causal'])
+    finally:
+        om.PW_DISTS_EXACT = False
+    eng = cgpcm_b200.Engine(c['nh'], c['nx'], causal=c['causal'])
+    eng.set_data(c['t'], c['y'], c['th'], c['tx'])
+    got = eng.kernel_samples(c['params'], t, samples, reg=c['reg'])
+    assert got.shape == (46, 11)
+    # the trace against iKh (entries ~ 1/reg) cancels most of h^T Ahh h: relative to the terms that are summed
+    scale = np.abs(want).max() + 1.0 / c['reg'] * 1e-9
+    assert np.abs(got - want).max() <= 1e-9 * scale + 1e-7 * np.abs(want).max()
+    assert eng.kernel_samples(c['params'], np.zeros(0), samples, reg=c['reg']).shape == (0, 11)
+
+
+def test_predict_k_api():
+    c = make_case('toy_small')
+    config.reg = c['reg']
+    np.random.seed(6)
+    mod = VCGPCM.from_recipe(Session(), Data(c['t'], c['y']), nx=c['nx'], nh=c['nh'], tau_w=.1, tau_f=.05,
+                             causal=True, noise_init=1e-2)
+    t = np.linspace(-.3, .3, 61)
+    k = mod.predict_k(t, samples_h=16)
+    assert k.mean.x.shape == (61,) and np.all(k.lower.y <= k.upper.y + 1e-15)
+    assert k.mean.y[30] == pytest.approx(k.mean.y.max())            # a (normalised) kernel peaks at lag 0
+    assert np.abs(k.mean.y - k.mean.y[::-1]).max() < 0.25           # and is roughly even
+    p = mod.predict_k(t, samples_h=[mod.sample_q() for _ in range(5)], psd=True)
+    assert p.mean.x.shape == (61 + 4000,) and np.all(p.mean.y >= 0)
+    with pytest.raises(AssertionError):
+        mod.predict_k(np.array([0., .1, .3]), samples_h=2, psd=True)
+    config.reg = 1e-8

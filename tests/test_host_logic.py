@@ -152,3 +152,18 @@ def test_elliptical_slice_sampler_on_a_gaussian_target():
     assert min(ess.attempts) >= 1 and np.mean(ess.attempts) < 6
     one = ess.sample(1)
     assert one.shape == (2, 1)
+
+
+def test_fft_spectrum_follows_the_reference_conventions():
+    """cgpcm_b200.util.fft_spectrum = Data.fft of the reference (src/core/data.py:184-209): 2000 zeros on both sides,
+    fftshift, scaled by the spacing -> the spectrum of a Gaussian is the Gaussian with the continuous-time scaling."""
+    from cgpcm_b200.util import fft_spectrum
+    t = np.linspace(-2, 2, 401)
+    y = np.exp(-np.pi * (t / .2) ** 2)                              # FT: 0.2 exp(-pi (0.2 f)^2)
+    f, s = fft_spectrum(t, y)
+    assert f.shape == (4401,) and f[2200] == 0 and np.all(np.diff(f) > 0)
+    np.testing.assert_allclose(np.abs(s), .2 * np.exp(-np.pi * (.2 * f) ** 2), atol=1e-9)
+    f2, s2 = fft_spectrum(t, np.stack([y, 2 * y], 1))
+    np.testing.assert_allclose(np.abs(s2[:, 1]), 2 * np.abs(s), atol=1e-12)
+    with pytest.raises(AssertionError):
+        fft_spectrum(np.array([0., 1., 3.]), np.ones(3))

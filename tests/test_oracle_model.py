@@ -109,3 +109,17 @@ def test_predict_f_oracle_is_a_smoother():
     m1, v1 = om.predict_f(p, *args, c['t'][:5], [mu], smf=True)
     np.testing.assert_allclose(m2, m1, rtol=1e-13)
     np.testing.assert_allclose(v2, v1, rtol=1e-12)
+
+
+@pytest.mark.parametrize('causal', [True, False])
+def test_center_statistics_closed_forms(causal):
+    """oracle.psi_center_closed against the reference's integrands pushed through the restated integrate_box
+    (``_a_center`` / ``_Ahh_center``, src/core/cgpcm.py:164-166,190-192), and against the diagonal forms at t = 0."""
+    t = np.array([-.3, -.05, 0., .02, .11, .4])
+    th = np.linspace(-.02, .2, 7)
+    alpha, gamma = 39.27, 294.5
+    a1, A1 = om.psi_center_generic(t, th, alpha, gamma, causal)
+    a2, A2 = om.psi_center_closed(t, th, alpha, gamma, causal)
+    assert float((a1 - a2).abs().max()) < 1e-16 and float((A1 - A2).abs().max()) < 1e-15
+    assert float(a2[2]) == pytest.approx(float(om.psi_a(om.T(alpha), causal)), rel=1e-15)
+    np.testing.assert_allclose(A2[2].numpy(), om.psi_Ahh(th, om.T(alpha), om.T(gamma), causal).numpy(), rtol=1e-13, atol=1e-17)
