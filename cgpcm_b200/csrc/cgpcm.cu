@@ -1683,7 +1683,7 @@ int predict_run(cgpcm_handle* h, const double* params_host, double reg, const do
   PsiConst c;
   psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
   PsiConst cd = c;                       // test-side statistics are evaluated densely (no windows)
-  cd.cull = 1e300;
+  cd.cull = 746.0;
   BvnTab T;
   bvn_make_tab(gamma / (alpha + gamma + omega), &T);
   std::vector<Chunk> chunks;

@@ -32,7 +32,7 @@ struct PsiConst {
   double dhalf_logdet[3], dg1[3], dg2[3], dp[3], dq[3], drho[3];
   // Ahh
   double pref_hh;      // causal: 0.5 sqrt(pi/2B)  acausal: sqrt(pi/2B),  B = alpha + gamma
-  // culling: elements whose Gaussian envelope is below exp(-cull) are exactly 0 (1e300 = never)
+  // culling: elements whose Gaussian envelope is below exp(-cull) are exactly 0
   double cull;
   double r_xx;         // |t - tx| beyond which every Axx element of that row / column is culled
 };
@@ -68,7 +68,11 @@ inline void psi_make_const(double alpha, double gamma, double omega, int causal,
     c->drho[i] = dgam[i] / A - gamma / (A * A);
   }
   c->pref_hh = (causal ? 0.5 : 1.0) * sqrt(PI / (2.0 * (alpha + gamma)));
-  c->cull = cull > 0.0 ? cull : 1e300;
+  // Element-wise threshold.  With culling off it is 746: exp(E) with E < -745.14 is exactly 0 in IEEE double (below
+  // half the smallest subnormal), so such elements ARE 0 -- in the reference's TF arithmetic too -- and evaluating
+  // erfc / the BVN for them cannot change a single bit of any sum.  (Windows of inducing inputs / GEMM tiles are
+  // only dropped when the caller asks for culling: r_xx below and plan_chunks use `cull` itself.)
+  c->cull = cull > 0.0 ? cull : 746.0;
   // g1 (dk^2 + dl^2) - g2 dk dl >= (g1 - |g2| / 2) (dk^2 + dl^2)
   double lam = c->g1 - 0.5 * fabs(c->g2);
   c->r_xx = (cull > 0.0 && lam > 0.0) ? sqrt(cull / lam) : INFINITY;
