@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "dgemm_dmma.cuh"
 
 namespace cg {
@@ -94,9 +96,11 @@ __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* S
     b[1] = B_KC ? Bp[8 * (SL_BK + 4) + k4 * 4] : Bp[k4 * 4 * (SL_BN + 4) + 8];
   };
 
-  for (int kt = 0; kt < nkt; ++kt) {
+  // One k-tile.  STEPS = 4 for full tiles (no run-time condition anywhere near the DMMA stream: a conditional
+  // around mma.sync costs a WARPSYNC + branch per k4 step), 2 for the short last tile of K % 16 == 8.
+  auto ktile = [&](int kt, auto steps_tag) {
+    constexpr int STEPS = decltype(steps_tag)::value;
     const double* Sk = Sp + kt * SL_BK;
-    const int k4n = min(SL_BK / 4, (g.K - kt * SL_BK) >> 2);   // the last k-tile may be short (K % 16 == 8)
     double fa[MB], fb[2][2];
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) fa[mb] = Sk[mb * 8 * sk];   // resident operand: no need to wait for the stage
@@ -104,28 +108,29 @@ __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* S
     const double* Bp = ring + stage * TILE + b_off;
     load_b(Bp, 0, fb[0]);
 #pragma unroll
-    for (int k4 = 0; k4 < SL_BK / 4; ++k4) {
-      const bool more = k4 + 1 < SL_BK / 4 && k4 + 1 < k4n;
+    for (int k4 = 0; k4 < STEPS; ++k4) {
+      const bool more = k4 + 1 < STEPS;
       if (more) load_b(Bp, k4 + 1, fb[(k4 + 1) & 1]);
       if (k4 == 1 && stagger && kt == min(6, nkt - 1)) {      // group 0, first tile: release group 1 (see kernel)
         __syncwarp();
         if (lane == 0) mbar_arrive(stagger);
       }
-      if (k4 < k4n) {
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {
-          dmma_8x8x4(acc[mb][0][0], acc[mb][0][1], fa[mb], fb[k4 & 1][0]);
-          dmma_8x8x4(acc[mb][1][0], acc[mb][1][1], fa[mb], fb[k4 & 1][1]);
-          // reload one block behind: the DMMAs that still read fa[mb] have a head start on the overwriting load
-          if (more && mb >= 1) fa[mb - 1] = Sk[(mb - 1) * 8 * sk + (k4 + 1) * 4];
-        }
-        if (more) fa[MB - 1] = Sk[(MB - 1) * 8 * sk + (k4 + 1) * 4];
+      for (int mb = 0; mb < MB; ++mb) {
+        dmma_8x8x4(acc[mb][0][0], acc[mb][0][1], fa[mb], fb[k4 & 1][0]);
+        dmma_8x8x4(acc[mb][1][0], acc[mb][1][1], fa[mb], fb[k4 & 1][1]);
+        // reload one block behind: the DMMAs that still read fa[mb] have a head start on the overwriting load
+        if (more && mb >= 1) fa[mb - 1] = Sk[(mb - 1) * 8 * sk + (k4 + 1) * 4];
       }
+      if (more) fa[MB - 1] = Sk[(MB - 1) * 8 * sk + (k4 + 1) * 4];
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + stage);
     if (++stage == SL_STAGES) { stage = 0; phase ^= 1u; }
-  }
+  };
+  const int nfull = g.K / SL_BK;
+  for (int kt = 0; kt < nfull; ++kt) ktile(kt, std::integral_constant<int, 4>());
+  if (nfull < nkt) ktile(nfull, std::integral_constant<int, 2>());
 
   // epilogue
   const int cols = g.N - n0;
