@@ -54,5 +54,36 @@ if rank == 0:
     assert abs(f - e1) <= 2e-9 * abs(e1) and np.abs(g - g1s).max() <= 2e-9 * np.abs(g1s).max()
     assert abs(f_fr - e2) <= 2e-9 * abs(e2) and np.abs(g_fr - g2s).max() <= 2e-9 * np.abs(g2s).max()
     print('OK')
+# the widened rows (fpi, SMF bound, predict_f) under sharding: every rank computes the same answer as one GPU
+mod.precompute()
+p0 = mod._pack()
+rng = np.random.default_rng(3)
+smp = p0[5:5 + m] + .01 * rng.standard_normal(m)
+t_star = np.linspace(wl['t'][0], wl['t'][-1], 301)
+samples = p0[5:5 + m] + .01 * rng.standard_normal((3, m))
+sh_fpi = mod.engine.fpi(p0, 2, reg=config.reg)
+sh_smf = mod.engine.elbo_smf(p0, smp, mode=0, reg=config.reg)
+sh_pred = mod.engine.predict_f(p0, t_star, samples, reg=config.reg)
+if rank == 0:
+    one_fpi = eng.fpi(p0, 2, reg=config.reg)
+    one_smf = eng.elbo_smf(p0, smp, mode=0, reg=config.reg)
+    one_pred = eng.predict_f(p0, t_star, samples, reg=config.reg)
+    rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max())
+    print('fpi mu_u rel %.2e var_u rel %.2e; smf elbo rel %.2e loglik rel %.2e; predict_f mean rel %.2e var rel %.2e' % (
+        rel(sh_fpi[0], one_fpi[0]), rel(sh_fpi[1], one_fpi[1]), rel(sh_smf[0], one_smf[0]), rel(sh_smf[2], one_smf[2]),
+        rel(sh_pred[0], one_pred[0]), rel(sh_pred[1], one_pred[1])))
+    # the fixed-point map is ill-conditioned at this shape (two inversions of matrices with cond ~ 1/reg per round):
+    # its own sensitivity to the summation order is measured on one GPU (chunk 512 vs 128) and bounds the comparison
+    eng2 = cgpcm_b200.Engine(m, m, device=local)
+    eng2.set_option('chunk', 128)
+    eng2.set_data(wl['t'], wl['y'], mod.th, mod.tx)
+    eng2.precompute(*wl['hyp'], reg=config.reg)
+    alt_fpi = eng2.fpi(p0, 2, reg=config.reg)
+    noise = [rel(alt_fpi[i], one_fpi[i]) for i in (0, 1)]
+    print('fpi sensitivity to the summation order on one GPU: mu_u %.2e var_u %.2e' % tuple(noise))
+    assert rel(sh_fpi[0], one_fpi[0]) < 1e-6 + 10 * noise[0] and rel(sh_fpi[1], one_fpi[1]) < 1e-6 + 10 * noise[1]
+    assert rel(sh_smf[0], one_smf[0]) < 2e-9 and rel(sh_smf[2], one_smf[2]) < 1e-6
+    assert rel(sh_pred[0], one_pred[0]) < 1e-6 and rel(sh_pred[1], one_pred[1]) < 1e-6
+    print('OK widened rows')
 dist.barrier()
 dist.destroy_process_group()
