@@ -457,6 +457,56 @@ class VCGPCM(CGPCM):
         return UncertainData(mean=Data(x, k.mean(axis=1)), lower=Data(x, np.percentile(k, lower_perc, axis=1)),
                              upper=Data(x, np.percentile(k, upper_perc, axis=1)), std=Data(x, k.std(axis=1)))
 
+    def _filter_draws(self, t, samples_h):
+        if np.isscalar(samples_h) or isinstance(samples_h, (int, np.integer)):
+            samples = [self.sample_q() for _ in range(int(samples_h))]
+        else:
+            samples = list(samples_h)
+        samples = np.stack([np.asarray(x, dtype=np.float64).ravel() for x in samples])
+        noise = np.random.randn(t.shape[0], samples.shape[0])
+        return self.engine.filter_samples(self._pack(), t, samples, noise, reg=config.reg)       # [n, B]
+
+    @staticmethod
+    def _mc_stats(x, samples):
+        from .data import Data, UncertainData
+        from .util import lower_perc, upper_perc
+        return UncertainData(mean=Data(x, samples.mean(axis=1)), lower=Data(x, np.percentile(samples, lower_perc, axis=1)),
+                             upper=Data(x, np.percentile(samples, upper_perc, axis=1)), std=Data(x, samples.std(axis=1)))
+
+    def predict_h(self, t, samples_h=500, normalise=True, phase_transform='minimum_phase'):
+        """Predict the filter at ``t`` (``src/core/cgpcm.py:714-779``).  The posterior draws of the filter come from the
+        GPU (``cgpcm_filter_samples``); the positive part, the phase transform (``None`` or ``'minimum_phase'``), the
+        energy normalisation and the percentile band are post-processing of those draws."""
+        from .util import minimum_phase, energy
+        if phase_transform not in (None, 'minimum_phase'):
+            raise NotImplementedError('phase_transform must be None or "minimum_phase"')
+        t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
+        draws = self._filter_draws(t, samples_h)
+        keep = t >= 0 if self.causal else np.ones(t.shape[0], dtype=bool)
+        x = t[keep]
+        cols = []
+        for b in range(draws.shape[1]):
+            y = draws[keep, b]
+            if phase_transform is not None:
+                y = minimum_phase(y)
+            if normalise:
+                y = y / energy(x, y) ** .5
+            cols.append(y)
+        return self._mc_stats(x, np.stack(cols, 1))
+
+    def predict_psd(self, t, samples_h=500, normalise=True):
+        """Predict the PSD from posterior draws of the filter (``src/core/cgpcm.py:663-712``): autocorrelation of
+        every draw, then the reference's FFT convention."""
+        from .util import autocorrelation, fft_spectrum
+        t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
+        draws = self._filter_draws(t, samples_h)
+        cols, freq = [], None
+        for b in range(draws.shape[1]):
+            lags, ac = autocorrelation(t, draws[:, b], normalise=normalise)
+            freq, spec = fft_spectrum(lags, ac)
+            cols.append(np.abs(spec))
+        return self._mc_stats(freq, np.stack(cols, 1))
+
     @property
     def mats(self):
         """Psi statistics at the current (or frozen) hyper-parameters as numpy arrays."""

@@ -1921,6 +1921,100 @@ int kernel_run(cgpcm_handle* h, const double* params_host, double reg, const dou
   return 0;
 }
 
+// Posterior draws of the filter for VCGPCM.predict_h / predict_psd (src/core/cgpcm.py:663-779):
+//   out[p][b] = (Kuh^T h_b)[p] + (L eps_b)[p],   A = Lh^-1 Kuh,   L = chol(reg(k_h(t, t) - A^T A))
+// noise_host: eps as [n][B] (row p, column b).  Four DMMA GEMMs, one triangular inverse, one Cholesky.
+int filter_run(cgpcm_handle* h, const double* params_host, double reg, const double* t_host, long n,
+               const double* samples_host, int B, const double* noise_host, double* out) {
+  const int nh = h->nh, nhp = h->nhp;
+  const long ld = h->ld;
+  for (long i = 0; i < 5; ++i)
+    if (!std::isfinite(params_host[i])) { h->err = "non-finite parameter"; return -4; }
+  for (long i = 0; i < n; ++i)
+    if (!std::isfinite(t_host[i])) { h->err = "non-finite input"; return -4; }
+  for (long i = 0; i < (long)B * nh; ++i)
+    if (!std::isfinite(samples_host[i])) { h->err = "non-finite sample"; return -4; }
+  for (long i = 0; i < n * B; ++i)
+    if (!std::isfinite(noise_host[i])) { h->err = "non-finite noise"; return -4; }
+  if (n > 8192) { h->err = "predict_h / predict_psd: at most 8192 inputs"; return -1; }
+  const double alpha = exp(params_host[2]), gamma = exp(params_host[3]), omega = exp(params_host[4]);
+  h->launches = 0;
+  h->gemm_flops = h->gemm_flops_exec = 0.0;
+  h->gemm_launches = 0;
+  h->pev_used = 0;
+  PsiConst c;
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
+  cudaStream_t st = h->st;
+  const int ldn = round_up((int)n, 8);
+  const int Bp = round_up(B, 8);
+  double *d_t = nullptr, *d_kuh = nullptr, *d_ktt = nullptr, *d_a = nullptr, *d_hs = nullptr, *d_e = nullptr, *d_o = nullptr;
+  auto cleanup = [&]() {
+    double* ps[] = {d_t, d_kuh, d_ktt, d_a, d_hs, d_e, d_o};
+    for (double* q : ps) if (q) cudaFree(q);
+  };
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[256]; snprintf(b_, sizeof b_, \
+    "CUDA error %s in filter_samples (%s)", cudaGetErrorString(e_), #call); h->err = b_; cleanup(); return -2; } } while (0)
+#define PRC(call) do { if (call) { cleanup(); return -2; } } while (0)
+  PCK(cudaMalloc(&d_t, (size_t)n * sizeof(double)));
+  PCK(cudaMalloc(&d_kuh, (size_t)nhp * ldn * sizeof(double)));
+  PCK(cudaMalloc(&d_ktt, (size_t)ldn * ldn * sizeof(double)));
+  PCK(cudaMalloc(&d_a, (size_t)nhp * ldn * sizeof(double)));
+  PCK(cudaMalloc(&d_hs, (size_t)nhp * Bp * sizeof(double)));
+  PCK(cudaMalloc(&d_e, (size_t)ldn * Bp * sizeof(double)));
+  PCK(cudaMalloc(&d_o, (size_t)ldn * Bp * sizeof(double)));
+  PCK(cudaEventRecord(h->ev[0], st));
+  PCK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
+  PCK(cudaMemcpyAsync(d_t, t_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  // Hs[i][b] = samples[b][i] (transposed on the host), E[p][b] = noise[p][b]; zero padding
+  std::vector<double> hs((size_t)nhp * Bp, 0.0), ee((size_t)ldn * Bp, 0.0);
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < nh; ++i) hs[(size_t)i * Bp + b] = samples_host[(size_t)b * nh + i];
+  for (long p2 = 0; p2 < n; ++p2)
+    for (int b = 0; b < B; ++b) ee[(size_t)p2 * Bp + b] = noise_host[(size_t)p2 * B + b];
+  PCK(cudaMemcpyAsync(d_hs, hs.data(), hs.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  PCK(cudaMemcpyAsync(d_e, ee.data(), ee.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  PRC(prior_stage(h, c, reg));                                  // M_LH = chol(reg(Kh)), padded with the identity
+  filter_kernels_kernel<<<148 * 4, 256, 0, st>>>(h->th, nh, nhp, d_t, (int)n, ldn, alpha, gamma, reg, d_kuh, d_ktt);
+  L(h);
+  // X = Lh^-1 ;  A = X Kuh ;  S = Ktt - A^T A ;  L = chol(S)
+  {
+    cudaError_t e = trtri_lower(st, h->M(M_LH), h->M(M_T1), h->M(M_T2), nhp, ld);
+    L(h, 20);
+    if (e != cudaSuccess) { h->err = "trtri launch failed"; cleanup(); return -2; }
+  }
+  PRC(gemm(h, true, false, false, nhp, ldn, nhp, 1.0, h->M(M_T1), ld, d_kuh, ldn, 0.0, d_a, ldn));
+  PRC(gemm(h, false, false, false, ldn, ldn, nhp, -1.0, d_a, ldn, d_a, ldn, 1.0, d_ktt, ldn));
+  {
+    cudaError_t e = potrf_lower(st, d_ktt, ldn, ldn, h->info, 5);
+    L(h, 20);
+    if (e != cudaSuccess) { h->err = "potrf launch failed"; cleanup(); return -2; }
+  }
+  // out = Kuh^T Hs + L E
+  PRC(gemm(h, false, false, false, ldn, Bp, nhp, 1.0, d_kuh, ldn, d_hs, Bp, 0.0, d_o, Bp));
+  PRC(gemm(h, true, false, false, ldn, Bp, ldn, 1.0, d_ktt, ldn, d_e, Bp, 1.0, d_o, Bp));
+  PCK(cudaMemcpy2DAsync(out, (size_t)B * sizeof(double), d_o, (size_t)Bp * sizeof(double), (size_t)B * sizeof(double), n,
+                        cudaMemcpyDefault, st));
+  int info[4];
+  PCK(cudaMemcpyAsync(info, h->info, sizeof info, cudaMemcpyDeviceToHost, st));
+  PCK(cudaEventRecord(h->ev[6], st));
+  PCK(cudaStreamSynchronize(st));
+  PCK(cudaGetLastError());
+  cleanup();
+#undef PCK
+#undef PRC
+  if (info[0]) {
+    h->err = info[0] / 100000 == 5 ? "matrix k_h(t, t) - A^T A + reg I is not positive definite"
+                                   : "matrix Kh is not positive definite";
+    return -3;
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+  memset(h->timing, 0, sizeof h->timing);
+  h->timing[0] = ms;
+  h->timing[6] = (double)h->launches;
+  return 0;
+}
+
 }  // namespace cgimpl
 
 extern "C" {
@@ -2002,6 +2096,24 @@ int cgpcm_kernel_samples(cgpcm_handle* h, const double* params, double reg, cons
   if (is_device_ptr(samples)) CK(cudaMemcpy(smp.data(), samples, smp.size() * sizeof(double), cudaMemcpyDeviceToHost));
   else memcpy(smp.data(), samples, smp.size() * sizeof(double));
   return kernel_run(h, host.data(), reg, ts.data(), n, smp.data(), n_samples, out);
+}
+
+int cgpcm_filter_samples(cgpcm_handle* h, const double* params, double reg, const double* t, int64_t n,
+                         const double* samples, int32_t n_samples, const double* noise, double* out) {
+  if (!h || !params || n < 0 || n_samples < 1 || !samples || !noise || !out || (n > 0 && !t)) return -1;
+  if (!h->th) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  if (!std::isfinite(reg) || reg < 0) { h->err = "reg must be finite and >= 0"; return -4; }
+  if (n == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  std::vector<double> host, ts(n), smp((size_t)n_samples * h->nh), ns((size_t)n * n_samples);
+  if (fetch_params(h, params, 5, host)) return -2;
+  auto fetch = [&](const double* src, std::vector<double>& dst) -> int {
+    if (is_device_ptr(src)) CK(cudaMemcpy(dst.data(), src, dst.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    else memcpy(dst.data(), src, dst.size() * sizeof(double));
+    return 0;
+  };
+  if (fetch(t, ts) || fetch(samples, smp) || fetch(noise, ns)) return -2;
+  return filter_run(h, host.data(), reg, ts.data(), n, smp.data(), n_samples, ns.data(), out);
 }
 
 int cgpcm_fpi(cgpcm_handle* h, const double* params, int32_t num, int32_t high_reg, double reg, double* mu_u,

@@ -159,3 +159,38 @@ __global__ void kernel_finish_kernel(const double* __restrict__ G, long ldg, con
 }
 
 }  // namespace cg
+
+namespace cg {
+
+// Filter-side kernel matrices of predict_h / predict_psd (src/core/cgpcm.py:685-688,738-741; DEQ kernel
+// src/core/kernel.py:43-46):  Kuh[i][p] = k_h(th_i, t_p)  (nhp x ldn, zero padded),
+// Ktt[p][q] = k_h(t_p, t_q) + reg [p == q]  (ldn x ldn; identity on the padding block so that its Cholesky exists).
+__global__ void filter_kernels_kernel(const double* __restrict__ th, int nh, int nhp, const double* __restrict__ t, int n,
+                                      int ldn, double alpha, double gamma, double reg, double* __restrict__ Kuh,
+                                      double* __restrict__ Ktt) {
+  const long n1 = (long)nhp * ldn, n2 = (long)ldn * ldn;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2; idx += (long)gridDim.x * blockDim.x) {
+    if (idx < n1) {
+      const int i = (int)(idx / ldn), p = (int)(idx - (long)i * ldn);
+      double v = 0.0;
+      if (i < nh && p < n) {
+        const double a = th[i], b = t[p];
+        v = exp(-alpha * (a * a + b * b) - gamma * (a - b) * (a - b));
+      }
+      Kuh[idx] = v;
+    } else {
+      const long e = idx - n1;
+      const int p = (int)(e / ldn), q = (int)(e - (long)p * ldn);
+      double v = (p == q) ? 1.0 : 0.0;
+      if (p < n && q < n) {
+        const double a = t[p], b = t[q];
+        v = exp(-alpha * (a * a + b * b) - gamma * (a - b) * (a - b)) + (p == q ? reg : 0.0);
+      } else if (p < n || q < n) {
+        v = 0.0;
+      }
+      Ktt[e] = v;
+    }
+  }
+}
+
+}  // namespace cg

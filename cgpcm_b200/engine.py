@@ -145,6 +145,19 @@ class Engine(object):
                                                       int(samples.shape[0]), _lib.ptr(out)))
         return out
 
+    def filter_samples(self, params, t, samples, noise, reg=1e-8):
+        """Posterior draws ``[n, B]`` of the filter at ``t`` for filter ``samples`` ([B, nh]) and standard normal
+        ``noise`` ([n, B]) (``src/core/cgpcm.py:663-779``)."""
+        t = np.ascontiguousarray(np.asarray(t, dtype=np.float64).ravel())
+        samples = np.ascontiguousarray(np.asarray(samples, dtype=np.float64).reshape(-1, self.nh))
+        noise = np.ascontiguousarray(np.asarray(noise, dtype=np.float64).reshape(t.shape[0], samples.shape[0]))
+        out = np.empty((t.shape[0], samples.shape[0]))
+        if t.shape[0]:
+            self._ck(_lib.lib().cgpcm_filter_samples(self._h, _lib.ptr(np.ascontiguousarray(params[:5])), float(reg),
+                                                      _lib.ptr(t), int(t.shape[0]), _lib.ptr(samples),
+                                                      int(samples.shape[0]), _lib.ptr(noise), _lib.ptr(out)))
+        return out
+
     def fpi(self, params, num, high_reg=False, reg=1e-8):
         """``num`` rounds of the fixed-point iteration on the frozen Psi statistics, then the optimal q(z):
         ``(mu_u[nh], var_u[nh(nh+1)/2], mu_z[nx], var_z[nx(nx+1)/2])`` (``src/core/cgpcm.py:479-516,577-592``)."""

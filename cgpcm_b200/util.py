@@ -50,3 +50,29 @@ def fft_spectrum(t, y, zero_pad=2000):
     pad = np.zeros((zero_pad,) + y.shape[1:], dtype=y.dtype)
     spec = dx * np.fft.fftshift(np.fft.fft(np.concatenate((pad, y, pad), axis=0), axis=0), axes=0)
     return np.fft.fftshift(np.fft.fftfreq(spec.shape[0])) / dx, spec
+
+
+def minimum_phase(y):
+    """``Data.minimum_phase`` (``src/core/data.py:293-303``): the minimum-phase signal with the magnitude spectrum
+    of ``y`` (homomorphic method: Hilbert transform of the log magnitude)."""
+    from scipy import signal
+    mag = np.abs(np.fft.fft(y))
+    spec = np.exp(signal.hilbert(np.log(mag)).conj())
+    return np.real(np.fft.ifft(spec))
+
+
+def energy(x, y):
+    """``Data.energy`` (``src/core/data.py:354-359``): trapezoidal integral of ``y^2``."""
+    trap = getattr(np, 'trapezoid', None) or np.trapz
+    return trap(np.asarray(y) ** 2, x)
+
+
+def autocorrelation(x, y, normalise=False):
+    """``Data.autocorrelation`` (``src/core/data.py:136-171``, biased estimate): ``(lags, ac)``."""
+    y = np.where(np.isnan(y), 0.0, y)
+    n = y.shape[0]
+    ac = np.convolve(y[::-1], y) / n
+    lag = x[-1] - x[0]
+    if normalise:
+        ac = ac / ac.max()
+    return np.linspace(-lag, lag, 2 * n - 1), ac

@@ -110,6 +110,13 @@ int cgpcm_predict_f(cgpcm_handle* h, const double* params, double reg, const dou
 int cgpcm_kernel_samples(cgpcm_handle* h, const double* params, double reg, const double* t, int64_t n,
                          const double* samples, int32_t n_samples, double* out);
 
+/* The posterior draws of the filter that mod.predict_h / mod.predict_psd post-process (src/core/cgpcm.py:663-779):
+ * out[p * n_samples + b] = (Kuh^T h_b + L eps_b)[p] at inputs t[n] with Kuh = k_h(th, t), A = Lh^-1 Kuh,
+ * L = chol(reg(k_h(t, t) - A^T A)); samples[n_samples][nh] are the filter samples h_b, noise[n][n_samples] the
+ * standard normal draws eps (the reference draws them inside the graph).  n <= 8192. */
+int cgpcm_filter_samples(cgpcm_handle* h, const double* params, double reg, const double* t, int64_t n,
+                         const double* samples, int32_t n_samples, const double* noise, double* out);
+
 /* mod.fpi(num, z=True, high_reg) followed by mod.convert(z=True) (src/core/cgpcm.py:479-516,577-592): num rounds of
  * the fixed-point iteration q(u) -> optimal q(z) -> optimal q(u) on the Psi statistics frozen by cgpcm_precompute
  * (Normal.from_natural, src/core/distribution.py:20-33; high_reg adds 1e-4 to both precisions), starting from the

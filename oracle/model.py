@@ -532,3 +532,23 @@ def kernel_samples(params, th, r, t, samples_h, causal=True):
             h = T(np.asarray(hs, np.float64)).reshape(-1, 1)
             cols.append(s2_f * (a + torch.sum((h @ h.T - iKh) * Ahh, (-1, -2))))
     return torch.stack(cols, 1).numpy().copy()
+
+
+# ----------------------------------------------------------------------------- filter prediction (second part)
+def filter_samples(params, th, r, t, samples_h, noise):
+    """The posterior draws of the filter that ``VCGPCM.predict_h`` / ``predict_psd`` (``cgpcm.py:663-779``) post-process:
+    ``Kuh = k_h(th, t)``, ``A = Lh^-1 Kuh``, ``L = chol(reg(k_h(t, t) - A^T A))``,
+    ``sample_b = Kuh^T h_b + L eps_b`` with ``noise[:, b] = eps_b`` (the reference draws ``randn`` in the graph).
+    Returns [n, B]."""
+    with torch.no_grad():
+        nh = len(th)
+        s2, s2_f, alpha, gamma, omega, _, _ = unpack(T(np.asarray(params, np.float64)), nh)
+        thT, tt = T(th), T(t)
+        Kh = reg(deq(1., alpha, gamma, thT), r)
+        Lh = torch.linalg.cholesky(Kh)
+        Kuh = deq(1., alpha, gamma, thT, tt)
+        A = trisolve(Lh, Kuh)
+        L = torch.linalg.cholesky(reg(deq(1., alpha, gamma, tt) - A.T @ A, r))
+        H = T(np.asarray(samples_h, np.float64)).reshape(-1, nh).T          # [nh, B]
+        out = Kuh.T @ H + L @ T(np.asarray(noise, np.float64))
+    return out.numpy().copy()

@@ -123,3 +123,51 @@ def test_predict_k_api():
     with pytest.raises(AssertionError):
         mod.predict_k(np.array([0., .1, .3]), samples_h=2, psd=True)
     config.reg = 1e-8
+
+
+@pytest.mark.parametrize('name,n', [('toy_small', 37), ('sweep_hi', 64), ('hrir', 50)])
+def test_filter_samples_match_oracle(name, n):
+    """predict_h / predict_psd's posterior draws of the filter (src/core/cgpcm.py:663-779)."""
+    c = make_case(name)
+    rng = np.random.default_rng(12)
+    nh = c['nh']
+    samples = c['params'][5:5 + nh] + .3 * rng.standard_normal((6, nh))
+    lo, hi = c['th'].min(), c['th'].max()
+    t = np.linspace(lo - .3 * (hi - lo), hi + .3 * (hi - lo), n)
+    noise = rng.standard_normal((n, 6))
+    om.PW_DISTS_EXACT = True
+    try:
+        want = om.filter_samples(c['params'], c['th'], c['reg'], t, samples, noise)
+        mean_only = om.filter_samples(c['params'], c['th'], c['reg'], t, samples, np.zeros_like(noise))
+    finally:
+        om.PW_DISTS_EXACT = False
+    eng = cgpcm_b200.Engine(c['nh'], c['nx'], causal=c['causal'])
+    eng.set_data(c['t'], c['y'], c['th'], c['tx'])
+    got0 = eng.filter_samples(c['params'], t, samples, np.zeros_like(noise), reg=c['reg'])
+    got = eng.filter_samples(c['params'], t, samples, noise, reg=c['reg'])
+    scale = np.abs(want).max()
+    # conditional mean Kuh^T h: plain kernel evaluations and one GEMM
+    assert np.abs(got0 - mean_only).max() <= 1e-12 * scale
+    # the noise term goes through chol(reg(Ktt - A^T A)), the Nystrom residual of a kernel matrix with cond ~ 1/reg
+    # (measured agreement: 3e-11 relative at reg = 1e-6)
+    resid = np.abs((got - got0) - (want - mean_only)).max()
+    assert resid <= 1e-8 * scale, resid
+
+
+def test_predict_h_and_psd_api():
+    c = make_case('toy_small')
+    config.reg = c['reg']
+    np.random.seed(8)
+    mod = VCGPCM.from_recipe(Session(), Data(c['t'], c['y']), nx=c['nx'], nh=c['nh'], tau_w=.1, tau_f=.05,
+                             causal=True, noise_init=1e-2)
+    t = np.linspace(-.1, .3, 81)
+    h = mod.predict_h(t, samples_h=12)
+    assert np.all(h.mean.x >= 0) and h.mean.x.shape == (61,)          # causal model: the positive part of t
+    assert np.all(np.isfinite(h.mean.y)) and np.all(h.lower.y <= h.upper.y + 1e-15)
+    h_raw = mod.predict_h(t, samples_h=[mod.sample_q() for _ in range(4)], normalise=False, phase_transform=None)
+    assert h_raw.mean.y.shape == (61,)
+    p = mod.predict_psd(t, samples_h=6)
+    assert p.mean.x.shape == (2 * 81 - 1 + 4000,) and np.all(p.mean.y >= 0)
+    with pytest.raises(NotImplementedError):
+        mod.predict_h(t, samples_h=2, phase_transform='zero_phase')
+    config.reg = 1e-8

@@ -167,3 +167,16 @@ def test_fft_spectrum_follows_the_reference_conventions():
     np.testing.assert_allclose(np.abs(s2[:, 1]), 2 * np.abs(s), atol=1e-12)
     with pytest.raises(AssertionError):
         fft_spectrum(np.array([0., 1., 3.]), np.ones(3))
+
+
+def test_signal_helpers_follow_the_reference():
+    """minimum_phase / energy / autocorrelation of cgpcm_b200.util (src/core/data.py:136-171,293-303,354-359)."""
+    from cgpcm_b200.util import minimum_phase, energy, autocorrelation
+    x = np.linspace(0, 1, 101)
+    y = np.exp(-30 * (x - .5) ** 2) * np.cos(40 * x)
+    m = minimum_phase(y)
+    np.testing.assert_allclose(np.abs(np.fft.fft(m)), np.abs(np.fft.fft(y)), rtol=1e-8, atol=1e-10)   # same magnitude
+    assert np.sum(m[:20] ** 2) > np.sum(y[:20] ** 2)              # energy moved to the front
+    assert energy(x, np.ones(101)) == pytest.approx(1.0)
+    lags, ac = autocorrelation(x, y, normalise=True)
+    assert lags.shape == (201,) and ac[100] == pytest.approx(1.0) and np.allclose(ac, ac[::-1])
