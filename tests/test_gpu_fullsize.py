@@ -79,3 +79,34 @@ def test_gradient_directional_derivative(wl, eng):
         an = float(g @ d)
         # evaluation noise ~1e-10 * |ELBO| = 1e-4 over 2h = 2e-3 -> ~0.1 absolute = 4e-8 * |g|
         assert abs(est - an) <= 2e-5 * abs(an) + 2e-7 * gnorm, (sl, est, an)
+
+
+def test_oracle_parity_at_m200_through_the_large_shape_kernels():
+    """nh = nx = 200 with few observations: the evaluation goes through the persistent small-left kernel (dgemm_sl,
+    N = 48 x 200 = 9600 columns per chunk) and the symmetric kernel (dgemm_sym, M = 200) -- the kernels of the bench
+    shape -- at a size the oracle still handles.  Dense and culled, with and without the sweep stores."""
+    from oracle import model as om
+    from tests.cases import ulp_noise
+    n = 96
+    w = sweep_workload(4000, M, seed=3)
+    sl = slice(1000, 1000 + n)                      # a window in the middle: inducing inputs on both sides
+    t, y = np.ascontiguousarray(w['t'][sl]), np.ascontiguousarray(w['y'][sl])
+    om.PW_DISTS_EXACT = True
+    try:
+        (e0, t0, g0), (en, tn, gn) = ulp_noise(
+            lambda p, th: om.elbo_and_grad(p, t, y, th, w['tx'], w['reg']), w['params'], w['th'], trials=1)
+    finally:
+        om.PW_DISTS_EXACT = False
+    scale = max(abs(e0), np.abs(t0).max())
+    for opts in (dict(cull=0.0, chunk=48, store=1), dict(cull=80.0, chunk=64, store=0)):
+        e = cgpcm_b200.Engine(M, M)
+        for k, v in opts.items():
+            e.set_option(k, v)
+        e.set_data(t, y, w['th'], w['tx'])
+        e1, t1, g1 = e.elbo_grad(w['params'], reg=w['reg'])
+        tm = e.last_timing()
+        assert tm['gemm_launches'] > 0
+        assert abs(e1 - e0) <= 1e-9 * scale + 3 * en, opts
+        assert np.abs(t1 - t0).max() <= 1e-9 * scale + 3 * tn, opts
+        assert np.abs(g1 - g0).max() <= 1e-9 * np.abs(g0).max() + 3 * gn, opts
+        e.close()
