@@ -89,3 +89,35 @@ def test_psi_rejects_bad_input():
         eng.psi(1.0, -1.0, 1.0)
     with pytest.raises(ValueError):
         cgpcm_b200.Engine(4, 4).psi(1.0, 1.0, 1.0)      # set_data not called
+
+
+@pytest.mark.parametrize('rho', [0.926, 0.95, 0.985, 0.998])
+@pytest.mark.parametrize('spread', [0.3, 3.0, 30.0])
+def test_axx_pair_hoisted_branch_against_oracle(rho, spread):
+    """The pair-hoisted / Chebyshev evaluation of Genz's |rho| >= 0.925 branch (bvn.cuh) over its whole argument range:
+    correlations from the branch limit to ~1, observation times from inside the inducing inputs to far outside
+    (x1 x2 from <-200, where the un-hoisted routine takes over, to >200, where only the tail term remains).
+    sum_Axx is produced by the hoisted kernel, the per-observation Axx by the plain Genz routine; both against the
+    oracle (torch Genz + closed forms)."""
+    rng = np.random.default_rng(int(rho * 1000) + int(spread * 10))
+    nx, nh, n = 24, 8, 300
+    tx = np.sort(rng.uniform(-1, 1, nx))
+    th = np.linspace(-.02, .2, nh)
+    t = np.sort(rng.uniform(-1 - spread, 1 + spread, n))
+    y = rng.standard_normal(n)
+    gamma = 40.0
+    alpha = 0.25 * gamma * (1 - rho) / rho
+    omega = 0.75 * gamma * (1 - rho) / rho                      # rho = gamma / (alpha + gamma + omega)
+    assert gamma / (alpha + gamma + omega) == pytest.approx(rho)
+    eng = cgpcm_b200.Engine(nh, nx)
+    eng.set_option('cull', 0.0)
+    eng.set_data(t, y, th, tx)
+    got = eng.psi(alpha, gamma, omega, per_observation=True)
+    _, _, Axx, _ = [np.asarray(v) for v in om.psi_closed(t, th, tx, alpha, gamma, omega, causal=True)]
+    np.testing.assert_allclose(got['Axx'], Axx, atol=2e-14, rtol=1e-11)
+    want = Axx.sum(0)
+    assert np.abs(got['sum_Axx'] - want).max() <= 1e-12 * np.abs(want).max() + 1e-14
+    # the sweep's tangents ride on the same per-pair set-up: value-only and tangent variants agree on the sum
+    wl_params = np.concatenate([np.log([.1, 1., alpha, gamma, omega]), np.zeros(nh), np.eye(nh)[np.tril_indices(nh)] * .1])
+    e, terms, g = eng.elbo_grad(wl_params, reg=1e-6)
+    assert np.isfinite(e) and np.all(np.isfinite(g))
