@@ -30,6 +30,7 @@
 #include "../../include/cgpcm_b200.h"
 #include "dgemm_sl.cuh"
 #include "dgemm_sym.cuh"
+#include "gram_kernels.cuh"
 #include "linalg.cuh"
 #include "predict_kernels.cuh"
 #include "psi_kernels.cuh"
@@ -155,6 +156,13 @@ struct cgpcm_handle {
   long storeA_elems = 0, storeT_elems = 0;
   bool use_store = false;      // decided per evaluation
   bool storeA_frozen_valid = false;   // storeA holds the frozen regime's Ahx blocks (constant between evaluations)
+  // fourth-order Psi tensor of the frozen regime (gram_kernels.cuh), option "gram": 0 off (default), 1 when it pays,
+  // 2 whenever it fits.  Opt-in: the contraction with m2 ~ iKh cancels AFTER the sum over observations instead of
+  // before it, which costs ~sqrt(N) in rounding noise (gram_kernels.cuh).
+  int gram_opt = 0;
+  double* gram = nullptr;
+  long gram_elems = 0;
+  bool gram_valid = false;
   double* symacc[2] = {nullptr, nullptr};   // per-K-slice private accumulators of the symmetric contractions
   int sym_used[2] = {0, 0};                 // slices touched since sym_begin
   double* axx_part = nullptr;
@@ -699,6 +707,73 @@ int backward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>&
   return 0;
 }
 
+// ---- fourth-order Psi tensor of the frozen regime (gram_kernels.cuh) --------------------------------------------
+// Built at cgpcm_precompute when it pays: two streaming passes over G per evaluation (16 R^2 bytes, R = nxp nhp)
+// against the contraction sweeps (4 nc nh kwp (nh + kwp) flops per chunk), and when it fits.
+int gram_build(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& chunks) {
+  h->gram_valid = false;
+  if (!h->gram_opt || chunks.empty() || h->nhp > 512) return 0;
+  const long R = (long)h->nxp * h->nhp;
+  const double bytes = 8.0 * (double)R * R;
+  double sweep_flops = 0.0;
+  for (const Chunk& ch : chunks) sweep_flops += 4.0 * ch.nc * h->nhp * ch.kwp * (double)(h->nhp + ch.kwp);
+  const double t_gram = 2.0 * bytes / 4e12, t_sweep = sweep_flops / 25e12 + 5e-6 * 6 * chunks.size();
+  if (h->gram_opt == 1 && t_gram > 0.5 * t_sweep) return 0;
+  if (h->gram_elems < R * R) {
+    if (h->gram) { cudaFree(h->gram); h->gram = nullptr; h->gram_elems = 0; }
+    size_t free_b = 0, tot_b = 0;
+    if (cudaMemGetInfo(&free_b, &tot_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (bytes > 0.35 * (double)free_b) return 0;
+    if (cudaMalloc(&h->gram, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); h->gram = nullptr; return 0; }
+    h->gram_elems = R * R;
+  }
+  CK(cudaMemsetAsync(h->gram, 0, (size_t)bytes, h->st));
+  for (const Chunk& ch : chunks) {
+    const long row = (long)ch.kwp * h->nhp;
+    ahx_gen_nki_kernel<<<148 * 8, 256, 0, h->st>>>(h->t + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->nhp, h->tx, h->nx, ch.k_lo,
+                                                   ch.kwp, h->wsT, c);
+    L(h);
+    double* Gwin = h->gram + (long)ch.k_lo * h->nhp * (R + 1);
+    // G_window += Ac^T Ac (lower tiles)
+    if (gemm(h, false, false, false, (int)row, (int)row, ch.nc, 1.0, h->wsT, row, h->wsT, row, 1.0, Gwin, R, 1, 0, 1))
+      return -2;
+  }
+  dim3 grid((unsigned)((R + 31) / 32), (unsigned)((R + 31) / 32));
+  gram_mirror_kernel<<<grid, 256, 0, h->st>>>(h->gram, R, (int)R);
+  L(h);
+  CK(cudaGetLastError());
+  h->gram_valid = true;
+  return 0;
+}
+
+// M_C1 = sum_n A_n^T Hm A_n over the frozen regime's blocks: from G when resident, else the forward sweep
+int frozen_c1(cgpcm_handle* h, const std::vector<Chunk>& chunks, const double* Hm) {
+  if (!h->gram_valid) return forward_sweep(h, h->fc, chunks, Hm, nullptr, false, false);
+  const long R = (long)h->nxp * h->nhp;
+  zero(h, h->M(M_C1), h->ld * h->ld);
+  gram_c1_kernel<<<h->nx * (h->nx + 1) / 2, 256, 0, h->st>>>(h->gram, R, h->nx, h->nh, h->nhp, Hm, h->ld, h->M(M_C1), h->ld);
+  L(h);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// out (ld x ld) = sum_n A_n W A_n^T from G
+int gram_q(cgpcm_handle* h, const double* W, double* out) {
+  const long R = (long)h->nxp * h->nhp;
+  const int slices = 16;
+  const int threads = std::min(256, round_up(h->nhp, 32));
+  zero(h, out, h->ld * h->ld);
+  dim3 grid(h->nh, slices);
+  gram_q_kernel<<<grid, threads, h->nx * sizeof(double), h->st>>>(h->gram, R, h->nx, h->nh, h->nhp, W, h->ld, h->ypart,
+                                                                  h->ld);
+  L(h);
+  const long total = (long)h->nhp * h->ld;
+  ypart_reduce_kernel<<<148, 256, 0, h->st>>>(h->ypart, slices, total, total, out);
+  L(h);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // Q-type sweep with an arbitrary symmetric ld x ld matrix W in place of iKx:  M_Q = sum_n A_n W A_n^T  over the
 // frozen regime's Ahx blocks (the z = False contraction of _optimal_q, src/core/cgpcm.py:473-475).
 int q_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& chunks, const double* W) {
@@ -810,7 +885,7 @@ int cgpcm_destroy(cgpcm_handle* h) {
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->comm && h->own_comm && nccl().ok) nccl().CommDestroy(h->comm);
   double* ptrs[] = {h->t, h->y, h->th, h->tx, h->mats, h->vecs, h->sc, h->params_d, h->gvar_d, h->wsA, h->wsT,
-                    h->wsV, h->axx_part, h->ypart, h->gpart, h->symacc[0], h->symacc[1], h->storeA, h->storeT, h->cheb_d};
+                    h->wsV, h->axx_part, h->ypart, h->gpart, h->symacc[0], h->symacc[1], h->storeA, h->storeT, h->cheb_d, h->gram};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   if (h->info) cudaFree(h->info);
@@ -872,6 +947,12 @@ int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
     h->storeA_frozen_valid = false;
     return 0;
   }
+  if (!strcmp(key, "gram")) {
+    h->gram_opt = (int)value;
+    h->gram_valid = false;
+    if (!h->gram_opt && h->gram) { cudaFree(h->gram); h->gram = nullptr; h->gram_elems = 0; }
+    return 0;
+  }
   if (!strcmp(key, "sl")) {
     h->sl_opt = (int)value;
     return 0;
@@ -904,6 +985,7 @@ int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_
   h->n_local = n_local;
   h->frozen = false;
   h->storeA_frozen_valid = false;
+  h->gram_valid = false;
   const long na = std::max<long>(n_local, 1);
   CK(cudaMalloc(&h->t, na * sizeof(double)));
   CK(cudaMalloc(&h->y, na * sizeof(double)));
@@ -943,7 +1025,7 @@ namespace cgimpl {
 
 int ensure_sweep_buffers(cgpcm_handle* h) {
   if (ensure_ws(h)) return -2;
-  int ys = (round_up(h->chunk, 32) + 32) * h->nxp / 8 / AHX_NSUB + 2;   // narrowest window = 8 columns
+  int ys = std::max(16, (round_up(h->chunk, 32) + 32) * h->nxp / 8 / AHX_NSUB + 2);   // narrowest window = 8 columns; >= the 16 slices of gram_q
   if (ys > h->y_slices) {
     if (h->ypart) cudaFree(h->ypart);
     h->ypart = nullptr;
@@ -1147,9 +1229,13 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   }
   CK(cudaEventRecord(h->ev[2], st));
   const bool want_hyp = full && !freeze && grad && (grad_mask & (CGPCM_GRAD_ALPHA | CGPCM_GRAD_GAMMA | CGPCM_GRAD_OMEGA));
-  if (plan_store(h, chunks, want_hyp)) return -2;
+  if ((full || !h->gram_valid) && plan_store(h, chunks, want_hyp)) return -2;
   if (full) h->storeA_frozen_valid = false;      // a full-regime sweep overwrites the resident Ahx blocks
-  if (forward_sweep(h, ca, chunks, Hm, h->M(M_IKX), full, want_hyp)) return -2;
+  if (!full && h->gram_valid) {
+    if (frozen_c1(h, chunks, Hm)) return -2;     // two streaming passes over the resident Psi tensor instead of sweeps
+  } else {
+    if (forward_sweep(h, ca, chunks, Hm, h->M(M_IKX), full, want_hyp)) return -2;
+  }
   // tail scalars [n, sum_y2]
   {
     double tail[2] = {(double)h->n_local, h->sum_y2_local};
@@ -1204,6 +1290,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     h->fc = c;
     h->frozen = true;
     h->storeA_frozen_valid = h->use_store;       // the blocks just generated are the frozen regime's
+    if (gram_build(h, c, chunks)) return -2;
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     return 0;
@@ -1291,7 +1378,11 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   const bool want_q = grad_mask & (CGPCM_GRAD_MU_U | CGPCM_GRAD_VAR_U);
   const bool want_grad = grad && grad_mask;
   if (want_grad && (want_hyp || want_q)) {
-    if (backward_sweep(h, ca, chunks, Hm, want_hyp, h->fwd_tail + 2)) return -2;
+    if (!full && h->gram_valid) {
+      if (gram_q(h, h->M(M_C1BAR), h->M(M_HBAR))) return -2;
+    } else {
+      if (backward_sweep(h, ca, chunks, Hm, want_hyp, h->fwd_tail + 2)) return -2;
+    }
     // ---- 6. all-reduce #2
     if (h->world > 1) {
       if (allreduce(h, h->M(M_HBAR), l2)) return -2;
@@ -1538,7 +1629,7 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
   CK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
   CK(cudaMemcpyAsync(h->params_d, params_host, np * sizeof(double), cudaMemcpyHostToDevice, st));
   if (prior_stage(h, c, reg)) return -2;
-  if (plan_store(h, chunks, false)) return -2;
+  if (!h->gram_valid && plan_store(h, chunks, false)) return -2;
   double* Lq = h->M(M_LQ);
   double* mu = h->V(V_MU);
   double* muz = h->V(V_MUZ);
@@ -1566,7 +1657,7 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
       Hm[idx] = var[idx] + mu[i] * mu[j];
     });
     L(h);
-    if (forward_sweep(h, h->fc, chunks, Hm, nullptr, false, false)) return -2;
+    if (frozen_c1(h, chunks, Hm)) return -2;
     if (allreduce(h, h->M(M_C1), l2)) return -2;
     {
       double* Pm = h->M(M_LP);
@@ -1594,7 +1685,8 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
       });
       L(h);
     }
-    if (q_sweep(h, h->fc, chunks, h->M(M_WX))) return -2;
+    if (h->gram_valid) { if (gram_q(h, h->M(M_WX), h->M(M_Q))) return -2; }
+    else if (q_sweep(h, h->fc, chunks, h->M(M_WX))) return -2;
     if (allreduce(h, h->M(M_Q), l2)) return -2;
     {
       double* Pu = h->M(M_SO);
@@ -1717,7 +1809,7 @@ int predict_run(cgpcm_handle* h, const double* params_host, double reg, const do
                         cudaMemcpyHostToDevice, st));
   PCK(cudaMemsetAsync(d_acc, 0, (size_t)2 * std::max<long>(n_star, 1) * sizeof(double), st));
   PRC(prior_stage(h, c, reg));
-  PRC(plan_store(h, chunks, false));
+  if (!h->gram_valid) PRC(plan_store(h, chunks, false));
   // q(u) moments
   double* Lq = h->M(M_LQ);
   double* mu = h->V(V_MU);
@@ -1751,7 +1843,7 @@ int predict_run(cgpcm_handle* h, const double* params_host, double reg, const do
         Hm[idx] = smf_ ? mvec[i] * mvec[j] : var[idx] + mvec[i] * mvec[j];
       });
       L(h);
-      PRC(forward_sweep(h, h->fc, chunks, Hm, nullptr, false, false));
+      PRC(frozen_c1(h, chunks, Hm));
       PRC(allreduce(h, h->M(M_C1), l2));
       double* Pm = h->M(M_LP);
       const double* kx = h->M(M_KX);

@@ -70,7 +70,11 @@ int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_
  * "profile" (1 = CUDA events around every GEMM launch so that cgpcm_last_timing reports their sum),
  * "store" (1 = default: keep the Ahx blocks and H*Ahx of the forward sweep resident in HBM for the backward sweep
  * when they fit -- 2 x 8 nh N nx bytes; 0 = always regenerate / recompute per chunk),
- * "sl" (1 = default: products with a small left operand run on the persistent bulk-copy kernel; 0 = tiled kernel). */
+ * "sl" (1 = default: products with a small left operand run on the persistent bulk-copy kernel; 0 = tiled kernel),
+ * "gram" (0 = default: off; 1: cgpcm_precompute also builds the fourth-order tensor G = sum_n Ahx_n (x) Ahx_n, 8 (nh nx)^2
+ * bytes, when it fits and pays, and MODE_FROZEN evaluations / fpi / SMF / predict_f contract with it instead of
+ * sweeping over the observations; 2 = whenever it fits.  Opt-in because it is noisier: the cancellation against
+ * m2 ~ iKh then happens after the sum over observations, ~sqrt(N) more rounding noise than the sweeps). */
 int cgpcm_set_option(cgpcm_handle* h, const char* key, double value);
 
 /* Psi statistics at hyper-parameters hyp = {alpha, gamma, omega}: what `sess.run(mats[...])` returns

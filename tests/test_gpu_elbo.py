@@ -122,6 +122,38 @@ def test_sweep_stores_do_not_change_the_result(name):
         np.testing.assert_array_equal(a[2], b[2])
 
 
+@pytest.mark.parametrize('name', ['toy_small', 'sweep_wide', 'sweep_hi'])
+def test_psi_tensor_of_the_frozen_regime(name):
+    """Option "gram": the precomputed regime contracts the resident fourth-order tensor G = sum_n Ahx_n (x) Ahx_n
+    instead of sweeping over the observations (gram_kernels.cuh).  Forced on (2) against off (0): the frozen ELBO and
+    gradient, a fixed-point round and the SMF bound agree to the rounding of a different summation order."""
+    c = make_case(name)
+    p = c['params'].copy()
+    p[0] += .2
+    p[5:] *= 1.03
+    rng = np.random.default_rng(1)
+    smp = p[5:5 + c['nh']] + .01 * rng.standard_normal(c['nh'])
+    outs = []
+    for gram in (2, 0):
+        eng = _engine(c, chunk=64, gram=gram)
+        eng.precompute(*c['hyp'], reg=c['reg'])
+        fr = eng.elbo_grad(p, mode=MODE_FROZEN, reg=c['reg'])
+        launches = eng.last_timing()['launches']
+        fpi = eng.fpi(p, 1, reg=c['reg'])
+        smf = eng.elbo_smf(p, smp, mode=MODE_FROZEN, reg=c['reg'])
+        full = eng.elbo_grad(p, reg=c['reg'])                      # the full regime is untouched by the option
+        outs.append((fr, fpi, smf, full, launches))
+    (fr1, fpi1, smf1, full1, l1), (fr0, fpi0, smf0, full0, l0) = outs
+    assert l1 < l0                                                 # no sweep launches in the tensor path
+    scale = max(abs(fr0[0]), np.abs(fr0[1]).max())
+    assert abs(fr1[0] - fr0[0]) <= 1e-9 * scale
+    assert np.abs(fr1[2] - fr0[2]).max() <= 1e-8 * np.abs(fr0[2]).max()
+    for a, b in zip(fpi1, fpi0):
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
+    assert abs(smf1[0] - smf0[0]) <= 1e-9 * scale and abs(smf1[2] - smf0[2]) <= 1e-7 * max(abs(smf0[2]), 1.0)
+    assert full1[0] == full0[0] and np.array_equal(full1[2], full0[2])
+
+
 def test_device_resident_buffers():
     c = make_case('toy_small')
     dev = lambda x: torch.tensor(x, dtype=torch.float64, device='cuda')

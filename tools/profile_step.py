@@ -17,14 +17,22 @@ ap.add_argument('--cull', type=float, default=0.0)
 ap.add_argument('--chunk', type=int, default=512)
 ap.add_argument('--warmup', type=int, default=2)
 ap.add_argument('--mode', type=int, default=1)
-a = ap.parse_args()
+a, _unknown = ap.parse_known_args()
 wl = sweep_workload(a.n, a.m)
 eng = cgpcm_b200.Engine(a.m, a.m)
 eng.set_option('cull', a.cull)
 eng.set_option('chunk', a.chunk)
 eng.set_data(wl['t'], wl['y'], wl['th'], wl['tx'])
+ap_gram = [x for x in sys.argv if x.startswith('--gram=')]
+if ap_gram:
+    eng.set_option('gram', int(ap_gram[0].split('=')[1]))
 if a.mode == 0:
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     eng.precompute(*wl['hyp'], reg=wl['reg'])
+    torch.cuda.synchronize()
+    print('precompute wall %.1f ms' % ((time.perf_counter() - t0) * 1e3))
 for _ in range(a.warmup):
     eng.elbo_grad(wl['params'], mode=a.mode, reg=wl['reg'])
 torch.cuda.synchronize()
