@@ -14,7 +14,10 @@
 // Layouts (S always k-contiguous: S[m*lds + k]):
 //   B_KC = false: B(k,n) at B[k*ldb + n], C(m,n) at C[m*ldc + n]               (left multiply,  T1 = H A)
 //   B_KC = true : B(k,n) at B[n*ldb + k], C(m,n) at C[n*ldc + m]  (transposed)  (right multiply, out^T = W X^T)
-// Requirements: M, N, K multiples of 8; K <= 200; M <= 208; lds, ldb, ldc even; 16-byte aligned pointers.
+// Requirements: M, N, K multiples of 8; 16 <= K <= 200; 16 <= M <= 208; lds, ldb, ldc even; 16-byte aligned pointers.
+// M <= 104 (the windows of inducing inputs that survive when all-zero tiles are skipped) runs as one "half" owned by
+// every CTA; otherwise rows [0, 104) and [104, M) are two halves dealt to CTAs in proportion to their DMMA work.
+// The row blocks per half are compile-time (5, 9, 12 or 13 blocks of 8 rows; the smallest that covers the half).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -42,7 +45,7 @@ struct SlArgs {
   int M, N, K;
   long lds, ldb, ldc;
   double alpha;
-  int ctas0;      // CTAs [0, ctas0) own rows [0, 104), the rest rows [104, M)
+  int ctas0;      // CTAs [0, ctas0) own rows [0, 8 MB0), the rest rows [8 MB0, M)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -164,16 +167,16 @@ __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
   double* Ssm = rings + 2 * SL_STAGES * TILE;                         // [104][sk]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int half = (int)blockIdx.x >= g.ctas0 ? 1 : 0;
-  const int m_base = half ? SL_MB * 8 : 0;
-  const int rows = min(SL_MB * 8, g.M - m_base);          // valid rows of this half
+  const int half = (MB1 > 0 && (int)blockIdx.x >= g.ctas0) ? 1 : 0;
+  const int m_base = half ? MB0 * 8 : 0;
+  const int rows = min((half ? MB1 : MB0) * 8, g.M - m_base);   // valid rows of this half
   const int q = half ? blockIdx.x - g.ctas0 : blockIdx.x; // index among the CTAs of this half
   const int cq = half ? gridDim.x - g.ctas0 : g.ctas0;
   const int ntiles = (g.N + SL_BN - 1) / SL_BN;
   const int nkt = (g.K + SL_BK - 1) / SL_BK;
 
   // ---- resident half of S (rows beyond the matrix zero-filled), barriers
-  for (int e = tid; e < SL_MB * 8 * (g.K / 2); e += SL_NT) {
+  for (int e = tid; e < (half ? MB1 : MB0) * 8 * (g.K / 2); e += SL_NT) {
     const int r = e / (g.K / 2), c2 = (e - r * (g.K / 2)) * 2;
     double2 v = make_double2(0.0, 0.0);
     if (r < rows) v = *reinterpret_cast<const double2*>(g.S + (long)(m_base + r) * g.lds + c2);
@@ -249,10 +252,14 @@ __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
   for (int it = grpid; q + (long)it * cq < ntiles; it += 2) {
     const int n0 = (q + it * cq) * SL_BN;
     uint64_t* sg = it == 0 ? stagger : nullptr;
-    if (half == 0 || MB1 == MB0)
+    if constexpr (MB1 == 0 || MB1 == MB0) {
       sl_consume_tile<MB0, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
-    else
-      sl_consume_tile<MB1, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
+    } else {
+      if (half == 0)
+        sl_consume_tile<MB0, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
+      else
+        sl_consume_tile<MB1, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
+    }
   }
 }
 
@@ -263,8 +270,24 @@ inline size_t dgemm_sl_smem(int K, bool b_kc) {
 }
 
 inline bool dgemm_sl_supported(int M, int N, int K) {
-  return M > 104 && M <= 2 * SL_MB * 8 && K >= 16 && K <= SL_KMAX && (M % 8) == 0 && (N % 8) == 0 && (K % 8) == 0 &&
+  return M >= 16 && M <= 2 * SL_MB * 8 && K >= 16 && K <= SL_KMAX && (M % 8) == 0 && (N % 8) == 0 && (K % 8) == 0 &&
          N >= 64 * 148;
+}
+
+// smallest instantiated number of 8-row blocks that covers mb blocks
+inline int dgemm_sl_blocks(int mb) { return mb <= 5 ? 5 : mb <= 9 ? 9 : mb <= 12 ? 12 : 13; }
+
+template <int MB0, int MB1>
+inline void dgemm_sl_launch(cudaStream_t st, bool b_kc, const SlArgs& g, int sms, size_t smem) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    const int mx = 232448;
+    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<MB0, MB1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<MB0, MB1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    attr_done = true;
+  }
+  if (b_kc) dgemm_sl_kernel<MB0, MB1, true><<<sms, SL_NT, smem, st>>>(g);
+  else dgemm_sl_kernel<MB0, MB1, false><<<sms, SL_NT, smem, st>>>(g);
 }
 
 // b_kc = false: C[m*ldc + n] = alpha sum_k S[m*lds + k] B[k*ldb + n];  b_kc = true: C[n*ldc + m] = alpha sum_k S[m*lds + k] B[n*ldb + k]
@@ -272,28 +295,29 @@ inline cudaError_t dgemm_sl(cudaStream_t st, bool b_kc, int M, int N, int K, dou
                             const double* B, long ldb, double* C, long ldc, int sms = 148) {
   SlArgs g;
   g.S = S; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lds = lds; g.ldb = ldb; g.ldc = ldc; g.alpha = alpha;
-  const int rows1 = M - SL_MB * 8;
-  // CTAs are shared between the two halves in proportion to their rows
-  int ctas0 = (int)((double)sms * (SL_MB * 8) / M + 0.5);
-  if (ctas0 >= sms) ctas0 = sms - 1;
-  g.ctas0 = ctas0;
   const size_t smem = dgemm_sl_smem(K, b_kc);
-  const bool pair12 = rows1 == 96;
-  static bool attr_done = false;
-  if (!attr_done) {
-    const int mx = 232448;
-    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<13, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<13, 12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<13, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<13, 13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    attr_done = true;
-  }
-  if (pair12) {
-    if (b_kc) dgemm_sl_kernel<13, 12, true><<<sms, SL_NT, smem, st>>>(g);
-    else dgemm_sl_kernel<13, 12, false><<<sms, SL_NT, smem, st>>>(g);
+  const int mb = M / 8;
+  if (mb <= SL_MB) {
+    g.ctas0 = sms;
+    switch (dgemm_sl_blocks(mb)) {
+      case 5: dgemm_sl_launch<5, 0>(st, b_kc, g, sms, smem); break;
+      case 9: dgemm_sl_launch<9, 0>(st, b_kc, g, sms, smem); break;
+      case 12: dgemm_sl_launch<12, 0>(st, b_kc, g, sms, smem); break;
+      default: dgemm_sl_launch<13, 0>(st, b_kc, g, sms, smem); break;
+    }
   } else {
-    if (b_kc) dgemm_sl_kernel<13, 13, true><<<sms, SL_NT, smem, st>>>(g);
-    else dgemm_sl_kernel<13, 13, false><<<sms, SL_NT, smem, st>>>(g);
+    // CTAs are shared between the two halves in proportion to their DMMA blocks (+1: per-tile overhead)
+    const int mb1 = dgemm_sl_blocks(mb - SL_MB);
+    int ctas0 = (int)((double)sms * (SL_MB + 1) / (SL_MB + mb1 + 2) + 0.5);
+    if (ctas0 >= sms) ctas0 = sms - 1;
+    if (ctas0 < 1) ctas0 = 1;
+    g.ctas0 = ctas0;
+    switch (mb1) {
+      case 5: dgemm_sl_launch<13, 5>(st, b_kc, g, sms, smem); break;
+      case 9: dgemm_sl_launch<13, 9>(st, b_kc, g, sms, smem); break;
+      case 12: dgemm_sl_launch<13, 12>(st, b_kc, g, sms, smem); break;
+      default: dgemm_sl_launch<13, 13>(st, b_kc, g, sms, smem); break;
+    }
   }
   return cudaGetLastError();
 }

@@ -55,6 +55,16 @@ def test_dense_equals_culled_and_terms_sum(wl, eng):
     assert np.abs(dense[2] - culled[2]).max() <= 1e-9 * np.abs(dense[2]).max()
     assert dense[1].sum() == pytest.approx(dense[0], rel=1e-13)
     assert t_c['total_ms'] > 0
+    # cull = 746: only windows whose elements are exactly 0.0 in IEEE double are skipped (exp(E) underflows for
+    # E < -745.13) -- the same sums as the all-tiles evaluation in a different order
+    t_d = eng.last_timing()
+    eng.set_option('cull', 746.0)
+    exact = eng.elbo_grad(wl['params'], reg=wl['reg'])
+    t_e = eng.last_timing()
+    eng.set_option('cull', 80.0)
+    assert abs(dense[0] - exact[0]) <= 2e-10 * abs(dense[0])
+    assert np.abs(dense[2] - exact[2]).max() <= 1e-9 * np.abs(dense[2]).max()
+    assert t_e['gemm_flops'] < 0.5 * t_d['gemm_flops']
 
 
 def test_gradient_directional_derivative(wl, eng):

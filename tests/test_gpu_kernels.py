@@ -88,11 +88,15 @@ def test_dgemm_split_k_and_lower_only():
 
 @pytest.mark.parametrize('b_kc', [0, 1])
 @pytest.mark.parametrize('M,K,N', [(200, 200, 64 * 148 + 64 * 37), (200, 184, 64 * 150 + 8), (168, 200, 64 * 148),
-                                   (208, 24, 64 * 149 + 40)])
+                                   (208, 24, 64 * 149 + 40),
+                                   # windows of inducing inputs (one half, 5 / 9 / 12 / 13 row blocks) and 104 + a short half
+                                   (96, 96, 64 * 148 + 64 * 5), (40, 40, 64 * 300 + 16), (16, 16, 64 * 148),
+                                   (72, 56, 64 * 150 + 24), (104, 104, 64 * 148), (88, 200, 64 * 149),
+                                   (112, 112, 64 * 148 + 8), (136, 136, 64 * 151)])
 def test_dgemm_small_left(b_kc, M, K, N):
     """Persistent small-left-operand kernel (dgemm_sl.cuh: resident S, bulk-copy ring, mbarriers) against numpy,
-    both layouts (left multiply / transposed right multiply), ragged N tiles, short last k-tile, M = 104 + 96
-    and the zero-padded generic halves."""
+    both layouts (left multiply / transposed right multiply), ragged N tiles, short last k-tile, M = 104 + 96,
+    the zero-padded generic halves and the single-half windows (M <= 104)."""
     rng = np.random.default_rng(M + K + N + b_kc)
     S = rng.standard_normal((M, K))
     B = rng.standard_normal((K, N))
