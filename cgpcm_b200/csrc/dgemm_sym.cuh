@@ -16,6 +16,11 @@
 // Each K-slice accumulates into its own private M x M buffer across all launches of a sweep (C[z] += ...),
 // and one fixed-order reduction at the end of the sweep adds the slices: deterministic, and the per-launch
 // split-K reduction disappears.
+//
+// Orders below 200 (the windows of inducing inputs that survive when all-zero tiles are skipped) run the same kernel
+// with G = 1..4 warp-block rows.  With few blocks (G <= 3) every block is shared by KSUB = 2 or 4 warps that take
+// alternate k4 steps of each k-tile, so that the SM still carries >= 12 DMMA-issuing warps; their accumulators are
+// added in a fixed order through shared memory before the epilogue.
 #pragma once
 #include "dgemm_dmma.cuh"
 
@@ -33,6 +38,18 @@ constexpr int SY_STAGE = 2 * SY_PANEL;
 constexpr int SY_SMEM_BYTES = SY_STAGES * SY_STAGE * 8;
 constexpr int SY_MAX_SPLITS = 148;
 
+// Per-order staging: G warp-block rows stage GM = 40 G panel rows; smaller panels get a deeper pipeline so that the
+// bytes in flight per SM stay ~100 KB (the low-order contractions are close to HBM-bound: 6 flop / byte at M = 96).
+template <int G>
+struct SymCfg {
+  static constexpr int GM = G * SY_BLK;
+  static constexpr int LDN = GM + 4;                     // row stride of the m-contiguous layout, == 4 (mod 8)
+  static constexpr int PANEL = GM * (SY_BK + 4);         // doubles (>= SY_BK * LDN)
+  static constexpr int STAGE = 2 * PANEL;
+  static constexpr int STAGES = G >= 5 ? 3 : G == 4 ? 4 : G == 3 ? 5 : G == 2 ? 7 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE * 8;
+};
+
 struct SymArgs {
   const double* A;
   const double* B;
@@ -45,11 +62,14 @@ struct SymArgs {
 };
 
 // One consumer warp: block (gi, gj) of the lower triangle.  DIAG: gi == gj, only the DMMA tiles i >= j are computed.
-template <bool KC, bool DIAG>
-__device__ __forceinline__ void sym_consume(const SymArgs& g, const double* smem, int ktiles, int gi, int gj, int lane) {
+template <bool KC, bool DIAG, int G, int KSUB, int NCONS>
+__device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int ktiles, int gi, int gj, int lane,
+                                            int sub, int blk) {
+  constexpr int STEPS = (SY_BK / 4) / KSUB;      // k4 steps of a k-tile taken by this warp
+  constexpr int LDN = SymCfg<G>::LDN, PANEL = SymCfg<G>::PANEL, STAGE = SymCfg<G>::STAGE, STAGES = SymCfg<G>::STAGES;
   const int grp = lane >> 2, tig = lane & 3;
-  const int a_off = KC ? (gi * SY_BLK + grp) * (SY_BK + 4) + tig : tig * (SY_MP + 4) + gi * SY_BLK + grp;
-  const int b_off = SY_PANEL + (KC ? (gj * SY_BLK + grp) * (SY_BK + 4) + tig : tig * (SY_MP + 4) + gj * SY_BLK + grp);
+  const int a_off = KC ? (gi * SY_BLK + grp) * (SY_BK + 4) + tig : tig * LDN + gi * SY_BLK + grp;
+  const int b_off = PANEL + (KC ? (gj * SY_BLK + grp) * (SY_BK + 4) + tig : tig * LDN + gj * SY_BLK + grp);
 
   double acc[5][5][2];
 #pragma unroll
@@ -62,21 +82,23 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, const double* smem
   // loaded as soon as its register dies: each load then has at least four DMMAs of this warp (and all the
   // DMMAs of the SMSP's other warps) between issue and first use.
   auto ldf = [&](const double* P, int k4, int x) {
-    return KC ? P[x * 8 * (SY_BK + 4) + k4 * 4] : P[k4 * 4 * (SY_MP + 4) + x * 8];
+    return KC ? P[x * 8 * (SY_BK + 4) + k4 * 4] : P[k4 * 4 * LDN + x * 8];
   };
 
   int stage = 0;
   for (int kt = 0; kt < ktiles; ++kt) {
     __syncthreads();
-    const double* Ap = smem + stage * SY_STAGE + a_off;
-    const double* Bp = smem + stage * SY_STAGE + b_off;
+    const double* Ap = smem + stage * STAGE + a_off;
+    const double* Bp = smem + stage * STAGE + b_off;
     double fa[5], fb[5];
+    const int k40 = KSUB > 1 ? sub * STEPS : 0;
 #pragma unroll
-    for (int x = 0; x < 5; ++x) { fa[x] = ldf(Ap, 0, x); fb[x] = ldf(Bp, 0, x); }
+    for (int x = 0; x < 5; ++x) { fa[x] = ldf(Ap, k40, x); fb[x] = ldf(Bp, k40, x); }
 #pragma unroll
-    for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
-      const bool more = k4 + 1 < SY_BK / 4;
-      if ((k4 & 1) == 0) {
+    for (int s4 = 0; s4 < STEPS; ++s4) {
+      const int k4 = k40 + s4;
+      const bool more = s4 + 1 < STEPS;
+      if ((s4 & 1) == 0) {
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
 #pragma unroll
@@ -98,7 +120,37 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, const double* smem
         }
       }
     }
-    if (++stage == SY_STAGES) stage = 0;
+    if (++stage == STAGES) stage = 0;
+  }
+
+  if (KSUB > 1) {
+    // add the KSUB partial accumulators of this block in a fixed order (sub 1, 2, .. into sub 0) through the drained
+    // pipeline buffers; named barrier 1 = the consumer warps only (the producer warp has left)
+    asm volatile("bar.sync 1, %0;\n" ::"n"(NCONS * 32) : "memory");
+    double* red = smem + (long)blk * (KSUB - 1) * 1600;
+    if (sub > 0) {
+      double* r = red + (sub - 1) * 1600 + lane;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          r[(i * 5 + j) * 64] = acc[i][j][0];
+          r[(i * 5 + j) * 64 + 32] = acc[i][j][1];
+        }
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(NCONS * 32) : "memory");
+    if (sub > 0) return;
+#pragma unroll
+    for (int q = 0; q < KSUB - 1; ++q) {
+      const double* r = red + q * 1600 + lane;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          acc[i][j][0] += r[(i * 5 + j) * 64];
+          acc[i][j][1] += r[(i * 5 + j) * 64 + 32];
+        }
+    }
   }
 
   double* C = g.C + (long)blockIdx.x * g.c_split_stride;
@@ -129,16 +181,20 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, const double* smem
 // no loader state, so they fit the 128-register budget of a 512-thread CTA); warp 15 is the producer and
 // issues every cp.async of both panels.  One __syncthreads per k-tile hands a filled stage to the consumers
 // and a drained one back to the producer.
-template <bool KC>
-__global__ void __launch_bounds__(SY_NT, 1) dgemm_sym_kernel(const SymArgs g) {
+template <bool KC, int G = SY_G, int KSUB = 1>
+__global__ void __launch_bounds__((G * (G + 1) / 2 * KSUB + 1) * 32, 1) dgemm_sym_kernel(const SymArgs g) {
   extern __shared__ __align__(16) double smem[];
+  constexpr int NB = G * (G + 1) / 2;          // warp blocks of the lower triangle
+  constexpr int NCONS = NB * KSUB;             // consumer warps; warp NCONS is the producer
+  constexpr int GM = SymCfg<G>::GM;            // panel rows this instantiation stages
+  constexpr int LDN = SymCfg<G>::LDN, PANEL = SymCfg<G>::PANEL, STAGE = SymCfg<G>::STAGE, STAGES = SymCfg<G>::STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kbeg = blockIdx.x * g.k_per_split;
   const int kend = min(g.K, kbeg + g.k_per_split);
   if (kend <= kbeg) return;
   const int ktiles = (kend - kbeg + SY_BK - 1) / SY_BK;
 
-  if (warp == SY_NW) {
+  if (warp == NCONS) {
     // ------------------------------------------------------------------ producer warp
     const double* srcA;
     const double* srcB;
@@ -157,15 +213,15 @@ __global__ void __launch_bounds__(SY_NT, 1) dgemm_sym_kernel(const SymArgs g) {
     }
     int kleft = kend - kbeg;
     auto issue = [&](int stage) {
-      double* base = smem + stage * SY_STAGE + dst;
+      double* base = smem + stage * STAGE + dst;
       if (KC) {
         const bool kok = kofs < kleft;
         const int r0 = lane >> 3;
 #pragma unroll 10
-        for (int r = 0; r < SY_MP / 4; ++r) {
+        for (int r = 0; r < GM / 4; ++r) {
           const bool v = kok && r * 4 + r0 < g.M;
           cp_async16(base + r * 4 * (SY_BK + 4), v ? srcA + (long)r * 4 * g.lda : g.A, v);
-          cp_async16(base + SY_PANEL + r * 4 * (SY_BK + 4), v ? srcB + (long)r * 4 * g.ldb : g.B, v);
+          cp_async16(base + PANEL + r * 4 * (SY_BK + 4), v ? srcB + (long)r * 4 * g.ldb : g.B, v);
         }
         srcA += SY_BK;
         srcB += SY_BK;
@@ -176,10 +232,10 @@ __global__ void __launch_bounds__(SY_NT, 1) dgemm_sym_kernel(const SymArgs g) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int m = (q * 32 + lane) * 2;
-            if (m < SY_MP) {
+            if (m < GM) {
               const bool v = kok && m < g.M;
-              cp_async16(base + kk * (SY_MP + 4) + q * 64, v ? srcA + (long)kk * g.lda + q * 64 : g.A, v);
-              cp_async16(base + SY_PANEL + kk * (SY_MP + 4) + q * 64, v ? srcB + (long)kk * g.ldb + q * 64 : g.B, v);
+              cp_async16(base + kk * LDN + q * 64, v ? srcA + (long)kk * g.lda + q * 64 : g.A, v);
+              cp_async16(base + PANEL + kk * LDN + q * 64, v ? srcB + (long)kk * g.ldb + q * 64 : g.B, v);
             }
           }
         }
@@ -189,19 +245,19 @@ __global__ void __launch_bounds__(SY_NT, 1) dgemm_sym_kernel(const SymArgs g) {
       kleft -= SY_BK;
     };
 #pragma unroll
-    for (int s0 = 0; s0 < SY_STAGES - 1; ++s0) {
+    for (int s0 = 0; s0 < STAGES - 1; ++s0) {
       if (s0 < ktiles) issue(s0);
       cp_async_commit();
     }
     int stage = 0;
     for (int kt = 0; kt < ktiles; ++kt) {
-      cp_async_wait<SY_STAGES - 2>();
+      cp_async_wait<STAGES - 2>();
       __syncthreads();
-      int st2 = stage + SY_STAGES - 1;
-      if (st2 >= SY_STAGES) st2 -= SY_STAGES;
-      if (kt + SY_STAGES - 1 < ktiles) issue(st2);
+      int st2 = stage + STAGES - 1;
+      if (st2 >= STAGES) st2 -= STAGES;
+      if (kt + STAGES - 1 < ktiles) issue(st2);
       cp_async_commit();
-      if (++stage == SY_STAGES) stage = 0;
+      if (++stage == STAGES) stage = 0;
     }
     cp_async_wait<0>();
     return;
@@ -211,14 +267,24 @@ __global__ void __launch_bounds__(SY_NT, 1) dgemm_sym_kernel(const SymArgs g) {
   // Block of this warp.  The five diagonal blocks only need their lower 15 of 25 DMMA tiles; blocks are dealt to
   // warps so that every SM sub-partition (warp % 4) carries about the same number of DMMAs per k-step:
   // {F,F,D,D} = 80, {F,F,D,D} = 80, {F,F,F,D} = 90, {F,F,F + producer} = 75   (F = 25, D = 15).
-  const int blk = (int)((0xE92DA50C863B741ull >> (4 * warp)) & 15);   // warp -> block {1,4,7,11,3,6,8,12,0,5,10,13,2,9,14}
+  const int blk = (G == SY_G && KSUB == 1)
+                      ? (int)((0xE92DA50C863B741ull >> (4 * warp)) & 15)   // warp -> block {1,4,7,11,3,6,8,12,0,5,10,13,2,9,14}
+                      : warp / KSUB;
+  const int sub = KSUB > 1 ? warp % KSUB : 0;
   const int gi = blk >= 10 ? 4 : blk >= 6 ? 3 : blk >= 3 ? 2 : blk >= 1 ? 1 : 0;
   const int gj = blk - gi * (gi + 1) / 2;
-  if (gi == gj) sym_consume<KC, true>(g, smem, ktiles, gi, gj, lane);
-  else sym_consume<KC, false>(g, smem, ktiles, gi, gj, lane);
+  if (gi == gj) sym_consume<KC, true, G, KSUB, NCONS>(g, smem, ktiles, gi, gj, lane, sub, blk);
+  else sym_consume<KC, false, G, KSUB, NCONS>(g, smem, ktiles, gi, gj, lane, sub, blk);
 }
 
-inline bool dgemm_sym_supported(int M) { return M > 160 && M <= SY_MP && (M % 8) == 0; }
+inline bool dgemm_sym_supported(int M) { return M >= 8 && M <= SY_MP && (M % 8) == 0; }
+
+// warp-block rows the launch for order M uses, and the DMMA flops it executes per unit of K
+inline int dgemm_sym_rows(int M) { return (M + SY_BLK - 1) / SY_BLK; }
+inline double dgemm_sym_cells(int M) {
+  const int G = dgemm_sym_rows(M);
+  return G * (G - 1) / 2 * (double)(SY_BLK * SY_BLK) + G * 15.0 * 64;   // full blocks + diagonal blocks (15 of 25 tiles)
+}
 
 // Number of K-slices a launch with this K uses (<= SY_MAX_SPLITS).
 inline int dgemm_sym_splits(int K, int* k_per_split = nullptr) {
@@ -237,14 +303,29 @@ inline cudaError_t dgemm_sym(cudaStream_t st, bool kc, int M, int K, const doubl
   g.A = A; g.B = B; g.C = C; g.M = M; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
   g.c_split_stride = c_split_stride; g.accumulate = accumulate;
   const int splits = dgemm_sym_splits(K, &g.k_per_split);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute((const void*)dgemm_sym_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES);
-    cudaFuncSetAttribute((const void*)dgemm_sym_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES);
-    attr_done = true;
+  const int G = dgemm_sym_rows(M);
+#define CG_SYM_LAUNCH(GG, KS)                                                                                      \
+  do {                                                                                                             \
+    static bool attr_done = false;                                                                                 \
+    if (!attr_done) {                                                                                              \
+      cudaFuncSetAttribute((const void*)dgemm_sym_kernel<true, GG, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           SymCfg<GG>::SMEM_BYTES);                                                                \
+      cudaFuncSetAttribute((const void*)dgemm_sym_kernel<false, GG, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           SymCfg<GG>::SMEM_BYTES);                                                                \
+      attr_done = true;                                                                                            \
+    }                                                                                                              \
+    constexpr int NT = (GG * (GG + 1) / 2 * KS + 1) * 32;                                                          \
+    if (kc) dgemm_sym_kernel<true, GG, KS><<<splits, NT, SymCfg<GG>::SMEM_BYTES, st>>>(g);                         \
+    else dgemm_sym_kernel<false, GG, KS><<<splits, NT, SymCfg<GG>::SMEM_BYTES, st>>>(g);                           \
+  } while (0)
+  switch (G) {
+    case 1: CG_SYM_LAUNCH(1, 4); break;
+    case 2: CG_SYM_LAUNCH(2, 4); break;
+    case 3: CG_SYM_LAUNCH(3, 2); break;
+    case 4: CG_SYM_LAUNCH(4, 1); break;
+    default: CG_SYM_LAUNCH(5, 1); break;
   }
-  if (kc) dgemm_sym_kernel<true><<<splits, SY_NT, SY_SMEM_BYTES, st>>>(g);
-  else dgemm_sym_kernel<false><<<splits, SY_NT, SY_SMEM_BYTES, st>>>(g);
+#undef CG_SYM_LAUNCH
   return cudaGetLastError();
 }
 
