@@ -40,9 +40,9 @@ constexpr int SY_MAX_SPLITS = 148;
 
 // Per-order staging: G warp-block rows stage GM = 40 G panel rows; smaller panels get a deeper pipeline so that the
 // bytes in flight per SM stay ~100 KB (the low-order contractions are close to HBM-bound: 6 flop / byte at M = 96).
-template <int G>
+template <int G, int TB = 5>
 struct SymCfg {
-  static constexpr int GM = G * SY_BLK;
+  static constexpr int GM = G * TB * 8;
   static constexpr int LDN = GM + 4;                     // row stride of the m-contiguous layout, == 4 (mod 8)
   static constexpr int PANEL = GM * (SY_BK + 4);         // doubles (>= SY_BK * LDN)
   static constexpr int STAGE = 2 * PANEL;
@@ -62,20 +62,23 @@ struct SymArgs {
 };
 
 // One consumer warp: block (gi, gj) of the lower triangle.  DIAG: gi == gj, only the DMMA tiles i >= j are computed.
-template <bool KC, bool DIAG, int G, int KSUB, int NCONS>
+template <bool KC, bool DIAG, int G, int KSUB, int NCONS, int TB>
 __device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int ktiles, int gi, int gj, int lane,
                                             int sub, int blk) {
   constexpr int STEPS = (SY_BK / 4) / KSUB;      // k4 steps of a k-tile taken by this warp
-  constexpr int LDN = SymCfg<G>::LDN, PANEL = SymCfg<G>::PANEL, STAGE = SymCfg<G>::STAGE, STAGES = SymCfg<G>::STAGES;
+  using Cfg = SymCfg<G, TB>;
+  constexpr int LDN = Cfg::LDN, PANEL = Cfg::PANEL, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES;
+  constexpr int BLK = TB * 8;                    // rows / columns of a warp block
+  constexpr int RED = TB * TB * 64;              // doubles of one warp's accumulators
   const int grp = lane >> 2, tig = lane & 3;
-  const int a_off = KC ? (gi * SY_BLK + grp) * (SY_BK + 4) + tig : tig * LDN + gi * SY_BLK + grp;
-  const int b_off = PANEL + (KC ? (gj * SY_BLK + grp) * (SY_BK + 4) + tig : tig * LDN + gj * SY_BLK + grp);
+  const int a_off = KC ? (gi * BLK + grp) * (SY_BK + 4) + tig : tig * LDN + gi * BLK + grp;
+  const int b_off = PANEL + (KC ? (gj * BLK + grp) * (SY_BK + 4) + tig : tig * LDN + gj * BLK + grp);
 
-  double acc[5][5][2];
+  double acc[TB][TB][2];
 #pragma unroll
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < TB; ++i)
 #pragma unroll
-    for (int j = 0; j < 5; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < TB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // Fragments are single-buffered (25 accumulator pairs leave no room for a second set).  The 5 x 5 DMMA block
   // is walked row-major on even k4 steps and column-major on odd ones, and every fragment of the next step is
@@ -90,31 +93,31 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int 
     __syncthreads();
     const double* Ap = smem + stage * STAGE + a_off;
     const double* Bp = smem + stage * STAGE + b_off;
-    double fa[5], fb[5];
+    double fa[TB], fb[TB];
     const int k40 = KSUB > 1 ? sub * STEPS : 0;
 #pragma unroll
-    for (int x = 0; x < 5; ++x) { fa[x] = ldf(Ap, k40, x); fb[x] = ldf(Bp, k40, x); }
+    for (int x = 0; x < TB; ++x) { fa[x] = ldf(Ap, k40, x); fb[x] = ldf(Bp, k40, x); }
 #pragma unroll
     for (int s4 = 0; s4 < STEPS; ++s4) {
       const int k4 = k40 + s4;
       const bool more = s4 + 1 < STEPS;
       if ((s4 & 1) == 0) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < TB; ++i) {
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
+          for (int j = 0; j < TB; ++j) {
             if (!DIAG || i >= j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-            if (more && i == 4) fb[j] = ldf(Bp, k4 + 1, j);
+            if (more && i == TB - 1) fb[j] = ldf(Bp, k4 + 1, j);
           }
           if (more) fa[i] = ldf(Ap, k4 + 1, i);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
+        for (int j = 0; j < TB; ++j) {
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
+          for (int i = 0; i < TB; ++i) {
             if (!DIAG || i >= j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-            if (more && j == 4) fa[i] = ldf(Ap, k4 + 1, i);
+            if (more && j == TB - 1) fa[i] = ldf(Ap, k4 + 1, i);
           }
           if (more) fb[j] = ldf(Bp, k4 + 1, j);
         }
@@ -127,40 +130,40 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int 
     // add the KSUB partial accumulators of this block in a fixed order (sub 1, 2, .. into sub 0) through the drained
     // pipeline buffers; named barrier 1 = the consumer warps only (the producer warp has left)
     asm volatile("bar.sync 1, %0;\n" ::"n"(NCONS * 32) : "memory");
-    double* red = smem + (long)blk * (KSUB - 1) * 1600;
+    double* red = smem + (long)blk * (KSUB - 1) * RED;
     if (sub > 0) {
-      double* r = red + (sub - 1) * 1600 + lane;
+      double* r = red + (sub - 1) * RED + lane;
 #pragma unroll
-      for (int i = 0; i < 5; ++i)
+      for (int i = 0; i < TB; ++i)
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          r[(i * 5 + j) * 64] = acc[i][j][0];
-          r[(i * 5 + j) * 64 + 32] = acc[i][j][1];
+        for (int j = 0; j < TB; ++j) {
+          r[(i * TB + j) * 64] = acc[i][j][0];
+          r[(i * TB + j) * 64 + 32] = acc[i][j][1];
         }
     }
     asm volatile("bar.sync 1, %0;\n" ::"n"(NCONS * 32) : "memory");
     if (sub > 0) return;
 #pragma unroll
     for (int q = 0; q < KSUB - 1; ++q) {
-      const double* r = red + q * 1600 + lane;
+      const double* r = red + q * RED + lane;
 #pragma unroll
-      for (int i = 0; i < 5; ++i)
+      for (int i = 0; i < TB; ++i)
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          acc[i][j][0] += r[(i * 5 + j) * 64];
-          acc[i][j][1] += r[(i * 5 + j) * 64 + 32];
+        for (int j = 0; j < TB; ++j) {
+          acc[i][j][0] += r[(i * TB + j) * 64];
+          acc[i][j][1] += r[(i * TB + j) * 64 + 32];
         }
     }
   }
 
   double* C = g.C + (long)blockIdx.x * g.c_split_stride;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int row = gi * SY_BLK + i * 8 + grp;
+  for (int i = 0; i < TB; ++i) {
+    const int row = gi * BLK + i * 8 + grp;
     if (row >= g.M) continue;
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const int col = gj * SY_BLK + j * 8 + tig * 2;
+    for (int j = 0; j < TB; ++j) {
+      const int col = gj * BLK + j * 8 + tig * 2;
       if (col >= g.M || (DIAG && j > i)) continue;
       double2* p = reinterpret_cast<double2*>(C + (long)row * g.ldc + col);
       double v0 = acc[i][j][0], v1 = acc[i][j][1];
@@ -181,13 +184,14 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int 
 // no loader state, so they fit the 128-register budget of a 512-thread CTA); warp 15 is the producer and
 // issues every cp.async of both panels.  One __syncthreads per k-tile hands a filled stage to the consumers
 // and a drained one back to the producer.
-template <bool KC, int G = SY_G, int KSUB = 1>
+template <bool KC, int G = SY_G, int KSUB = 1, int TB = 5>
 __global__ void __launch_bounds__((G * (G + 1) / 2 * KSUB + 1) * 32, 1) dgemm_sym_kernel(const SymArgs g) {
   extern __shared__ __align__(16) double smem[];
   constexpr int NB = G * (G + 1) / 2;          // warp blocks of the lower triangle
   constexpr int NCONS = NB * KSUB;             // consumer warps; warp NCONS is the producer
-  constexpr int GM = SymCfg<G>::GM;            // panel rows this instantiation stages
-  constexpr int LDN = SymCfg<G>::LDN, PANEL = SymCfg<G>::PANEL, STAGE = SymCfg<G>::STAGE, STAGES = SymCfg<G>::STAGES;
+  using Cfg = SymCfg<G, TB>;
+  constexpr int GM = Cfg::GM;                  // panel rows this instantiation stages
+  constexpr int LDN = Cfg::LDN, PANEL = Cfg::PANEL, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kbeg = blockIdx.x * g.k_per_split;
   const int kend = min(g.K, kbeg + g.k_per_split);
@@ -267,23 +271,32 @@ __global__ void __launch_bounds__((G * (G + 1) / 2 * KSUB + 1) * 32, 1) dgemm_sy
   // Block of this warp.  The five diagonal blocks only need their lower 15 of 25 DMMA tiles; blocks are dealt to
   // warps so that every SM sub-partition (warp % 4) carries about the same number of DMMAs per k-step:
   // {F,F,D,D} = 80, {F,F,D,D} = 80, {F,F,F,D} = 90, {F,F,F + producer} = 75   (F = 25, D = 15).
-  const int blk = (G == SY_G && KSUB == 1)
+  const int blk = (G == SY_G && KSUB == 1 && TB == 5)
                       ? (int)((0xE92DA50C863B741ull >> (4 * warp)) & 15)   // warp -> block {1,4,7,11,3,6,8,12,0,5,10,13,2,9,14}
                       : warp / KSUB;
   const int sub = KSUB > 1 ? warp % KSUB : 0;
   const int gi = blk >= 10 ? 4 : blk >= 6 ? 3 : blk >= 3 ? 2 : blk >= 1 ? 1 : 0;
   const int gj = blk - gi * (gi + 1) / 2;
-  if (gi == gj) sym_consume<KC, true, G, KSUB, NCONS>(g, smem, ktiles, gi, gj, lane, sub, blk);
-  else sym_consume<KC, false, G, KSUB, NCONS>(g, smem, ktiles, gi, gj, lane, sub, blk);
+  if (gi == gj) sym_consume<KC, true, G, KSUB, NCONS, TB>(g, smem, ktiles, gi, gj, lane, sub, blk);
+  else sym_consume<KC, false, G, KSUB, NCONS, TB>(g, smem, ktiles, gi, gj, lane, sub, blk);
 }
 
 inline bool dgemm_sym_supported(int M) { return M >= 8 && M <= SY_MP && (M % 8) == 0; }
 
-// warp-block rows the launch for order M uses, and the DMMA flops it executes per unit of K
-inline int dgemm_sym_rows(int M) { return (M + SY_BLK - 1) / SY_BLK; }
+// Warp blocks are TB x TB DMMA tiles (TB = 5: 40 rows, TB = 4: 32 rows), G <= 5 block rows; the launch for order M
+// uses the pair that executes the fewest DMMA cells (ties: the larger block, fewer fragment loads per DMMA).
+inline double dgemm_sym_cells_of(int G, int TB) {
+  return G * (G - 1) / 2 * (double)(64 * TB * TB) + G * (TB * (TB + 1) / 2) * 64.0;   // full + diagonal blocks
+}
+inline void dgemm_sym_pick(int M, int* G, int* TB) {
+  const int g5 = (M + 39) / 40, g4 = (M + 31) / 32;
+  if (g4 <= SY_G && dgemm_sym_cells_of(g4, 4) < dgemm_sym_cells_of(g5, 5)) { *G = g4; *TB = 4; }
+  else { *G = g5; *TB = 5; }
+}
 inline double dgemm_sym_cells(int M) {
-  const int G = dgemm_sym_rows(M);
-  return G * (G - 1) / 2 * (double)(SY_BLK * SY_BLK) + G * 15.0 * 64;   // full blocks + diagonal blocks (15 of 25 tiles)
+  int G, TB;
+  dgemm_sym_pick(M, &G, &TB);
+  return dgemm_sym_cells_of(G, TB);
 }
 
 // Number of K-slices a launch with this K uses (<= SY_MAX_SPLITS).
@@ -303,27 +316,33 @@ inline cudaError_t dgemm_sym(cudaStream_t st, bool kc, int M, int K, const doubl
   g.A = A; g.B = B; g.C = C; g.M = M; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
   g.c_split_stride = c_split_stride; g.accumulate = accumulate;
   const int splits = dgemm_sym_splits(K, &g.k_per_split);
-  const int G = dgemm_sym_rows(M);
-#define CG_SYM_LAUNCH(GG, KS)                                                                                      \
+  int G, TB;
+  dgemm_sym_pick(M, &G, &TB);
+#define CG_SYM_LAUNCH(GG, KS, TT)                                                                                      \
   do {                                                                                                             \
     static bool attr_done = false;                                                                                 \
     if (!attr_done) {                                                                                              \
-      cudaFuncSetAttribute((const void*)dgemm_sym_kernel<true, GG, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           SymCfg<GG>::SMEM_BYTES);                                                                \
-      cudaFuncSetAttribute((const void*)dgemm_sym_kernel<false, GG, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           SymCfg<GG>::SMEM_BYTES);                                                                \
+      cudaFuncSetAttribute((const void*)dgemm_sym_kernel<true, GG, KS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           SymCfg<GG, TT>::SMEM_BYTES);                                                                \
+      cudaFuncSetAttribute((const void*)dgemm_sym_kernel<false, GG, KS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           SymCfg<GG, TT>::SMEM_BYTES);                                                                \
       attr_done = true;                                                                                            \
     }                                                                                                              \
     constexpr int NT = (GG * (GG + 1) / 2 * KS + 1) * 32;                                                          \
-    if (kc) dgemm_sym_kernel<true, GG, KS><<<splits, NT, SymCfg<GG>::SMEM_BYTES, st>>>(g);                         \
-    else dgemm_sym_kernel<false, GG, KS><<<splits, NT, SymCfg<GG>::SMEM_BYTES, st>>>(g);                           \
+    if (kc) dgemm_sym_kernel<true, GG, KS, TT><<<splits, NT, SymCfg<GG, TT>::SMEM_BYTES, st>>>(g);                         \
+    else dgemm_sym_kernel<false, GG, KS, TT><<<splits, NT, SymCfg<GG, TT>::SMEM_BYTES, st>>>(g);                           \
   } while (0)
-  switch (G) {
-    case 1: CG_SYM_LAUNCH(1, 4); break;
-    case 2: CG_SYM_LAUNCH(2, 4); break;
-    case 3: CG_SYM_LAUNCH(3, 2); break;
-    case 4: CG_SYM_LAUNCH(4, 1); break;
-    default: CG_SYM_LAUNCH(5, 1); break;
+  switch (G * 10 + TB) {
+    case 15: CG_SYM_LAUNCH(1, 4, 5); break;
+    case 25: CG_SYM_LAUNCH(2, 4, 5); break;
+    case 35: CG_SYM_LAUNCH(3, 2, 5); break;
+    case 45: CG_SYM_LAUNCH(4, 1, 5); break;
+    case 14: CG_SYM_LAUNCH(1, 4, 4); break;
+    case 24: CG_SYM_LAUNCH(2, 4, 4); break;
+    case 34: CG_SYM_LAUNCH(3, 2, 4); break;
+    case 44: CG_SYM_LAUNCH(4, 1, 4); break;
+    case 54: CG_SYM_LAUNCH(5, 1, 4); break;
+    default: CG_SYM_LAUNCH(5, 1, 5); break;
   }
 #undef CG_SYM_LAUNCH
   return cudaGetLastError();

@@ -124,7 +124,7 @@ def test_dgemm_small_left(b_kc, M, K, N):
 @pytest.mark.parametrize('M,K', [(200, 4096), (200, 50), (168, 1234), (184, 16 * 148 * 3 + 6),
                                  # windows: 4 / 3 / 2 / 1 warp-block rows, the last three with k-sub-sliced warps
                                  (160, 2000), (136, 778), (96, 16 * 148 * 2 + 10), (120, 64), (80, 5000), (48, 334),
-                                 (40, 16 * 200), (8, 100)])
+                                 (40, 16 * 200), (8, 100), (64, 1000), (128, 1500), (32, 640), (104, 900), (152, 320)])
 def test_dgemm_sym(kc, M, K):
     """Symmetric-output split-K DMMA kernel (dgemm_sym.cuh): C = X S X^T with S symmetric, computed as A B^T with
     A = X, B = X S, against numpy; ragged K, orders below the 200-row panel, both operand layouts."""
