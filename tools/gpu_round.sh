@@ -5,7 +5,7 @@
 #   steps    one evaluation at the bench shape: dense, culled, frozen (tools/profile_step.py)
 #   bench    bench.py (ours + reference arm)
 #   launches ncu launch lists of one dense and one culled evaluation
-#   ncu-sl / ncu-sym / ncu-axx   ncu --set full of the named kernel inside one dense evaluation
+#   ncu-sl / ncu-sym / ncu-axx   ncu --set full of the named kernel inside one evaluation (CULL=746 exact-zero windows by default, NCAP launches)
 TAG=${1:-run}; shift
 STEPS=${@:-tests gemm steps}
 O=gpurun_out/$TAG
@@ -28,7 +28,7 @@ for S in $STEPS; do
     ncu-sl|ncu-sym|ncu-axx)
            K=${S#ncu-}; R=dgemm_sl; [ $K = sym ] && R=dgemm_sym; [ $K = axx ] && R=axx_sum
            SK=6; [ $K = axx ] && SK=0
-           timeout 600 python tools/profile_step.py --cull 0 > $O/ps_dense.log 2>&1 && \
-           timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$R -s $SK -c 3 -o $O/${K}_prof python tools/profile_step.py --cull 0 > $O/ncu_$K.log 2>&1; tail -2 $O/ncu_$K.log;;
+           timeout 600 python tools/profile_step.py --cull ${CULL:-746} > $O/ps_step.log 2>&1 && \
+           timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$R -s $SK -c ${NCAP:-3} -o $O/${K}_prof python tools/profile_step.py --cull ${CULL:-746} > $O/ncu_$K.log 2>&1; tail -2 $O/ncu_$K.log;;
   esac
 done
