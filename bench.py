@@ -167,7 +167,7 @@ def fp64_peak():
 def run_ours(args):
     import torch
     import cgpcm_b200
-    from cgpcm_b200.cgpcm import shard_bounds
+    from cgpcm_b200.cgpcm import shard_bounds, window_costs, window_radius
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -182,7 +182,9 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     wl = sweep_workload(args.n, args.m)
-    lo, hi = shard_bounds(args.n, rank, world)
+    # shards of equal estimated cost (observations near the ends of the series have narrower windows)
+    cost = window_costs(wl['t'], wl['tx'], args.m, window_radius(*wl['hyp'], args.cull)) if world > 1 else None
+    lo, hi = shard_bounds(args.n, rank, world, cost)
     eng = cgpcm_b200.Engine(args.m, args.m, causal=True, device=local_rank)
     if world > 1:
         box = [cgpcm_b200.Engine.unique_id() if rank == 0 else None]

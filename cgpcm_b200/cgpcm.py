@@ -228,11 +228,50 @@ class CGPCM(object):
                    noise_init=noise_init, tx_range=tx_range)
 
 
-def shard_bounds(n, rank, world):
-    """Contiguous slice ``[lo, hi)`` of ``n`` observations owned by ``rank`` (sizes differ by <= 1)."""
+def shard_bounds(n, rank, world, cost=None):
+    """Contiguous slice ``[lo, hi)`` of ``n`` observations owned by ``rank``.  Without ``cost`` the sizes differ by
+    <= 1; with ``cost`` (``n`` non-negative per-observation costs, see ``window_costs``) the slices carry equal shares
+    of the total cost: observations near the ends of a series see fewer inducing inputs of the noise process inside
+    their window and are cheaper, so equal counts would leave the inner ranks with ~35 % more work."""
+    if cost is not None and world > 1 and n >= world:
+        cum = np.cumsum(np.asarray(cost, dtype=np.float64))
+        if cum.shape[0] != n:
+            raise ValueError('cost must have one entry per observation')
+        if cum[-1] > 0:
+            cuts = [0]
+            for r in range(1, world):
+                c = int(np.searchsorted(cum, cum[-1] * r / world))
+                cuts.append(min(max(c, cuts[-1] + 1), n - (world - r)))      # every rank keeps >= 1 observation
+            cuts.append(n)
+            return cuts[rank], cuts[rank + 1]
     base, extra = divmod(n, world)
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+def window_radius(alpha, gamma, omega, cull):
+    """``|t - tx|`` beyond which every ``Ahx`` element has a Gaussian envelope below ``exp(-cull)``: the radius
+    ``plan_chunks`` (csrc/cgpcm.cu) gives the windows of inducing inputs (``cull = 746``: exactly 0 in IEEE double)."""
+    A = alpha + gamma + omega
+    e_hh = ((alpha + gamma) * A - gamma * gamma) / A
+    e_dd = omega * (alpha + gamma) / A
+    e_hd = 2.0 * gamma * omega / A
+    lam = e_dd - e_hd * e_hd / (4.0 * e_hh)
+    return float(np.sqrt(cull / lam)) if (cull > 0 and lam > 0) else float('inf')
+
+
+def window_costs(t, tx, nh, radius):
+    """Per-observation cost proxy for ``shard_bounds``: with ``kw`` inducing inputs of the noise process inside the
+    window of observation ``n``, the contractions cost ``nh kw (4 nh + 7 kw)`` flop (T1, Q, Hbar: ``nh^2 kw``-type;
+    right-multiplies and C1: ``nh kw^2``-type), the Ahx kernels ``~ nh kw`` and the Axx kernel ``~ kw^2`` elements
+    (weights from the bench shape's per-kernel times, profiles/r01_launches_exact746_N1e5_M200.csv)."""
+    t = np.asarray(t, dtype=np.float64)
+    txs = np.sort(np.asarray(tx, dtype=np.float64))
+    if not np.isfinite(radius):
+        return np.ones(t.shape[0])
+    kw = (np.searchsorted(txs, t + radius, side='right') - np.searchsorted(txs, t - radius, side='left')).astype(np.float64)
+    kw = np.maximum(kw, 8.0)
+    return nh * kw * (4.0 * nh + 7.0 * kw + 430.0) + 480.0 * kw * kw
 
 
 class VCGPCM(CGPCM):
@@ -253,7 +292,12 @@ class VCGPCM(CGPCM):
         rank, world = getattr(sess, 'rank', 0), getattr(sess, 'world', 1)
         if world > 1:
             self._init_comm(rank, world)
-        lo, hi = shard_bounds(self.n, rank, world)
+        cost = None
+        if world > 1:
+            # balance the shards at the recipe's hyper-parameters and the library's default cull (80)
+            cost = window_costs(self.e.x, self.tx, self.nh,
+                                window_radius(self.alpha.eval(), self.gamma.eval(), self.omega.eval(), 80.0))
+        lo, hi = shard_bounds(self.n, rank, world, cost)
         self.engine.set_data(self.e.x[lo:hi], self.e.y[lo:hi], self.th, self.tx)
         self._init_inducing_points()
         self._cache = None

@@ -335,9 +335,9 @@ inline void L(cgpcm_handle* h, int n = 1) { h->launches += n; }
 
 // out[0] = sum_{r<rows, c<cols} A[r][c] * B[r][c]
 void frob(cgpcm_handle* h, const double* A, const double* B, int rows, int cols, double* out) {
-  long ld = h->ld;
+  const int ld = (int)h->ld;
   reduce_to(h->st, (long)rows * cols, [=] __device__(long idx) {
-    long r = idx / cols, c = idx % cols;
+    const int r = (int)idx / cols, c = (int)idx - r * cols;      // rows * cols < 2^31: 32-bit division
     return A[r * ld + c] * B[r * ld + c];
   }, out);
   L(h);
@@ -544,6 +544,13 @@ int axx_sweep(cgpcm_handle* h, const PsiConst& c, const BvnTab& T, bool tangents
   return 0;
 }
 
+// y-reduction slices (grid.y of ahx_gen_kernel) the chunks of a sweep touch: only these are zeroed and reduced
+int y_slices_used(const std::vector<Chunk>& chunks) {
+  int m = 1;
+  for (const Chunk& ch : chunks) m = std::max(m, (ch.nc + AHX_NSUB - 1) / AHX_NSUB);
+  return m;
+}
+
 int gen_chunk(cgpcm_handle* h, const PsiConst& c, const Chunk& ch, bool with_y, double* dstA = nullptr) {
   if (!dstA) dstA = h->wsA;
   const int threads = std::min(256, round_up(ch.kwp, 32));
@@ -625,7 +632,7 @@ int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& 
   if (full) {
     zero(h, h->M(M_Q), h->ld * h->ld);
     if (sym_begin(h, 1)) return -2;
-    zero(h, h->ypart, (long)h->y_slices * h->nhp * h->ld);
+    zero(h, h->ypart, (long)std::min(h->y_slices, y_slices_used(chunks)) * h->nhp * h->ld);
   }
   // with the sweep stores the Ahx block (and T1 when the backward sweep will need it) go straight to their
   // resident slots; the frozen regime's blocks do not change between evaluations and are generated once
@@ -654,7 +661,8 @@ int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& 
   if (full) {
     if (sym_finish(h, 1, h->nhp, h->M(M_Q))) return -2;
     long total = (long)h->nhp * h->ld;
-    ypart_reduce_kernel<<<148, 256, 0, h->st>>>(h->ypart, h->y_slices, total, total, h->M(M_Y));
+    ypart_reduce_kernel<<<148, 256, 0, h->st>>>(h->ypart, std::min(h->y_slices, y_slices_used(chunks)), total, total,
+                                                h->M(M_Y));
     L(h);
   }
   CK(cudaGetLastError());
@@ -1087,11 +1095,12 @@ int cgpcm_psi(cgpcm_handle* h, const double hyp[3], double* sum_Axx, double* Ahh
     // Y only: generate chunks with the fused y-reduction, no GEMMs
     std::vector<Chunk> chunks;
     plan_chunks(h, c, chunks);
-    zero(h, h->ypart, (long)h->y_slices * h->nhp * ld);
+    const int ys = std::min(h->y_slices, y_slices_used(chunks));
+    zero(h, h->ypart, (long)ys * h->nhp * ld);
     for (const Chunk& ch : chunks)
       if (gen_chunk(h, c, ch, true)) return -2;
     long total = (long)h->nhp * ld;
-    ypart_reduce_kernel<<<148, 256, 0, h->st>>>(h->ypart, h->y_slices, total, total, h->M(M_Y));
+    ypart_reduce_kernel<<<148, 256, 0, h->st>>>(h->ypart, ys, total, total, h->M(M_Y));
     L(h);
     if (allreduce(h, h->M(M_Y), ld * ld)) return -2;
     if (export_mat(h, h->M(M_Y), h->nh, h->nx, sum_Ahx_y)) return -2;
@@ -1481,12 +1490,12 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
         const double* kh0 = h->M(M_KH0);
         const double* thd = h->th;
         reduce_to(st, (long)nh * nh, [=] __device__(long idx) {
-          long i = idx / nh, j = idx % nh;
+          const int i = (int)idx / nh, j = (int)idx - i * nh;   // 32-bit division (nh * nh < 2^31)
           double ti = thd[i], tj = thd[j];
           return -khbar[i * ld + j] * (ti * ti + tj * tj) * kh0[i * ld + j];
         }, h->sc + S_G_KH_A);
         reduce_to(st, (long)nh * nh, [=] __device__(long idx) {
-          long i = idx / nh, j = idx % nh;
+          const int i = (int)idx / nh, j = (int)idx - i * nh;   // 32-bit division (nh * nh < 2^31)
           double d = thd[i] - thd[j];
           return -khbar[i * ld + j] * d * d * kh0[i * ld + j];
         }, h->sc + S_G_KH_G);
@@ -1502,7 +1511,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
         const double* kx0 = h->M(M_KX0);
         const double* txd = h->tx;
         reduce_to(st, (long)nx * nx, [=] __device__(long idx) {
-          long k = idx / nx, l = idx % nx;
+          const int k = (int)idx / nx, l = (int)idx - k * nx;
           double kxbar = t2[k * ld + l] + pbar[k * ld + l] + 0.5 * ikx[k * ld + l];
           double d = txd[k] - txd[l];
           return -kxbar * (0.5 / omega + 0.5 * d * d) * kx0[k * ld + l];
@@ -1516,11 +1525,11 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
         const double* da = h->M(M_DAHH_A);
         const double* dg = h->M(M_DAHH_G);
         reduce_to(st, (long)nh * nh, [=] __device__(long idx) {
-          long i = idx / nh, j = idx % nh;
+          const int i = (int)idx / nh, j = (int)idx - i * nh;   // 32-bit division (nh * nh < 2^31)
           return 0.5 * r * tl[0] * (ikh[i * ld + j] - m2[i * ld + j]) * da[i * ld + j];
         }, h->sc + S_G_AHH_A);
         reduce_to(st, (long)nh * nh, [=] __device__(long idx) {
-          long i = idx / nh, j = idx % nh;
+          const int i = (int)idx / nh, j = (int)idx - i * nh;   // 32-bit division (nh * nh < 2^31)
           return 0.5 * r * tl[0] * (ikh[i * ld + j] - m2[i * ld + j]) * dg[i * ld + j];
         }, h->sc + S_G_AHH_G);
         L(h, 2);
@@ -1532,7 +1541,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
         for (int k3 = 0; k3 < 3; ++k3) {
           const double* dm = h->M(M_AXX1 + k3);
           reduce_to(st, (long)nx * nx, [=] __device__(long idx) {
-            long k = idx / nx, l = idx % nx;
+            const int k = (int)idx / nx, l = (int)idx - k * nx;
             return r * (pbar[k * ld + l] + 0.5 * ikx[k * ld + l]) * dm[k * ld + l];
           }, h->sc + S_G_AXX_A + k3);
         }

@@ -129,6 +129,33 @@ def test_shard_bounds_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_bounds_by_cost():
+    """Cost-balanced shards: a partition, every rank non-empty, equal shares of the window-cost proxy; the proxy's
+    radius is the one plan_chunks uses (csrc/cgpcm.cu: ahx_radius)."""
+    rng = np.random.default_rng(0)
+    t = np.sort(rng.uniform(0, 100, 5000))
+    tx = np.linspace(0, 100, 200)
+    R = cg.window_radius(39.27, 1237.0, 1.5708, 746.0)
+    A = 39.27 + 1237.0 + 1.5708
+    lam = 1.5708 * (39.27 + 1237.0) / A - (2 * 1237.0 * 1.5708 / A) ** 2 / (4 * ((39.27 + 1237.0) * A - 1237.0 ** 2) / A)
+    assert R == pytest.approx(np.sqrt(746.0 / lam))
+    assert cg.window_radius(1., 1., 1., 0.0) == float('inf')
+    cost = cg.window_costs(t, tx, 200, R)
+    assert cost.shape == t.shape and cost[0] < cost[2500]            # the ends of the series are cheaper
+    for w in [2, 3, 8]:
+        b = [cg.shard_bounds(len(t), r, w, cost) for r in range(w)]
+        assert b[0][0] == 0 and b[-1][1] == len(t)
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        shares = np.array([cost[lo:hi].sum() for lo, hi in b])
+        assert shares.min() > 0 and shares.max() / shares.min() < 1.01
+    assert b[0][1] - b[0][0] > b[3][1] - b[3][0]                      # edge shards hold more observations
+    # degenerate costs fall back to equal counts; tiny n keeps every rank non-empty
+    assert cg.shard_bounds(10, 1, 2, np.zeros(10)) == (5, 10)
+    b = [cg.shard_bounds(3, r, 3, np.array([0., 0., 5.])) for r in range(3)]
+    assert b == [(0, 1), (1, 2), (2, 3)]
+    assert np.all(cg.window_costs(t, tx, 200, float('inf')) == 1.0)
+
+
 def test_tril_packing_matches_numpy_order():
     L = np.tril(np.arange(1., 17.).reshape(4, 4))
     v = util.tril_to_vec(L)
