@@ -21,7 +21,7 @@ GRAD_ALL = 0x7f
 MODE_FROZEN, MODE_FULL = 0, 1
 
 EXPORTS = ['cgpcm_create', 'cgpcm_destroy', 'cgpcm_last_error', 'cgpcm_comm_unique_id', 'cgpcm_comm_init',
-           'cgpcm_set_data', 'cgpcm_set_option', 'cgpcm_psi', 'cgpcm_precompute', 'cgpcm_elbo_grad', 'cgpcm_elbo_smf', 'cgpcm_predict_f', 'cgpcm_kernel_samples', 'cgpcm_filter_samples', 'cgpcm_fpi',
+           'cgpcm_set_data', 'cgpcm_set_option', 'cgpcm_psi', 'cgpcm_precompute', 'cgpcm_elbo_grad', 'cgpcm_elbo_smf', 'cgpcm_predict_f', 'cgpcm_kernel_samples', 'cgpcm_filter_samples', 'cgpcm_akm_sample', 'cgpcm_fpi',
            'cgpcm_last_timing', 'cgpcm_bvn_cdf', 'cgpcm_dgemm', 'cgpcm_dgemm_sym', 'cgpcm_cholinv']
 
 
@@ -79,6 +79,7 @@ def lib():
     L.cgpcm_predict_f.argtypes = [vp, dp, dbl, dp, i64, dp, ctypes.c_int32, ctypes.c_int32, dp, dp]
     L.cgpcm_kernel_samples.argtypes = [vp, dp, dbl, dp, i64, dp, ctypes.c_int32, dp]
     L.cgpcm_filter_samples.argtypes = [vp, dp, dbl, dp, i64, dp, ctypes.c_int32, dp, dp]
+    L.cgpcm_akm_sample.argtypes = [vp, dp, dbl, dp, i64, dp, dp, dp, dp]
     L.cgpcm_fpi.argtypes = [vp, dp, ctypes.c_int32, ctypes.c_int32, dbl, dp, dp, dp, dp]
     L.cgpcm_last_timing.argtypes = [vp, dp]
     L.cgpcm_bvn_cdf.argtypes = [dp, dp, dp, dp, ctypes.c_size_t, vp]

@@ -212,7 +212,9 @@ class CGPCM(object):
             omega = .5 * length_scale(dtx)
             tx = np.linspace(tx_range[0], tx_range[1], nx)
         else:
-            raise ValueError('nx must be positive')
+            # the AKM has no noise-side inducing inputs (src/core/cgpcm.py:77-79): omega = nan, tx = []
+            omega = np.nan
+            tx = np.zeros(0)
         omega = var_pos('omega', to_float(omega))
         if not causal and nh % 2 == 0:
             nh += 1
@@ -264,14 +266,103 @@ def window_costs(t, tx, nh, radius):
     """Per-observation cost proxy for ``shard_bounds``: with ``kw`` inducing inputs of the noise process inside the
     window of observation ``n``, the contractions cost ``nh kw (4 nh + 7 kw)`` flop (T1, Q, Hbar: ``nh^2 kw``-type;
     right-multiplies and C1: ``nh kw^2``-type), the Ahx kernels ``~ nh kw`` and the Axx kernel ``~ kw^2`` elements
-    (weights from the bench shape's per-kernel times, profiles/r01_launches_exact746_N1e5_M200.csv)."""
+    (weights from the bench shape's per-kernel times, profiles/r01_launches_exact746_N1e5_M200.csv), plus a
+    per-observation term for what does not shrink with the window."""
     t = np.asarray(t, dtype=np.float64)
     txs = np.sort(np.asarray(tx, dtype=np.float64))
     if not np.isfinite(radius):
         return np.ones(t.shape[0])
     kw = (np.searchsorted(txs, t + radius, side='right') - np.searchsorted(txs, t - radius, side='left')).astype(np.float64)
     kw = np.maximum(kw, 8.0)
-    return nh * kw * (4.0 * nh + 7.0 * kw + 430.0) + 480.0 * kw * kw
+    return nh * kw * (4.0 * nh + 7.0 * kw + 430.0) + 480.0 * kw * kw + 100.0 * nh * txs.shape[0]
+
+
+class AKM(CGPCM):
+    """Approximate Kernel Model (``src/core/cgpcm.py:295-422``): the generative model the toy experiment's series are
+    drawn from (``data.load_akm``).  Filter draw ``h ~ N(0, reg(iKh))`` in the reference's parametrisation, function
+    draw ``f = sqrt(s2_f) chol(reg(K)) e`` with ``K = a + tr((h h^T - iKh) Ahh)`` at all pairs of inputs
+    (``cgpcm_akm_sample``), kernel ``k`` at lags (``cgpcm_kernel_samples``)."""
+
+    _required_pars = ['sess', 'th', 's2', 's2_f', 'alpha', 'gamma', 'causal', 'causal_id']
+
+    def __init__(self, **kw_args):
+        CGPCM.__init__(self, **kw_args)
+        if self.causal_id:
+            raise NotImplementedError('causal_id=True is not on the accelerated path (no task enables it)')
+        self.th = np.ascontiguousarray(self.th, dtype=np.float64)
+        self.nh = self.th.shape[0]
+        # the engine wants a noise side: eight dummy inducing inputs and omega = 1, none of which the AKM's
+        # statistics (functions of th, alpha, gamma only) read
+        self.engine = Engine(self.nh, 8, causal=self.causal, causal_id=False, device=getattr(self.sess, 'device', 0))
+        self.engine.set_data(np.zeros(1), np.zeros(1), self.th, np.linspace(0., 1., 8))
+        self.h_draw = self.e_draw = self.t = None
+
+    def _pack5(self):
+        return np.array([float(self.vars['s2'].value), float(self.vars['s2_f'].value), float(self.vars['alpha'].value),
+                         float(self.vars['gamma'].value), 0.0])
+
+    def _prior_factor(self):
+        """Cholesky factor of ``reg(iKh)``, the covariance of ``h_prior`` (``cgpcm.py:216-220``)."""
+        r = config.reg
+        alpha, gamma, th = self.alpha.eval(), self.gamma.eval(), self.th
+        Kh = np.exp(-alpha * (th[:, None] ** 2 + th[None, :] ** 2) - gamma * (th[:, None] - th[None, :]) ** 2)
+        Lh = np.linalg.cholesky(Kh + r * np.eye(self.nh))
+        iLh = np.linalg.solve(Lh, np.eye(self.nh))
+        return np.linalg.cholesky(iLh.T @ iLh + r * np.eye(self.nh))
+
+    def sample_h(self, h=None):
+        """Sample filter (``cgpcm.py:353-362``); ``h``: a draw in the parametrisation of the filter."""
+        if h is None:
+            self.h_draw = self._prior_factor() @ np.random.randn(self.nh, 1)
+        else:
+            self.h_draw = np.asarray(h, dtype=np.float64).reshape(self.nh, 1)
+
+    def sample_f(self, t):
+        """Sample function (``cgpcm.py:364-371``)."""
+        self.t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
+        self.e_draw = np.random.randn(self.t.shape[0], 1)
+
+    def sample(self, t, h=None):
+        """Sample filter and function (``cgpcm.py:373-380``)."""
+        self.sample_h(h)
+        self.sample_f(t)
+
+    def f(self):
+        """Construct function (``cgpcm.py:382-392``)."""
+        from .data import Data
+        return Data(self.t, self.engine.akm_sample(self._pack5(), self.t, self.h_draw, self.e_draw, reg=config.reg))
+
+    def h(self, t):
+        """Construct filter (``cgpcm.py:394-408``): ``k_h(t, th) h``, positive times only for the causal model."""
+        from .data import Data
+        t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
+        alpha, gamma, th = self.alpha.eval(), self.gamma.eval(), self.th
+        Kfu = np.exp(-alpha * (t[:, None] ** 2 + th[None, :] ** 2) - gamma * (t[:, None] - th[None, :]) ** 2)
+        d = Data(t, (Kfu @ self.h_draw).ravel())
+        return d.positive_part() if self.causal else d
+
+    def k(self, t):
+        """Construct the kernel (``cgpcm.py:410-421``)."""
+        from .data import Data
+        t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
+        return Data(t, self.engine.kernel_samples(self._pack5(), t, self.h_draw.reshape(1, -1), reg=config.reg)[:, 0])
+
+    def k_prior(self, t, iters=1000, psd=False, granularity=1):
+        """Prior distribution over kernels or PSDs (``cgpcm.py:304-351``): mean, lists of lower and upper bounds."""
+        from .data import Data
+        from .util import fft_spectrum
+        t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
+        hs = (self._prior_factor() @ np.random.randn(self.nh, int(iters))).T
+        samples = self.engine.kernel_samples(self._pack5(), t, hs, reg=config.reg)                # [n, iters]
+        x = t
+        if psd:
+            x, spec = fft_spectrum(t, samples)
+            samples = np.abs(spec)
+        mu = samples.mean(axis=1)
+        qs = np.arange(granularity, 50 - granularity, granularity)
+        lowers = [Data(x, np.percentile(samples, q, axis=1)) for q in qs]
+        uppers = [Data(x, np.percentile(samples, 100 - q, axis=1)) for q in qs]
+        return Data(x, mu), lowers, uppers
 
 
 class VCGPCM(CGPCM):
@@ -279,6 +370,8 @@ class VCGPCM(CGPCM):
 
     def __init__(self, **kw_args):
         CGPCM.__init__(self, **kw_args)
+        if np.size(self.tx) == 0:
+            raise ValueError('nx must be positive')
         if self.causal_id:
             raise NotImplementedError('causal_id=True is not on the accelerated path (no task enables it)')
         self.th = np.ascontiguousarray(self.th, dtype=np.float64)

@@ -2117,6 +2117,80 @@ int filter_run(cgpcm_handle* h, const double* params_host, double reg, const dou
   return 0;
 }
 
+// One draw of the Approximate Kernel Model, AKM.f() (src/core/cgpcm.py:382-392):
+//   K[p][q] = a(t_p, t_q) + tr((h h^T - iKh) Ahh(t_p, t_q)),   f = sqrt(s2_f) chol(reg(K)) e.
+// The pair statistics _a / _Ahh (cgpcm.py:156-158,182-184: upper limit min(t, t')) only depend on the lag:
+// shifting tau by t' turns them into the centre statistics at t - t' (oracle.model.psi_pairs_generic checks this on
+// the reference's integrands), so K is kernel_run at the n^2 lags with s2_f divided out again.
+int akm_run(cgpcm_handle* h, const double* params_host, double reg, const double* t_host, long n,
+            const double* h_host, const double* e_host, double* f_out, double* K_out) {
+  for (long i = 0; i < n; ++i)
+    if (!std::isfinite(t_host[i]) || !std::isfinite(e_host[i])) { h->err = "non-finite input"; return -4; }
+  if (n > 4096) { h->err = "AKM sample: at most 4096 inputs"; return -1; }
+  const double s2f = exp(params_host[1]);
+  cudaStream_t st = h->st;
+  const int ldn = round_up((int)n, 8);
+  std::vector<double> lags((size_t)n * n);
+  for (long p2 = 0; p2 < n; ++p2)
+    for (long q = 0; q < n; ++q) lags[(size_t)p2 * n + q] = t_host[p2] - t_host[q];
+  double *d_k = nullptr, *d_K = nullptr, *d_e = nullptr, *d_f = nullptr;
+  auto cleanup = [&]() {
+    double* ps[] = {d_k, d_K, d_e, d_f};
+    for (double* q : ps) if (q) cudaFree(q);
+  };
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[256]; snprintf(b_, sizeof b_, \
+    "CUDA error %s in akm_sample (%s)", cudaGetErrorString(e_), #call); h->err = b_; cleanup(); return -2; } } while (0)
+  PCK(cudaMalloc(&d_k, (size_t)n * n * sizeof(double)));
+  PCK(cudaMalloc(&d_K, (size_t)ldn * ldn * sizeof(double)));
+  PCK(cudaMalloc(&d_e, (size_t)ldn * sizeof(double)));
+  PCK(cudaMalloc(&d_f, (size_t)ldn * sizeof(double)));
+  {
+    int rc = kernel_run(h, params_host, reg, lags.data(), n * n, h_host, 1, d_k);     // s2_f (a + tr(..)) per lag
+    if (rc) { cleanup(); return rc; }
+  }
+  PCK(cudaEventRecord(h->ev[0], st));
+  PCK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
+  PCK(cudaMemsetAsync(d_e, 0, (size_t)ldn * sizeof(double), st));
+  PCK(cudaMemcpyAsync(d_e, e_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  {
+    const double* kk = d_k;
+    double* Kp = d_K;
+    const long nn = n;
+    const double inv = 1.0 / s2f;
+    ew(st, (long)ldn * ldn, [=] __device__(long idx) {
+      const int r = (int)(idx / ldn), q = (int)(idx - (long)r * ldn);
+      double v = (r == q) ? 1.0 : 0.0;                       // identity on the padding block
+      if (r < nn && q < nn) v = kk[(long)r * nn + q] * inv + (r == q ? reg : 0.0);
+      Kp[idx] = v;
+    });
+    L(h);
+  }
+  if (K_out)
+    PCK(cudaMemcpy2DAsync(K_out, (size_t)n * sizeof(double), d_K, (size_t)ldn * sizeof(double), (size_t)n * sizeof(double),
+                          n, cudaMemcpyDefault, st));
+  {
+    cudaError_t e = potrf_lower(st, d_K, ldn, ldn, h->info, 6);
+    L(h, 2 * ((ldn + LA_NB - 1) / LA_NB));
+    if (e != cudaSuccess) { h->err = "potrf launch failed"; cleanup(); return -2; }
+  }
+  matvec_kernel<<<(ldn + 7) / 8, 256, 0, st>>>(d_K, ldn, ldn, ldn, 0, d_e, sqrt(s2f), d_f);
+  L(h);
+  PCK(cudaMemcpyAsync(f_out, d_f, (size_t)n * sizeof(double), cudaMemcpyDefault, st));
+  int info[4];
+  PCK(cudaMemcpyAsync(info, h->info, sizeof info, cudaMemcpyDeviceToHost, st));
+  PCK(cudaEventRecord(h->ev[6], st));
+  PCK(cudaStreamSynchronize(st));
+  PCK(cudaGetLastError());
+  cleanup();
+#undef PCK
+  if (info[0]) { h->err = "AKM covariance a + tr((h h^T - iKh) Ahh) + reg I is not positive definite"; return -3; }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+  h->timing[0] += ms;
+  h->timing[6] = (double)h->launches;
+  return 0;
+}
+
 }  // namespace cgimpl
 
 extern "C" {
@@ -2216,6 +2290,25 @@ int cgpcm_filter_samples(cgpcm_handle* h, const double* params, double reg, cons
   };
   if (fetch(t, ts) || fetch(samples, smp) || fetch(noise, ns)) return -2;
   return filter_run(h, host.data(), reg, ts.data(), n, smp.data(), n_samples, ns.data(), out);
+}
+
+int cgpcm_akm_sample(cgpcm_handle* h, const double* params, double reg, const double* t, int64_t n,
+                     const double* sample_h, const double* e, double* f, double* K) {
+  if (!h || !params || n < 1 || !t || !sample_h || !e || !f) return -1;
+  if (!h->th) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  if (!std::isfinite(reg) || reg < 0) { h->err = "reg must be finite and >= 0"; return -4; }
+  CK(cudaSetDevice(h->device));
+  std::vector<double> host, ts(n), hs(h->nh), es(n);
+  if (fetch_params(h, params, 5, host)) return -2;
+  auto fetch = [&](const double* src, std::vector<double>& dst) -> int {
+    if (is_device_ptr(src)) CK(cudaMemcpy(dst.data(), src, dst.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    else memcpy(dst.data(), src, dst.size() * sizeof(double));
+    return 0;
+  };
+  if (fetch(t, ts) || fetch(sample_h, hs) || fetch(e, es)) return -2;
+  for (double v : hs)
+    if (!std::isfinite(v)) { h->err = "non-finite sample"; return -4; }
+  return akm_run(h, host.data(), reg, ts.data(), n, hs.data(), es.data(), f, K);
 }
 
 int cgpcm_fpi(cgpcm_handle* h, const double* params, int32_t num, int32_t high_reg, double reg, double* mu_u,

@@ -158,6 +158,22 @@ class Engine(object):
                                                       int(samples.shape[0]), _lib.ptr(noise), _lib.ptr(out)))
         return out
 
+    def akm_sample(self, params, t, sample_h, e, reg=1e-8, want_cov=False):
+        """One draw ``f = sqrt(s2_f) chol(reg(K)) e`` of the Approximate Kernel Model at inputs ``t`` for the filter
+        draw ``sample_h`` [nh] and the standard normal draw ``e`` [n] (``AKM.f``, ``src/core/cgpcm.py:382-392``).
+        Returns ``f`` [n], and the covariance ``reg(K)`` [n, n] when ``want_cov``."""
+        t = np.ascontiguousarray(np.asarray(t, dtype=np.float64).ravel())
+        sample_h = np.ascontiguousarray(np.asarray(sample_h, dtype=np.float64).ravel())
+        e = np.ascontiguousarray(np.asarray(e, dtype=np.float64).ravel())
+        if sample_h.shape[0] != self.nh or e.shape[0] != t.shape[0]:
+            raise ValueError('sample_h must have nh entries and e one entry per input')
+        f = np.empty(t.shape[0])
+        K = np.empty((t.shape[0], t.shape[0])) if want_cov else None
+        self._ck(_lib.lib().cgpcm_akm_sample(self._h, _lib.ptr(np.ascontiguousarray(params[:5])), float(reg),
+                                              _lib.ptr(t), int(t.shape[0]), _lib.ptr(sample_h), _lib.ptr(e),
+                                              _lib.ptr(f), _lib.ptr(K) if want_cov else None))
+        return (f, K) if want_cov else f
+
     def fpi(self, params, num, high_reg=False, reg=1e-8):
         """``num`` rounds of the fixed-point iteration on the frozen Psi statistics, then the optimal q(z):
         ``(mu_u[nh], var_u[nh(nh+1)/2], mu_z[nx], var_z[nx(nx+1)/2])`` (``src/core/cgpcm.py:479-516,577-592``)."""

@@ -121,6 +121,14 @@ int cgpcm_kernel_samples(cgpcm_handle* h, const double* params, double reg, cons
 int cgpcm_filter_samples(cgpcm_handle* h, const double* params, double reg, const double* t, int64_t n,
                          const double* samples, int32_t n_samples, const double* noise, double* out);
 
+/* One draw of the Approximate Kernel Model, AKM.f() (src/core/cgpcm.py:295-422, f: 382-392; the sampler behind
+ * data.load_akm, src/core/data.py:594-641, i.e. the toy experiment's series): f = sqrt(s2_f) chol(reg(K)) e at inputs
+ * t[n] with K[p][q] = a(t_p, t_q) + tr((h h^T - iKh) Ahh(t_p, t_q)) (pair statistics _a / _Ahh, cgpcm.py:156-158,
+ * 182-184), for the filter draw sample_h[nh] and the standard normal draw e[n] (the reference draws both inside the
+ * graph).  f[n] and the optional K[n][n] (before the Cholesky, reg included) may be host or device.  n <= 4096. */
+int cgpcm_akm_sample(cgpcm_handle* h, const double* params, double reg, const double* t, int64_t n,
+                     const double* sample_h, const double* e, double* f, double* K);
+
 /* mod.fpi(num, z=True, high_reg) followed by mod.convert(z=True) (src/core/cgpcm.py:479-516,577-592): num rounds of
  * the fixed-point iteration q(u) -> optimal q(z) -> optimal q(u) on the Psi statistics frozen by cgpcm_precompute
  * (Normal.from_natural, src/core/distribution.py:20-33; high_reg adds 1e-4 to both precisions), starting from the
@@ -145,13 +153,13 @@ int cgpcm_bvn_cdf(const double* x1, const double* x2, const double* rho, double*
 
 /* Building blocks exported for tests and micro-benchmarks (device pointers only).
  * cgpcm_dgemm: C = alpha op(A) op(B) + beta C on the DMMA kernels; a_kc/b_kc/c_tr as in dgemm_dmma.cuh
- * (shapes with a small k-contiguous left operand, 104 < M <= 208, K <= 200, N >= 9472, go to dgemm_sl.cuh).
+ * (shapes with a small k-contiguous left operand, 16 <= M <= 208, 16 <= K <= 200, N >= 9472, go to dgemm_sl.cuh).
  * cgpcm_cholinv: A (n x n, ld) -> L in place, Ainv, logdet (each may be NULL). */
 int cgpcm_dgemm(int a_kc, int b_kc, int c_tr, int M, int N, int K, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int splits,
                 int64_t c_split_stride, int lower_only, void* stream);
 /* cgpcm_dgemm_sym: the symmetric-output split-K contraction of dgemm_sym.cuh, C = op(A) op(B)^T (M x M, full
- * symmetric matrix written; 160 < M <= 200, M % 8 == 0).  kc = 1: A[m*lda + k], B[n*ldb + k]; kc = 0: A[k*lda + m],
+ * symmetric matrix written; 8 <= M <= 200, M % 8 == 0).  kc = 1: A[m*lda + k], B[n*ldb + k]; kc = 0: A[k*lda + m],
  * B[k*ldb + n].  The result is only meaningful when the product is symmetric (the lower triangle is mirrored).
  * work: NULL or a device buffer of 148 * M * M doubles for the K-slice partial results. */
 int cgpcm_dgemm_sym(int kc, int M, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,

@@ -552,3 +552,40 @@ def filter_samples(params, th, r, t, samples_h, noise):
         H = T(np.asarray(samples_h, np.float64)).reshape(-1, nh).T          # [nh, B]
         out = Kuh.T @ H + L @ T(np.asarray(noise, np.float64))
     return out.numpy().copy()
+
+
+# ----------------------------------------------------------------------------- AKM sampler (third part)
+def psi_pairs_generic(t, th, alpha, gamma, causal=True):
+    """``_a(t)`` / ``_Ahh(t)`` at all pairs of inputs (``cgpcm.py:156-158,182-184``) through the restated
+    ``integrate_box`` on the reference's integrands: ``t1``, ``t2`` on axes 0, 1, upper limit ``min(t1, t2)`` (causal)
+    or ``inf``.  ``a`` [n,n], ``Ahh`` [n,n,nh,nh].  Small sizes only."""
+    t, th = T(t), T(th)
+    v = expq.var
+    tau1, t1, t2, th1, th2 = v('tau1'), v('t1'), v('t2'), v('th1'), v('th2')
+    kh = lambda x, y: expq.kh(alpha, gamma, x, y)
+    expq_a = kh(t1 - tau1, t2 - tau1)
+    expq_Ahh = kh(t1 - tau1, th1) * kh(th2, t2 - tau1)
+    n, nh = t.shape[0], th.shape[0]
+    vm = {'t1': t.reshape(-1, 1, 1, 1), 't2': t.reshape(1, -1, 1, 1), 'th1': th.reshape(1, 1, -1, 1),
+          'th2': th.reshape(1, 1, 1, -1)}
+    vm['min_t1_t2'] = torch.minimum(vm['t1'], vm['t2'])
+    up = v('min_t1_t2') if causal else expq.inf
+    a = torch.as_tensor(expq_a.integrate_box(('tau1', -expq.inf, up), **vm))
+    a = a.reshape(n, n) if a.numel() == n * n else a.reshape(-1)[0] * torch.ones(n, n, dtype=DT)
+    Ahh = torch.as_tensor(expq_Ahh.integrate_box(('tau1', -expq.inf, up), **vm))
+    return a, (Ahh * torch.ones(n, n, nh, nh, dtype=DT)).reshape(n, n, nh, nh)
+
+
+def akm_f(params, th, r, t, h, e, causal=True):
+    """``AKM.f()`` (``cgpcm.py:382-392``) on the pair statistics of ``psi_pairs_generic``:
+    ``K = reg(a + tr((h h^T - iKh) Ahh))``, ``f = sqrt(s2_f) chol(K) e``.  Returns ``(f, K)``."""
+    with torch.no_grad():
+        nh = len(th)
+        s2, s2_f, alpha, gamma, omega, _, _ = unpack(T(np.asarray(params, np.float64)), nh)
+        Kh = reg(deq(1., alpha, gamma, T(th)), r)
+        iKh = cholinv(torch.linalg.cholesky(Kh))
+        a, Ahh = psi_pairs_generic(t, th, alpha, gamma, causal)
+        hv = T(np.asarray(h, np.float64)).reshape(-1, 1)
+        K = reg(a + torch.sum((hv @ hv.T - iKh) * Ahh, (-1, -2)), r)
+        f = torch.sqrt(s2_f) * (torch.linalg.cholesky(K) @ T(np.asarray(e, np.float64)).reshape(-1, 1))
+    return f.reshape(-1).numpy().copy(), K.numpy().copy()

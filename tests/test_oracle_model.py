@@ -123,3 +123,25 @@ def test_center_statistics_closed_forms(causal):
     assert float((a1 - a2).abs().max()) < 1e-16 and float((A1 - A2).abs().max()) < 1e-15
     assert float(a2[2]) == pytest.approx(float(om.psi_a(om.T(alpha), causal)), rel=1e-15)
     np.testing.assert_allclose(A2[2].numpy(), om.psi_Ahh(th, om.T(alpha), om.T(gamma), causal).numpy(), rtol=1e-13, atol=1e-17)
+
+
+@pytest.mark.parametrize('causal', [True, False])
+def test_pair_statistics_depend_on_the_lag_only(causal):
+    """The AKM's pair statistics ``_a(t)`` / ``_Ahh(t)`` (src/core/cgpcm.py:156-158,182-184; upper limit min(t1, t2)),
+    integrated from the reference's integrands by the restated integrate_box, equal the centre statistics
+    (:164-166,190-192) at the lag ``t1 - t2``: what ``cgpcm_akm_sample`` relies on."""
+    t = np.array([0., .1, .35, .5, .72, .73])
+    th = np.linspace(-.05, .2, 7)
+    a, Ahh = om.psi_pairs_generic(t, th, 5., 30., causal)
+    lags = (t[:, None] - t[None, :]).ravel()
+    ac, Ahhc = om.psi_center_closed(lags, th, 5., 30., causal)
+    assert float(abs(a.reshape(-1) - ac).max()) <= 1e-14
+    assert float(abs(Ahh.reshape(-1, 7, 7) - Ahhc).max()) <= 1e-14
+    # and the covariance of AKM.f is symmetric positive definite
+    p = np.zeros(5 + 7 + 28)
+    p[:5] = np.log([.1, 1.3, 5., 30., 1.])
+    rng = np.random.default_rng(0)
+    f, K = om.akm_f(p, th, 1e-6, t, 3 * rng.standard_normal(7), rng.standard_normal(6), causal=causal)
+    # symmetric up to the rounding of tr(iKh Ahh), iKh ~ 1/reg
+    assert np.abs(K - K.T).max() <= 1e-8 * np.abs(K).max() and np.linalg.eigvalsh(.5 * (K + K.T)).min() > 0
+    assert f.shape == (6,) and np.all(np.isfinite(f))

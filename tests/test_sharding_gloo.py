@@ -101,4 +101,7 @@ def test_two_rank_reduction_and_bootstrap():
         assert (srank, sworld, r, w) == (rank, world, rank, world)
         assert uid == b'id-from-rank-0\0'        # every rank joined with rank 0's id
         assert n == 41
-    assert [x[7] for x in res] == [21, 20]       # contiguous shards, sizes differ by at most one
+    # contiguous shards of equal estimated cost (cgpcm.window_costs): a partition of the 41 observations, near-equal
+    # sizes here because the toy windows cover the whole series
+    sizes = [x[7] for x in res]
+    assert sum(sizes) == 41 and abs(sizes[0] - sizes[1]) <= 3 and min(sizes) >= 1
