@@ -156,6 +156,11 @@ struct cgpcm_handle {
   long storeA_elems = 0, storeT_elems = 0;
   bool use_store = false;      // decided per evaluation
   bool storeA_frozen_valid = false;   // storeA holds the frozen regime's Ahx blocks (constant between evaluations)
+  // prior kernels of the precomputed regime: Kh, Kx, their factors and inverses only depend on (alpha, gamma, omega,
+  // reg), which are constants between cgpcm_precompute and the next full-regime call -- MODE_FROZEN evaluations,
+  // fixed-point rounds, SMF samples and predictions reuse them instead of refactoring (2 x ~40 launches) every time
+  bool prior_valid = false;
+  double prior_key[4] = {0, 0, 0, 0};
   // fourth-order Psi tensor of the frozen regime (gram_kernels.cuh), option "gram": 0 off (default), 1 when it pays,
   // 2 whenever it fits.  Opt-in: the contraction with m2 ~ iKh cancels AFTER the sum over observations instead of
   // before it, which costs ~sqrt(N) in rounding noise (gram_kernels.cuh).
@@ -814,8 +819,12 @@ int allreduce(cgpcm_handle* h, double* buf, long count) {
 }
 
 // ---- M x M prologue: prior kernels, inverses (src/core/cgpcm.py:214-229) -----------------------------
-int prior_stage(cgpcm_handle* h, const PsiConst& c, double reg) {
+int prior_stage(cgpcm_handle* h, const PsiConst& c, double reg, bool reuse = false) {
   const long ld = h->ld;
+  if (reuse && h->prior_valid && h->prior_key[0] == c.alpha && h->prior_key[1] == c.gamma && h->prior_key[2] == c.omega &&
+      h->prior_key[3] == reg)
+    return 0;
+  h->prior_valid = false;
   // Kh0, Kh(+jitter) -> M_LH ; Kx0, Kx(+jitter) -> M_KX ; Ahh and tangents
   prior_kernels_kernel<<<148 * 2, 256, 0, h->st>>>(h->th, h->nh, ld, h->tx, h->nx, ld, reg, h->M(M_KH0), h->M(M_LH),
                                                     h->M(M_KX0), h->M(M_KX), h->M(M_AHH), h->M(M_DAHH_A),
@@ -824,6 +833,8 @@ int prior_stage(cgpcm_handle* h, const PsiConst& c, double reg) {
   CK(cudaMemcpyAsync(h->M(M_LX), h->M(M_KX), ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
   if (chol_inv(h, h->M(M_LH), h->M(M_IKH), h->nh, h->nhp, nullptr, 1)) return -2;
   if (chol_inv(h, h->M(M_LX), h->M(M_IKX), h->nx, h->nxp, h->sc + S_LOGDET_KX, 2)) return -2;
+  h->prior_key[0] = c.alpha; h->prior_key[1] = c.gamma; h->prior_key[2] = c.omega; h->prior_key[3] = reg;
+  h->prior_valid = true;      // withdrawn by the caller when the info word reports a failed factorisation
   return 0;
 }
 
@@ -995,6 +1006,7 @@ int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_
   h->frozen = false;
   h->storeA_frozen_valid = false;
   h->gram_valid = false;
+  h->prior_valid = false;
   const long na = std::max<long>(n_local, 1);
   CK(cudaMalloc(&h->t, na * sizeof(double)));
   CK(cudaMalloc(&h->y, na * sizeof(double)));
@@ -1076,6 +1088,7 @@ int cgpcm_psi(cgpcm_handle* h, const double hyp[3], double* sum_Axx, double* Ahh
   bvn_make_tab(hyp[1] / (hyp[0] + hyp[1] + hyp[2]), &T);
   CK(cudaEventRecord(h->ev[0], h->st));
   const long ld = h->ld;
+  h->prior_valid = false;      // the slots of the prior kernels are overwritten below (without jitter)
   prior_kernels_kernel<<<148 * 2, 256, 0, h->st>>>(h->th, h->nh, ld, h->tx, h->nx, ld, 0.0, h->M(M_KH0), h->M(M_LH),
                                                     h->M(M_KX0), h->M(M_KX), h->M(M_AHH), h->M(M_DAHH_A),
                                                     h->M(M_DAHH_G), c);
@@ -1185,8 +1198,8 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   CK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
   if (!freeze) CK(cudaMemcpyAsync(h->params_d, params_host, np * sizeof(double), cudaMemcpyHostToDevice, st));
 
-  // ---- 1. prologue
-  if (prior_stage(h, c, reg)) return -2;
+  // ---- 1. prologue (a full-regime evaluation always rebuilds the prior kernels; the precomputed regime reuses them)
+  if (prior_stage(h, c, reg, !full)) return -2;
   double* Hm = h->M(M_H);
   const double* ikh_cur = h->M(M_IKH);
   const double* tl = h->fwd_tail;               // device: [N (all ranks), sum y^2 (all ranks)]
@@ -1279,6 +1292,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
       L(h);
     }
     CK(cudaStreamSynchronize(st));
+    if (info[0]) h->prior_valid = false;
     if (info[0]) {
       char b[128];
       snprintf(b, sizeof b, "matrix %s is not positive definite (pivot %d)", info[0] / 100000 == 1 ? "Kh" : "Kx",
@@ -1560,6 +1574,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   const double Ng = hs[S_COUNT + 0], sum_y2 = hs[S_COUNT + 1];
+  if (info[0]) h->prior_valid = false;
   if (info[0]) {
     static const char* names[] = {"?", "Kh", "Kx", "P", "iKh + reg I (prior of q(u))", "q(u) covariance"};
     int tag = info[0] / 100000;
@@ -1638,7 +1653,7 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
   CK(cudaEventRecord(h->ev[0], st));
   CK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
   CK(cudaMemcpyAsync(h->params_d, params_host, np * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (prior_stage(h, c, reg)) return -2;
+  if (prior_stage(h, c, reg, true)) return -2;
   if (!h->gram_valid && plan_store(h, chunks, false)) return -2;
   double* Lq = h->M(M_LQ);
   double* mu = h->V(V_MU);
@@ -1739,6 +1754,7 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
   CK(cudaEventRecord(h->ev[6], st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
+  if (info[0]) h->prior_valid = false;
   if (info[0]) {
     static const char* names[] = {"?", "Kh", "Kx", "P of q(z)", "P of q(u)", "a q covariance"};
     int tag = info[0] / 100000;
@@ -1818,7 +1834,7 @@ int predict_run(cgpcm_handle* h, const double* params_host, double reg, const do
   PCK(cudaMemcpy2DAsync(d_h, ld * sizeof(double), samples_host, nh * sizeof(double), nh * sizeof(double), B,
                         cudaMemcpyHostToDevice, st));
   PCK(cudaMemsetAsync(d_acc, 0, (size_t)2 * std::max<long>(n_star, 1) * sizeof(double), st));
-  PRC(prior_stage(h, c, reg));
+  PRC(prior_stage(h, c, reg, true));
   if (!h->gram_valid) PRC(plan_store(h, chunks, false));
   // q(u) moments
   double* Lq = h->M(M_LQ);
@@ -1927,6 +1943,7 @@ int predict_run(cgpcm_handle* h, const double* params_host, double reg, const do
   cleanup();
 #undef PCK
 #undef PRC
+  if (info[0]) h->prior_valid = false;
   if (info[0]) {
     static const char* names[] = {"?", "Kh", "Kx", "P of q(z)", "?", "?"};
     int tag = info[0] / 100000;
@@ -1991,7 +2008,7 @@ int kernel_run(cgpcm_handle* h, const double* params_host, double reg, const dou
   PCK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
   PCK(cudaMemcpyAsync(d_t, t_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
   PCK(cudaMemcpyAsync(d_hs, samples_host, (size_t)B * nh * sizeof(double), cudaMemcpyHostToDevice, st));
-  PRC(prior_stage(h, c, reg));                          // Kh -> iKh (M_IKH)
+  PRC(prior_stage(h, c, reg, true));                          // Kh -> iKh (M_IKH)
   hh_build_kernel<<<148 * 4, 256, 0, st>>>(d_hs, nh, B, Bp, h->M(M_IKH), ld, nh, nhl, d_HH);
   L(h);
   for (long p0 = 0; p0 < n; p0 += TC) {
@@ -2014,6 +2031,7 @@ int kernel_run(cgpcm_handle* h, const double* params_host, double reg, const dou
   cleanup();
 #undef PCK
 #undef PRC
+  if (info[0]) h->prior_valid = false;
   if (info[0]) { h->err = "matrix Kh is not positive definite"; return -3; }
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
@@ -2075,7 +2093,7 @@ int filter_run(cgpcm_handle* h, const double* params_host, double reg, const dou
     for (int b = 0; b < B; ++b) ee[(size_t)p2 * Bp + b] = noise_host[(size_t)p2 * B + b];
   PCK(cudaMemcpyAsync(d_hs, hs.data(), hs.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   PCK(cudaMemcpyAsync(d_e, ee.data(), ee.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-  PRC(prior_stage(h, c, reg));                                  // M_LH = chol(reg(Kh)), padded with the identity
+  PRC(prior_stage(h, c, reg, true));                                  // M_LH = chol(reg(Kh)), padded with the identity
   filter_kernels_kernel<<<148 * 4, 256, 0, st>>>(h->th, nh, nhp, d_t, (int)n, ldn, alpha, gamma, reg, d_kuh, d_ktt);
   L(h);
   // X = Lh^-1 ;  A = X Kuh ;  S = Ktt - A^T A ;  L = chol(S)
@@ -2104,6 +2122,7 @@ int filter_run(cgpcm_handle* h, const double* params_host, double reg, const dou
   cleanup();
 #undef PCK
 #undef PRC
+  if (info[0]) h->prior_valid = false;
   if (info[0]) {
     h->err = info[0] / 100000 == 5 ? "matrix k_h(t, t) - A^T A + reg I is not positive definite"
                                    : "matrix Kh is not positive definite";
@@ -2183,6 +2202,7 @@ int akm_run(cgpcm_handle* h, const double* params_host, double reg, const double
   PCK(cudaGetLastError());
   cleanup();
 #undef PCK
+  if (info[0]) h->prior_valid = false;
   if (info[0]) { h->err = "AKM covariance a + tr((h h^T - iKh) Ahh) + reg I is not positive definite"; return -3; }
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
