@@ -612,24 +612,28 @@ class VCGPCM(CGPCM):
 
     def predict_h(self, t, samples_h=500, normalise=True, phase_transform='minimum_phase'):
         """Predict the filter at ``t`` (``src/core/cgpcm.py:714-779``).  The posterior draws of the filter come from the
-        GPU (``cgpcm_filter_samples``); the positive part, the phase transform (``None`` or ``'minimum_phase'``), the
-        energy normalisation and the percentile band are post-processing of those draws."""
-        from .util import minimum_phase, energy
-        if phase_transform not in (None, 'minimum_phase'):
-            raise NotImplementedError('phase_transform must be None or "minimum_phase"')
+        GPU (``cgpcm_filter_samples``); the positive part, the phase transform (``None``, ``'minimum_phase'`` or
+        ``'zero_phase'``, the three ``experiment.predict`` asks for, ``src/core/experiment.py:316-321``), the energy
+        normalisation and the percentile band are post-processing of those draws."""
+        from .util import minimum_phase, zero_phase, energy
+        if phase_transform not in (None, 'minimum_phase', 'zero_phase'):
+            raise NotImplementedError('phase_transform must be None, "minimum_phase" or "zero_phase"')
         t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
         draws = self._filter_draws(t, samples_h)
         keep = t >= 0 if self.causal else np.ones(t.shape[0], dtype=bool)
         x = t[keep]
+        x_out = zero_phase(x, np.zeros_like(x))[0] if phase_transform == 'zero_phase' else x
         cols = []
         for b in range(draws.shape[1]):
             y = draws[keep, b]
-            if phase_transform is not None:
+            if phase_transform == 'minimum_phase':
                 y = minimum_phase(y)
+            elif phase_transform == 'zero_phase':
+                y = zero_phase(x, y)[1]
             if normalise:
-                y = y / energy(x, y) ** .5
+                y = y / energy(x_out, y) ** .5
             cols.append(y)
-        return self._mc_stats(x, np.stack(cols, 1))
+        return self._mc_stats(x_out, np.stack(cols, 1))
 
     def predict_psd(self, t, samples_h=500, normalise=True):
         """Predict the PSD from posterior draws of the filter (``src/core/cgpcm.py:663-712``): autocorrelation of

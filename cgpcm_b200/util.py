@@ -61,6 +61,19 @@ def minimum_phase(y):
     return np.real(np.fft.ifft(spec))
 
 
+def zero_phase(x, y):
+    """``Data.zero_phase`` (``src/core/data.py:265-276``): the zero-phase signal with the magnitude spectrum of ``y``,
+    centred; returns ``(x', y')`` with ``x' = dx (arange(n) - n // 2)``."""
+    x = np.asarray(x, dtype=np.float64)
+    d = np.diff(x)
+    if x.shape[0] < 2 or np.abs(d - d[0]).max() > 1e-8 * max(abs(d[0]), 1e-300):
+        raise AssertionError('data must be evenly spaced')
+    n = x.shape[0]
+    yz = np.real(np.fft.fftshift(np.fft.ifft(np.abs(np.fft.fft(y)))))
+    xz = d[0] * np.arange(n)
+    return xz - xz[n // 2], yz
+
+
 def energy(x, y):
     """``Data.energy`` (``src/core/data.py:354-359``): trapezoidal integral of ``y^2``."""
     trap = getattr(np, 'trapezoid', None) or np.trapz

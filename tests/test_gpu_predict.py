@@ -168,6 +168,9 @@ def test_predict_h_and_psd_api():
     assert h_raw.mean.y.shape == (61,)
     p = mod.predict_psd(t, samples_h=6)
     assert p.mean.x.shape == (2 * 81 - 1 + 4000,) and np.all(p.mean.y >= 0)
+    hz = mod.predict_h(t, samples_h=5, phase_transform='zero_phase')          # experiment.predict's third transform
+    assert hz.mean.x.shape == (61,) and hz.mean.x[30] == 0.0 and hz.mean.x[0] == pytest.approx(-30 * .005)
+    assert np.argmax(hz.mean.y) == 30                                         # a zero-phase signal peaks at its centre
     with pytest.raises(NotImplementedError):
-        mod.predict_h(t, samples_h=2, phase_transform='zero_phase')
+        mod.predict_h(t, samples_h=2, phase_transform='linear_phase')
     config.reg = 1e-8

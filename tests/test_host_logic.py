@@ -207,3 +207,10 @@ def test_signal_helpers_follow_the_reference():
     assert energy(x, np.ones(101)) == pytest.approx(1.0)
     lags, ac = autocorrelation(x, y, normalise=True)
     assert lags.shape == (201,) and ac[100] == pytest.approx(1.0) and np.allclose(ac, ac[::-1])
+    from cgpcm_b200.util import zero_phase                       # src/core/data.py:265-276
+    xz, yz = zero_phase(x, y)
+    assert xz[50] == 0.0 and xz[0] == pytest.approx(-.5) and xz.shape == (101,)
+    np.testing.assert_allclose(np.abs(np.fft.fft(yz)), np.abs(np.fft.fft(y)), rtol=1e-8, atol=1e-10)  # same magnitude
+    assert np.argmax(yz) == 50 and np.allclose(yz, yz[::-1], atol=1e-12)                      # even about the centre
+    with pytest.raises(AssertionError):
+        zero_phase(np.array([0., 1., 3.]), np.ones(3))
