@@ -28,17 +28,11 @@ namespace cg {
 
 constexpr int SY_BLK = 40;                 // rows / columns per warp block
 constexpr int SY_G = 5;                    // warp-block rows
-constexpr int SY_NW = SY_G * (SY_G + 1) / 2;
-constexpr int SY_NT = (SY_NW + 1) * 32;    // 512: 15 consumer warps + 1 producer warp
-constexpr int SY_MP = SY_G * SY_BLK;       // 200: largest supported order
+constexpr int SY_MP = SY_G * SY_BLK;       // 200: largest supported order (15 consumer warps + 1 producer warp)
 constexpr int SY_BK = 16;
-constexpr int SY_STAGES = 3;
-constexpr int SY_PANEL = SY_MP * (SY_BK + 4);   // doubles (>= SY_BK * (SY_MP + 4))
-constexpr int SY_STAGE = 2 * SY_PANEL;
-constexpr int SY_SMEM_BYTES = SY_STAGES * SY_STAGE * 8;
 constexpr int SY_MAX_SPLITS = 148;
 
-// Per-order staging: G warp-block rows stage GM = 40 G panel rows; smaller panels get a deeper pipeline so that the
+// Per-order staging: G warp-block rows of TB x TB DMMA tiles stage GM = 8 TB G panel rows; smaller panels get a deeper pipeline so that the
 // bytes in flight per SM stay ~100 KB (the low-order contractions are close to HBM-bound: 6 flop / byte at M = 96).
 template <int G, int TB = 5>
 struct SymCfg {
