@@ -11,6 +11,7 @@
 //                          what remains per element is exp() and FMAs, and the Genz branch is uniform.
 //   bvnd_general(h, k, r)  per-element correlation, for the stand-alone cgpcm_bvn_cdf export.
 #pragma once
+#include "cgmath.cuh"
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -302,6 +303,50 @@ __device__ __forceinline__ void bvn_partials_tab(double x1, double x2, const Bvn
   d2 = inv_sqrt_2pi * exp(-0.5 * x2 * x2) * phid((x1 - T.rho * x2) * T.inv_s);
   dr = exp(-(x1 * x1 - 2.0 * T.rho * x1 * x2 + x2 * x2) * T.inv_2om) * T.inv_2pis;
 }
+// The pair-hoisted value and the three partials of one element with all of its transcendentals evaluated in lock-step
+// (cgmath.cuh): five exp -- the caller's envelope exp(G), exp(-hk / 2), the two marginal densities and the bivariate
+// density -- and three erfc -- Phi(min(x1, x2)) and the two conditional Phis.  Same formulas as bvn_cdf_pair +
+// bvn_partials_tab; one materialised polynomial coefficient feeds five (three) FMAs and the eight chains overlap.
+// Returns false when hk < -U (outside the Chebyshev interval): the caller takes the un-hoisted routine.
+__device__ __forceinline__ bool bvn_pair_all(double G, double x1, double x2, const BvnTab& T, const BvnPair& R,
+                                             const double* sA, int deg, double& envexp, double& cdf, double& d1,
+                                             double& d2, double& dr) {
+  const double hk = x1 * x2;
+  if (hk < -BVN_CHEB_U) return false;
+  const double q = x1 * x1 - 2.0 * T.rho * x1 * x2 + x2 * x2;
+  const double ea[5] = {G, -0.5 * hk, -0.5 * x1 * x1, -0.5 * x2 * x2, -q * T.inv_2om};
+  const double is2 = 0.70710678118654752440;
+  const double ca[3] = {-fmin(x1, x2) * is2, -((x2 - T.rho * x1) * T.inv_s) * is2, -((x1 - T.rho * x2) * T.inv_s) * is2};
+  double ev[5], cv[3];
+  cg_exp_neg<5>(ea, ev);
+  cg_erfc<3>(ca, cv);
+  envexp = ev[0];
+  const double inv_sqrt_2pi = 0.39894228040143267794;
+  d1 = inv_sqrt_2pi * ev[2] * (0.5 * cv[1]);
+  d2 = inv_sqrt_2pi * ev[3] * (0.5 * cv[2]);
+  dr = ev[4] * T.inv_2pis;
+  const double tail = 0.5 * cv[0];
+  if (hk > BVN_CHEB_U) { cdf = tail; return true; }      // every remaining term is below exp(-100) (Genz's own cut)
+  const double E1 = ev[1];
+  const double c = (4.0 - hk) * 0.125, d = (12.0 - hk) * 0.0625;
+  const double bs = R.bs, as = T.as_;
+  const double t5 = 1.0 - d * bs * 0.2;
+  double s = R.P0 * (1.0 - c * (bs - as) * t5 * (1.0 / 3.0) + c * d * as * as * 0.2) -
+             R.Pb * (1.0 - c * bs * t5 * (1.0 / 3.0)) - (R.K0 + c * (R.K1 + d * R.K2));
+  const double ut = hk * (1.0 / BVN_CHEB_U), t2 = ut + ut;
+  const double* a = sA + threadIdx.x;
+  double b1 = 0.0, b2 = 0.0;
+#pragma unroll 4
+  for (int m = deg; m >= 1; --m) {
+    const double b0 = fma(t2, b1, a[m * BVN_PAIR_THREADS]) - b2;
+    b2 = b1;
+    b1 = b0;
+  }
+  s += fma(ut, b1, a[0]) - b2;
+  cdf = tail - E1 * s * (1.0 / CG_TWO_PI);
+  return true;
+}
+
 __device__ __forceinline__ void bvn_cdf_grad_tab(double x1, double x2, const BvnTab& T, double& cdf,
                                                  double& d1, double& d2, double& dr) {
   cdf = bvnd_tab(-x1, -x2, T);

@@ -1,0 +1,105 @@
+// FP64 exp / erfc for the Psi kernels, U elements at a time (sm_100a).
+//
+// Why not the CUDA math library here: `ahx_gen_kernel` spends one exp() and one erfc() per element and is bound by
+// instruction issue, not by the FP64 pipe (ncu, profiles/r01_ncu_psi_kernels_exact746.txt: FP64 pipe 54 % active,
+// issue slots 77 %).  Its SASS shows why: ptxas materialises every polynomial coefficient of the inlined library
+// routines with two 32-bit moves (UMOV / IMAD.MOV) right before the DFMA that uses it -- 105 of the 254 instructions of
+// the per-element loop are constant moves, 89 are FP64.  The routines below evaluate U independent arguments in
+// lock-step (arrays in registers, every step an unrolled loop over u), so one materialised coefficient feeds U DFMAs,
+// and they are branch-free (no slow paths: the argument ranges of the Psi statistics are known).
+//
+//   cg_exp_neg<U>(x)   exp(x) for x <= 0 (arguments below -750 give 0): n = rint(x log2 e), r = x - n ln 2 (two FMAs),
+//                      degree-12 polynomial (Chebyshev interpolant of exp on |r| <= ln2 / 2, error 3e-18), scaling by
+//                      2^n in two exact steps so that subnormal results round once.
+//   cg_erfc<U>(z)      erfc(z) for any finite z: with x = |z| (clamped at 27.3, where erfc underflows) and
+//                      t = (x - 4) / (x + 4) in [-1, 1),  erfc(x) = exp(-x^2) g(t) / (1 + 2 x),  g(t) = (1 + 2x) erfcx(x)
+//                      a degree-26 polynomial (Chebyshev interpolant, truncation 4e-17, sum |c_i| = 1.8 so Horner is
+//                      well conditioned); exp(-x^2) from the rounded square and its exact residual (fma);
+//                      one reciprocal (hardware approximation + 2 Newton steps) serves both divisions;
+//                      erfc(z) = 2 - erfc(-z) for z < 0.
+// Coefficients: computed with mpmath at 60 digits (tools/fit_cgmath.py), rounded to double; accuracy against mpmath is
+// tested in tests/test_gpu_kernels.py (cgpcm_math_test): <= 2 ulp (exp), <= 4 ulp (erfc) over the whole range.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace cg {
+
+// descending order (Horner): c12 .. c0
+#define CG_EXP_COEFS(X)                                                                                        \
+  X(0x1.af785d433f066p-26) X(0x1.27e4cc1847a65p-22) X(0x1.71dde76ab2f81p-19) X(0x1.a01a01adc27e2p-16)          \
+  X(0x1.a01a01b80226cp-13) X(0x1.6c16c16c14d77p-10) X(0x1.111111110db76p-7) X(0x1.5555555555559p-5)           \
+  X(0x1.5555555555562p-3) X(0x1.0000000000000p-1) X(0x1.0000000000000p+0) X(0x1.0000000000000p+0)
+#define CG_EXP_C12 0x1.1f8b43f2637adp-29
+
+// descending order: c25 .. c0
+#define CG_ERFC_COEFS(X)                                                                                       \
+  X(-0x1.2dbbbb75b6682p-33) X(-0x1.2d277a41632e3p-31) X(0x1.ebb009434f4efp-30) X(0x1.117f492198859p-28)        \
+  X(-0x1.f9443297365a1p-27) X(-0x1.78888d24fa8a1p-26) X(0x1.d8d5b12b4bdebp-24) X(0x1.5305495fa5317p-24)        \
+  X(-0x1.badf24e872985p-21) X(0x1.385bb6c82456ap-22) X(0x1.7f235478fdcf6p-18) X(-0x1.788189c990557p-17)        \
+  X(-0x1.9958a8c635c6bp-16) X(0x1.3be032de511d3p-13) X(-0x1.a1df2ad41dddep-13) X(-0x1.8d4a9990c5199p-11)       \
+  X(0x1.49c6728db72cdp-8) X(-0x1.0962388548d8dp-6) X(0x1.3079edf668f38p-5) X(-0x1.0fb06dfe48b0ep-4)            \
+  X(0x1.7fee004e13186p-4) X(-0x1.9ddb23c3e9106p-4) X(0x1.16ecefcfa533fp-4) X(0x1.f7f5df66fd7bep-7)             \
+  X(-0x1.1df1ad154a28ep-3) X(0x1.3ba5916e9fd7fp+0)
+#define CG_ERFC_C26 0x1.7d604a7f621f4p-35
+
+template <int U>
+__device__ __forceinline__ void cg_exp_neg(const double (&x)[U], double (&out)[U]) {
+  double r[U], p[U];
+  int ni[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double xc = fmax(x[u], -750.0);
+    const double t = fma(xc, 0x1.71547652b82fep+0, 6755399441055744.0);      // x log2(e) + 1.5 * 2^52
+    ni[u] = __double2loint(t);
+    const double n = t - 6755399441055744.0;
+    double rr = fma(n, -0x1.62e42fefa39efp-1, xc);
+    r[u] = fma(n, -0x1.abc9e3b39803fp-56, rr);
+    p[u] = CG_EXP_C12;
+  }
+#define CG_STEP(c)                  \
+  _Pragma("unroll") for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], c);
+  CG_EXP_COEFS(CG_STEP)
+#undef CG_STEP
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int k1 = ni[u] >> 1, k2 = ni[u] - k1;                               // both >= -541: normal powers of two
+    const double s1 = __hiloint2double((1023 + k1) << 20, 0), s2 = __hiloint2double((1023 + k2) << 20, 0);
+    out[u] = (p[u] * s1) * s2;
+  }
+}
+
+template <int U>
+__device__ __forceinline__ void cg_erfc(const double (&z)[U], double (&out)[U]) {
+  double x[U], t[U], inv[U], g[U], mh[U], l[U], e[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    x[u] = fmin(fabs(z[u]), 27.3);
+    const double a = x[u] + 4.0, b = fma(2.0, x[u], 1.0);
+    const double den = a * b;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));                   // ~2^-23 relative
+    double err = fma(-den, y, 1.0);
+    y = fma(y, err, y);
+    err = fma(-den, y, 1.0);
+    y = fma(y, err, y);                                                       // 1 / ((x + 4)(1 + 2x))
+    t[u] = (x[u] - 4.0) * (b * y);
+    inv[u] = a * y;                                                           // 1 / (1 + 2x)
+    const double h = x[u] * x[u];
+    l[u] = fma(x[u], x[u], -h);                                               // x^2 = h + l exactly
+    mh[u] = -h;
+    g[u] = CG_ERFC_C26;
+  }
+#define CG_STEP(c)                  \
+  _Pragma("unroll") for (int u = 0; u < U; ++u) g[u] = fma(g[u], t[u], c);
+  CG_ERFC_COEFS(CG_STEP)
+#undef CG_STEP
+  cg_exp_neg<U>(mh, e);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double ee = fma(-e[u], l[u], e[u]);                                 // exp(-(h + l)) = exp(-h) (1 - l)
+    const double r = ee * (g[u] * inv[u]);
+    out[u] = z[u] < 0.0 ? 2.0 - r : r;
+  }
+}
+
+}  // namespace cg

@@ -2459,6 +2459,62 @@ int cgpcm_dgemm_sym(int kc, int M, int K, const double* A, int64_t lda, const do
   return rc;
 }
 
+// cgmath.cuh under test: out_exp[i] = cg_exp_neg(min(x[i], 0)), out_erfc[i] = cg_erfc(x[i]), evaluated four at a time;
+// *mismatch = number of elements whose one-at-a-time evaluation differs in any bit (must be 0).
+__global__ void math_test_kernel(const double* __restrict__ x, long n, double* __restrict__ oe, double* __restrict__ oc,
+                                 int* __restrict__ mismatch) {
+  for (long i0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += (long)gridDim.x * blockDim.x * 4) {
+    double xe[4], xc[4], e4[4], c4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double v = i0 + u < n ? x[i0 + u] : 0.0;
+      xe[u] = fmin(v, 0.0);
+      xc[u] = v;
+    }
+    cg_exp_neg<4>(xe, e4);
+    cg_erfc<4>(xc, c4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u >= n) break;
+      const double a1[1] = {xe[u]}, b1[1] = {xc[u]};
+      double e1[1], c1[1];
+      cg_exp_neg<1>(a1, e1);
+      cg_erfc<1>(b1, c1);
+      if (__double_as_longlong(e1[0]) != __double_as_longlong(e4[u]) ||
+          __double_as_longlong(c1[0]) != __double_as_longlong(c4[u]))
+        atomicAdd(mismatch, 1);
+      oe[i0 + u] = e4[u];
+      oc[i0 + u] = c4[u];
+    }
+  }
+}
+
+int cgpcm_math_test(const double* x, int64_t n, double* out_exp, double* out_erfc, int* mismatch_host) {
+  if (!x || n < 1 || !out_exp || !out_erfc) return -1;
+  double *dx = nullptr, *de = nullptr, *dc = nullptr;
+  int* dm = nullptr;
+  int rc = 0;
+  if (cudaMalloc(&dx, n * sizeof(double)) != cudaSuccess || cudaMalloc(&de, n * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&dc, n * sizeof(double)) != cudaSuccess || cudaMalloc(&dm, sizeof(int)) != cudaSuccess) rc = -2;
+  if (!rc) {
+    cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyDefault);
+    cudaMemset(dm, 0, sizeof(int));
+    math_test_kernel<<<148 * 4, 256>>>(dx, n, de, dc, dm);
+    if (cudaDeviceSynchronize() != cudaSuccess) rc = -2;
+    cudaMemcpy(out_exp, de, n * sizeof(double), cudaMemcpyDefault);
+    cudaMemcpy(out_erfc, dc, n * sizeof(double), cudaMemcpyDefault);
+    int m = 0;
+    cudaMemcpy(&m, dm, sizeof(int), cudaMemcpyDeviceToHost);
+    if (mismatch_host) *mismatch_host = m;
+  }
+  cudaGetLastError();
+  if (dx) cudaFree(dx);
+  if (de) cudaFree(de);
+  if (dc) cudaFree(dc);
+  if (dm) cudaFree(dm);
+  return rc;
+}
+
 int cgpcm_cholinv(double* A, double* Ainv, double* logdet, int n, int64_t ld, int* info_host) {
   if (!A || n < 1 || ld < n || (ld % 8)) return -1;
   int np = round_up(n, 8);

@@ -16,6 +16,7 @@
 //   ahh_kernel       Ahh[i,j] and tangents; prior kernels Kh, Kx (kernel.py:43-46).
 #pragma once
 #include "bvn.cuh"
+#include "cgmath.cuh"
 
 namespace cg {
 
@@ -136,6 +137,25 @@ __global__ void __launch_bounds__(256, HOIST ? 2 : 3) axx_sum_kernel(const doubl
     const double q2 = dk * dk + dl * dl, pr = dk * dl;
     const double G = -c.g1 * q2 + c.g2 * pr;
     if (G < -c.cull) continue;
+    if (HOIST && TANGENTS) {
+      // every transcendental of the element in lock-step (bvn_pair_all); causal by construction of HOIST
+      const double x1 = c.p * dk + c.q * dl, x2 = c.q * dk + c.p * dl;
+      double eg, cdf, d1, d2, dr;
+      if (!bvn_pair_all(G, x1, x2, T, R, sA, deg, eg, cdf, d1, d2, dr)) {
+        eg = exp(G);
+        bvn_cdf_grad_tab(x1, x2, T, cdf, d1, d2, dr);
+      }
+      const double env = c.pref_xx * eg;
+      const double V = env * cdf;
+      s0 += V;
+      s1 += V * (-c.dg1[0] * q2 + c.dg2[0] * pr - c.dhalf_logdet[0]) +
+            env * (d1 * (c.dp[0] * dk + c.dq[0] * dl) + d2 * (c.dq[0] * dk + c.dp[0] * dl) + dr * c.drho[0]);
+      s2 += V * (-c.dg1[1] * q2 + c.dg2[1] * pr - c.dhalf_logdet[1]) +
+            env * (d1 * (c.dp[1] * dk + c.dq[1] * dl) + d2 * (c.dq[1] * dk + c.dp[1] * dl) + dr * c.drho[1]);
+      s3 += V * (-c.dg1[2] * q2 + c.dg2[2] * pr - c.dhalf_logdet[2]) +
+            env * (d1 * (c.dp[2] * dk + c.dq[2] * dl) + d2 * (c.dq[2] * dk + c.dp[2] * dl) + dr * c.drho[2]);
+      continue;
+    }
     const double env = c.pref_xx * exp(G);
     if (!c.causal) {
       s0 += env;
@@ -192,15 +212,47 @@ __global__ void axx_user_kernel(const double* __restrict__ t, int n_obs, const d
   }
 }
 
+// Ahx[n,i,k] for U values of d = t_n - tx_k at one th (App. A.3), in lock-step (cgmath.cuh): the envelope exp(E) and the
+// causal factor erfc(z).  Elements whose envelope is below exp(-c.cull) are exactly 0; `live[u] = false` forces 0 as well
+// (padding).  Every caller goes through this routine, so a given (th, d) gives the same bits everywhere.
+template <int U>
+__device__ __forceinline__ void ahx_values(double th, const double (&d)[U], const bool (&live)[U], const PsiConst& c,
+                                           double (&v)[U]) {
+  const double e0 = -c.e_hh * th * th, e1 = c.e_hd * th;
+  const double z0 = -(c.gamma * th) * c.inv_sqrtA, z1 = -c.omega * c.inv_sqrtA;
+  double E[U], z[U], ex[U], ec[U];
+  bool any = false;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    E[u] = fma(d[u], fma(-c.e_dd, d[u], e1), e0);            // -e_hh th^2 - e_dd d^2 + e_hd th d
+    z[u] = fma(z1, d[u], z0);                                // -(gamma th + omega d) / sqrt(A)
+    any = any || (live[u] && E[u] >= -c.cull);
+  }
+  if (!any) {                                                // e.g. 80 % of the elements when no window is cut
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = 0.0;
+    return;
+  }
+  cg_exp_neg<U>(E, ex);
+  if (c.causal) cg_erfc<U>(z, ec);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    double r = c.pref_hx * ex[u];
+    if (c.causal) r *= ec[u];
+    v[u] = (live[u] && E[u] >= -c.cull) ? r : 0.0;
+  }
+}
+
 __device__ __forceinline__ double ahx_value(double th, double d, const PsiConst& c) {
-  const double E = -c.e_hh * th * th - c.e_dd * d * d + c.e_hd * th * d;
-  if (E < -c.cull) return 0.0;
-  double v = c.pref_hx * exp(E);
-  if (c.causal) v *= erfc(-(c.gamma * th + c.omega * d) * c.inv_sqrtA);
-  return v;
+  const double dd[1] = {d};
+  const bool live[1] = {true};
+  double v[1];
+  ahx_values<1>(th, dd, live, c, v);
+  return v[0];
 }
 
 constexpr int AHX_NSUB = 32;
+constexpr int AHX_U = 4;          // observations a thread evaluates in lock-step
 
 // A[(i*nc + n)*kwp + k] for i < nhp, n < nc, k < kwp (zero outside the valid nh x n_valid x nx box).
 // Ypart[blockIdx.y][i][k_lo + k] += sum_n y_n A   (slice-private accumulation, reduced later).
@@ -220,13 +272,21 @@ __global__ void __launch_bounds__(256) ahx_gen_kernel(const double* __restrict__
     const double txk = ok ? tx[kg] : 0.0;
     double ysum = 0.0;
     double* dst = A + ((long)i * nc + n0) * kwp + k;
-    for (int n = n0; n < n1; ++n, dst += kwp) {
-      double v = 0.0;
-      if (ok && n < n_valid) {
-        v = ahx_value(thi, __ldg(t + n) - txk, c);
-        ysum += __ldg(y + n) * v;
+    for (int n = n0; n < n1; n += AHX_U, dst += (long)AHX_U * kwp) {
+      double d[AHX_U], yv[AHX_U], v[AHX_U];
+      bool live[AHX_U];
+#pragma unroll
+      for (int u = 0; u < AHX_U; ++u) {
+        live[u] = ok && n + u < n_valid;
+        d[u] = live[u] ? __ldg(t + n + u) - txk : 0.0;
+        yv[u] = live[u] ? __ldg(y + n + u) : 0.0;
       }
-      *dst = v;
+      ahx_values<AHX_U>(thi, d, live, c, v);
+#pragma unroll
+      for (int u = 0; u < AHX_U; ++u) {
+        ysum += yv[u] * v[u];                                // observations in increasing order, as before
+        if (n + u < n1) dst[(long)u * kwp] = v[u];
+      }
     }
     if (ok && Ypart) Ypart[(long)blockIdx.y * ypart_stride + (long)i * ldy + kg] += ysum;
   }
@@ -268,20 +328,29 @@ __global__ void __launch_bounds__(256) ahx_dot_kernel(const double* __restrict__
         }
         src += 4L * kwp;
         asrc += 4L * kwp;
+        // F = Ahx[n,i,k] itself is still in the chunk's block (same bits as the forward value); only the Gaussian
+        // factor exp(E - z^2) of the erfc derivative is evaluated here, four observations in lock-step (cgmath.cuh)
+        double Ev[4], zv[4], ga[4], gx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double d = tv[u] - txk;
+          Ev[u] = -c.e_hh * thi * thi - c.e_dd * d * d + c.e_hd * thi * d;
+          zv[u] = -(c.gamma * thi + c.omega * d) * c.inv_sqrtA;
+          ga[u] = Ev[u] - zv[u] * zv[u];
+        }
+        if (c.causal) cg_exp_neg<4>(ga, gx);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (nb + u >= n1) break;
           const double d = tv[u] - txk;
-          const double E = -c.e_hh * thi * thi - c.e_dd * d * d + c.e_hd * thi * d;
+          const double E = Ev[u];
           if (E < -c.cull) continue;
           const double w = wv[u] + yv[u] * yb;
           const double bh = -(c.gamma * thi + c.omega * d);    // b / 2
           const double uu = bh * 2.0 * c.inv_2A;               // b / (2A)
-          const double z = bh * c.inv_sqrtA;
-          // F = Ahx[n,i,k] itself is still in the chunk's block (same bits as the forward value); only the
-          // Gaussian factor of the erfc derivative is evaluated here
+          const double z = zv[u];
           const double F = av[u];
-          const double X = c.causal ? exp(E - z * z) * c.inv_sqrtA : 0.0;
+          const double X = c.causal ? gx[u] * c.inv_sqrtA : 0.0;
           const double zc = z * c.inv_2A;
           const double da = F * (-thi * thi - uu * uu - c.inv_2A) + X * zc;
           const double dg = F * (-(thi + uu) * (thi + uu) - c.inv_2A) + X * (thi * c.inv_sqrtA + zc);

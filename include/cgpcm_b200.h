@@ -165,6 +165,10 @@ int cgpcm_dgemm(int a_kc, int b_kc, int c_tr, int M, int N, int K, double alpha,
 int cgpcm_dgemm_sym(int kc, int M, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                     int64_t ldc, double* work, void* stream);
 int cgpcm_cholinv(double* A, double* Ainv, double* logdet, int n, int64_t ld, int* info_host);
+/* cgpcm_math_test: the in-register exp / erfc of the Psi kernels (csrc/cgmath.cuh) on n arguments (host or device):
+ * out_exp[i] = exp(min(x[i], 0)), out_erfc[i] = erfc(x[i]), evaluated four at a time; *mismatch = elements whose
+ * one-at-a-time evaluation differs in any bit (0 when the lock-step evaluation is faithful). */
+int cgpcm_math_test(const double* x, int64_t n, double* out_exp, double* out_erfc, int* mismatch_host);
 
 #ifdef __cplusplus
 }

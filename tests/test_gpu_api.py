@@ -10,7 +10,7 @@ torch = pytest.importorskip('torch')
 import cgpcm_b200
 from cgpcm_b200 import VCGPCM, Data, Session, config, learn
 from oracle import model as om
-from tests.cases import oracle_noise_floor
+from tests.cases import oracle_noise_floor  # noqa: F401 (kept for interactive use)
 
 
 def test_train_schedule_toy():
@@ -46,28 +46,23 @@ def test_train_schedule_toy():
     e_post = sess.run(elbo)
     assert e_start < e_pre <= e_main + 1e-9 and e_main <= e_post + 1e-9
     assert sum(sess.run([tm['tensor'] for tm in terms])) == pytest.approx(e_post, rel=1e-12)
-    # the oracle agrees at the trained variables
+    # the oracle agrees at the trained variables.  At the trained point (s2 ~ 4e-3, cond(Kh) ~ 1/reg) the ELBO (~ -8) is a
+    # sum of terms of magnitude ~1e2..1e3 that cancel and the gradient a cancellation of terms ~1e6 times larger than
+    # itself: the oracle's own terms / gradient move by ~1e-5 when its inputs move by 2 ulp (measured here).  The bar is
+    # 1e-9 relative to the largest term, term by term, plus 3 x that measured conditioning noise.
+    from tests.cases import ulp_noise
     p = mod._pack()
     om.PW_DISTS_EXACT = True
     try:
-        want = om.elbo_and_grad(p, t, y, mod.th, mod.tx, config.reg)
+        want, (enoise, tnoise, gnoise) = ulp_noise(
+            lambda pp, th: om.elbo_and_grad(pp, t, y, th, mod.tx, config.reg), p, mod.th, trials=4)
     finally:
         om.PW_DISTS_EXACT = False
-    # the trained ELBO (~ -8) is a sum of terms of magnitude ~1e2..1e3 that cancel: parity is 1e-9 relative
-    # to the largest term, term by term
     got_terms = np.array(sess.run([tm['tensor'] for tm in terms]))
     scale = np.abs(want[1]).max()
-    assert np.abs(got_terms - want[1]).max() <= 1e-9 * scale, (got_terms, want[1])
-    assert abs(want[0] - e_post) <= 1e-9 * scale
+    assert np.abs(got_terms - want[1]).max() <= 1e-9 * scale + 3 * tnoise, (got_terms, want[1], tnoise)
+    assert abs(want[0] - e_post) <= 1e-9 * scale + 3 * enoise
     gsel = mod._evaluate(True, ['mu_u', 'var_u', 's2_f', 's2', 'gamma', 'omega', 'alpha'])[2]
-    # at the trained point (s2 ~ 4e-3, cond(Kh) ~ 1/reg) the gradient is a cancellation of terms ~1e6 times
-    # larger than itself: the oracle's own gradient moves by ~1e-5 when its inputs move by 1 ulp.  The bar is
-    # 1e-9 relative or that measured conditioning noise, whichever is larger.
-    om.PW_DISTS_EXACT = True
-    try:
-        _, gnoise = oracle_noise_floor(p, t, y, mod.th, mod.tx, config.reg)
-    finally:
-        om.PW_DISTS_EXACT = False
     assert np.abs(gsel - want[2]).max() <= 1e-9 * np.abs(want[2]).max() + 3 * gnoise, gnoise
     mats = mod.mats
     assert mats['sum_Axx'].shape == (40, 40) and mats['Ahh'].shape == (21, 21)

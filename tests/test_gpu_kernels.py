@@ -177,3 +177,35 @@ def test_cholinv_reports_non_positive_definite():
     info = ctypes.c_int(0)
     rc = _lib.lib().cgpcm_cholinv(dA.data_ptr(), None, None, n, ld, ctypes.byref(info))
     assert rc == -3 and info.value == 8
+
+
+def test_in_register_exp_and_erfc_against_mpmath():
+    """csrc/cgmath.cuh (the lock-step exp / erfc of the Ahx kernels) against mpmath: <= 2 ulp for exp on [-745, 0],
+    <= 4 ulp for erfc on [-8, 27] (relative to the result, i.e. also where erfc is 1e-300), exact limits, and the
+    four-at-a-time evaluation gives the same bits as one at a time."""
+    import ctypes
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(11)
+    x = np.concatenate([-rng.uniform(0, 745, 1500), -10.0 ** rng.uniform(-12, 0, 300), [0.0, -1e-300, -744.4, -708.4],
+                        rng.uniform(-8, 27, 1500), rng.normal(0, 1.5, 700), [-6.5, -30.0, 26.5, 27.2, 0.5, 4.0]])
+    x = np.ascontiguousarray(x)
+    oe, oc = np.empty_like(x), np.empty_like(x)
+    mism = ctypes.c_int(-1)
+    rc = _lib.lib().cgpcm_math_test(_lib.ptr(x), x.shape[0], _lib.ptr(oe), _lib.ptr(oc), ctypes.byref(mism))
+    assert rc == 0 and mism.value == 0
+
+    def ulps(got, want):
+        want_f = float(want)
+        if want_f == 0.0 or abs(want_f) < 2.3e-308:          # subnormal results: absolute, in units of the least subnormal
+            return abs(got - want_f) / 5e-324 / 2 ** 3
+        return abs(mp.mpf(got) - want) / mp.mpf(np.spacing(abs(want_f)))
+
+    worst_e = max(ulps(oe[i], mp.exp(mp.mpf(min(x[i], 0.0)))) for i in range(x.shape[0]))
+    worst_c = max(ulps(oc[i], mp.erfc(mp.mpf(x[i]))) for i in range(x.shape[0]) if x[i] < 26.0)
+    assert worst_e <= 2.0, worst_e
+    assert worst_c <= 4.0, worst_c
+    i0 = int(np.where(x == 0.0)[0][0])
+    assert oe[i0] == 1.0 and oc[i0] == 1.0
+    assert oc[np.where(x == -30.0)[0][0]] == 2.0 and oc[np.where(x == -6.5)[0][0]] == 2.0
+    assert 0.0 <= oc[np.where(x == 27.2)[0][0]] <= 1e-320
