@@ -369,7 +369,7 @@ def run_ours(args):
                      'note': 'MEASURED_PEAKS.json has no FP64 figure; peak = FP64 tensor (DMMA) rate measured by '
                              'tools/fp64_peaks.cu; flops are algorithmic: 2 K M N per launch, K M (M + 1) for the '
                              'symmetric M x M results (only the lower triangle is needed); launch durations from '
-                             'CUDA events around every GEMM launch on the library stream'},
+                             'CUDA events around every run of consecutive GEMM launches on the library stream'},
         'breakdown_ms_per_step': {'axx_kernel': axx_ms / args.steps, 'ahx_gen_kernels': gen_ms / args.steps,
                                   'gemm_kernels': gemm_ms / args.steps},
         # BASELINE.json's second figure: logical bytes of the Psi statistics the reference materialises
