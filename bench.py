@@ -47,7 +47,7 @@ def parse():
                     help='headline (746): nothing is approximated -- the only Psi elements / GEMM tiles skipped are '
                          'those that are exactly 0.0 in IEEE double (their Gaussian envelope exp(E), E < -745.2, '
                          'underflows); 0 = every tile multiplied, 80 = envelope < exp(-80) dropped; both reported beside')
-    ap.add_argument('--chunk', type=int, default=512)
+    ap.add_argument('--chunk', type=int, default=0, help='0 = the library default: chosen per evaluation by the planner')
     ap.add_argument('--cpu-sample', type=int, default=300, help='observations in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -337,15 +337,16 @@ def run_ours(args):
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': 'scaling sweep N=%d observations, nh=nx=%d, causal VCGPCM, full regime (Psi rebuilt '
                                'and differentiated), grad w.r.t. all %d variables' % (n, m, npar),
-                   'n': n, 'nh': m, 'nx': m, 'cull': args.cull, 'chunk': args.chunk,
+                   'n': n, 'nh': m, 'nx': m, 'cull': args.cull,
+                   'chunk': args.chunk if args.chunk > 0 else 'planner (512 / 1024 / 2048 x nx columns per chunk by its cost model)',
                    'windows': {746.0: 'exact: only Psi elements / GEMM tiles that are exactly 0.0 in IEEE double '
                                       '(exp underflow of the Gaussian envelope) are skipped; same sums as the '
                                       'all-tiles evaluation in another order (other_window_settings[cull=0] holds '
                                       'the measured difference)',
                                0.0: 'every Psi tile and GEMM tile evaluated',
                                80.0: 'envelope < exp(-80) dropped'}.get(args.cull, 'envelope < exp(-cull) dropped'),
-                   'l2': 'flushed between timed steps (512 MB write); every chunk streams 3 x %.0f MB of operands '
-                         '(> 126 MB L2) and the sweep stores hold 2 x %.1f GB' % (8e-6 * m * args.chunk * m,
+                   'l2': 'flushed between timed steps (512 MB write); every chunk streams 3 x >= %.0f MB of operands '
+                         '(> 126 MB L2) and the sweep stores hold 2 x %.1f GB' % (8e-6 * m * max(args.chunk, 512) * m,
                                                                                    8e-9 * m * (hi - lo) * m),
                    'parallelism': 'observations sharded over %d GPU(s), one packed ncclAllReduce per sweep' % world},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
@@ -357,6 +358,8 @@ def run_ours(args):
                                'dominant), dgemm_sym_kernel (3 per chunk), dgemm_dmma_kernel (M x M algebra)',
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
                      'traffic': TRAFFIC_SL_BYTES if (args.n == 100000 and args.m == 200 and args.chunk == 512) else None,
+                     'traffic_per': 'dgemm_sl_kernel launch of 200 x 200 x 102400 (chunk 512); the planner\'s chunks hold '
+                                    '2 - 4 x as many columns with the same bytes per column',
                      'traffic_note': 'dram read + write bytes of one dgemm_sl_kernel launch (T1 = H A, 200 x 200 times '
                                      '200 x ~102400: the same shape with and without windows) from the ncu --set full '
                                      'captures in profiles/; algorithmic bytes of that launch: 328 MB',

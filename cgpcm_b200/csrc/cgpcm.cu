@@ -128,6 +128,7 @@ struct cgpcm_handle {
   // options
   int chunk = 512;          // observations per chunk at full window width
   double cull = 80.0;       // 0 = dense
+  bool chunk_auto = true;   // option "chunk" <= 0 (default): plan_chunks picks 512 / 1024 / 2048 by its cost model
   int profile = 0;          // 1 = CUDA events around every GEMM launch (roofline measurement)
   std::vector<cudaEvent_t> pev;
   size_t pev_used = 0;
@@ -436,11 +437,11 @@ double ahx_radius(const PsiConst& c, double cull) {
   return sqrt(cull / lam);
 }
 
-void plan_chunks(cgpcm_handle* h, const PsiConst& c, std::vector<Chunk>& out) {
+void plan_chunks_fixed(cgpcm_handle* h, const PsiConst& c, int chunk, std::vector<Chunk>& out) {
   out.clear();
   const long N = h->n_local;
   const double R = ahx_radius(c, h->cull);
-  const long budget = (long)h->chunk * h->nxp;    // columns (n, k) per row i
+  const long budget = (long)chunk * h->nxp;    // columns (n, k) per row i
   long n0 = 0;
   auto window = [&](long a, long b, int& k_lo, int& kwp) {
     if (!std::isfinite(R)) { k_lo = 0; kwp = h->nxp; return; }
@@ -459,7 +460,7 @@ void plan_chunks(cgpcm_handle* h, const PsiConst& c, std::vector<Chunk>& out) {
   };
   while (n0 < N) {
     long rem = N - n0;
-    int nc = (int)std::min<long>(rem, h->chunk);
+    int nc = (int)std::min<long>(rem, chunk);
     int k_lo, kwp;
     window(n0, n0 + nc, k_lo, kwp);
     if (kwp < h->nxp && nc < rem) {
@@ -478,6 +479,30 @@ void plan_chunks(cgpcm_handle* h, const PsiConst& c, std::vector<Chunk>& out) {
     ch.off = out.empty() ? 0 : out.back().off + (long)h->nhp * out.back().nc * out.back().kwp;
     out.push_back(ch);
     n0 += nc;
+  }
+}
+
+// Workspace budget of a chunk (columns = budget x nxp).  More observations per chunk mean fewer, longer launches (the
+// persistent GEMM kernels lose ~0.2 ms per chunk to ragged tile counts, pipeline ramps and launch gaps) but a wider
+// union window, i.e. more flops: measured at the bench shape, exact-zero windows, 127.6 / 126.3 / 120.0 / 131.1 / 140.0 ms
+// for 512 / 1024 / 2048 / 3072 / 4096, while cull = 80 (narrow windows, which widen relatively more) is fastest at 512.
+// With option "chunk" <= 0 (default) the planner evaluates the candidates with that cost model and keeps the cheapest;
+// the model only depends on the plan, so the frozen regime plans the same chunks at every evaluation.
+constexpr int CHUNK_AUTO_MAX = 2048;
+inline int chunk_cap(const cgpcm_handle* h) { return h->chunk_auto ? CHUNK_AUTO_MAX : h->chunk; }
+
+void plan_chunks(cgpcm_handle* h, const PsiConst& c, std::vector<Chunk>& out) {
+  if (!h->chunk_auto) { plan_chunks_fixed(h, c, h->chunk, out); return; }
+  double best = INFINITY;
+  std::vector<Chunk> cand;
+  for (int chunk : {512, 1024, CHUNK_AUTO_MAX}) {
+    plan_chunks_fixed(h, c, chunk, cand);
+    double cost = 0.0;
+    for (const Chunk& ch : cand) {
+      const double el = (double)ch.nc * h->nhp * ch.kwp;                       // Ahx elements of the chunk
+      cost += el * (4.0 * h->nhp + 7.0 * ch.kwp) / 27e12 + el * 1.5e-11 + 0.21e-3;   // contractions + Psi kernels + per chunk
+    }
+    if (cost < best) { best = cost; out.swap(cand); h->chunk = chunk; }
   }
 }
 
@@ -505,7 +530,7 @@ int plan_store(cgpcm_handle* h, const std::vector<Chunk>& chunks, bool need_t) {
 }
 
 int ensure_ws(cgpcm_handle* h) {
-  long need = (long)h->nhp * (round_up(h->chunk, 32) + 32) * h->nxp;
+  long need = (long)h->nhp * (round_up(chunk_cap(h), 32) + 32) * h->nxp;
   if (need > h->ws_elems) {
     if (h->wsA) { cudaFree(h->wsA); cudaFree(h->wsT); cudaFree(h->wsV); }
     h->wsA = h->wsT = h->wsV = nullptr;
@@ -964,9 +989,11 @@ int cgpcm_comm_init(cgpcm_handle* h, const void* id128, int rank, int world) {
 int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
   if (!h || !key) return -1;
   if (!strcmp(key, "chunk")) {
-    if (value < 8 || value > (1 << 20)) { h->err = "chunk out of range"; return -1; }
-    h->chunk = round_up((int)value, 32);
+    if (value > (1 << 20) || (value > 0 && value < 8)) { h->err = "chunk out of range"; return -1; }
+    h->chunk_auto = value <= 0;
+    if (!h->chunk_auto) h->chunk = round_up((int)value, 32);
     h->storeA_frozen_valid = false;
+    h->gram_valid = false;
     return 0;
   }
   if (!strcmp(key, "profile")) {
@@ -1058,7 +1085,7 @@ namespace cgimpl {
 
 int ensure_sweep_buffers(cgpcm_handle* h) {
   if (ensure_ws(h)) return -2;
-  int ys = std::max(16, (round_up(h->chunk, 32) + 32) * h->nxp / 8 / AHX_NSUB + 2);   // narrowest window = 8 columns; >= the 16 slices of gram_q
+  int ys = std::max(16, (round_up(chunk_cap(h), 32) + 32) * h->nxp / 8 / AHX_NSUB + 2);   // narrowest window = 8 columns; >= the 16 slices of gram_q
   if (ys > h->y_slices) {
     if (h->ypart) cudaFree(h->ypart);
     h->ypart = nullptr;

@@ -65,9 +65,10 @@ int cgpcm_comm_init(cgpcm_handle* h, const void* id128, int rank, int world);
 int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_local, const double* th,
                    const double* tx);
 
-/* Tuning knobs: "chunk" (observations per contraction chunk), "cull" (0 = dense; e > 0 = Psi entries whose
+/* Tuning knobs: "chunk" (workspace budget of a contraction chunk in observations x nx columns; 0 = default: the
+ * planner picks 512 / 1024 / 2048 per evaluation by its cost model), "cull" (0 = dense; e > 0 = Psi entries whose
  * Gaussian envelope is below exp(-e) are exactly 0 and whole windows of them are skipped; default 80),
- * "profile" (1 = CUDA events around every GEMM launch so that cgpcm_last_timing reports their sum),
+ * "profile" (1 = CUDA events around every run of consecutive GEMM launches so that cgpcm_last_timing reports their sum),
  * "store" (1 = default: keep the Ahx blocks and H*Ahx of the forward sweep resident in HBM for the backward sweep
  * when they fit -- 2 x 8 nh N nx bytes; 0 = always regenerate / recompute per chunk),
  * "sl" (1 = default: products with a small left operand run on the persistent bulk-copy kernel; 0 = tiled kernel),

@@ -14,7 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--n', type=int, default=100000)
 ap.add_argument('--m', type=int, default=200)
 ap.add_argument('--cull', type=float, default=0.0)
-ap.add_argument('--chunk', type=int, default=512)
+ap.add_argument('--chunk', type=int, default=0)
 ap.add_argument('--warmup', type=int, default=2)
 ap.add_argument('--mode', type=int, default=1)
 ap.add_argument('--shard', default='0/1', help='r/w: evaluate rank r\'s slice of the observations of a w-rank run (no communication)')
