@@ -32,7 +32,8 @@ from tests.workload import sweep_workload  # noqa: E402
 METRIC = 'VCGPCM ELBO+grad evals/sec (N=1e5, M=200)'
 UNIT = 'evals/s'
 FP64_PEAK_FALLBACK_TFLOPS = 37.16     # tools/fp64_peaks.cu on this pool's B200 (profiles/fp64_peaks_r01.json)
-TRAFFIC_SL_BYTES = 290.7e6            # dram__bytes_read + write of one dgemm_sl_kernel launch (profiles/r01_ncu_dgemm_sl.txt; 289.5e6 in r01_ncu_dgemm_sl_exact746.txt)
+TRAFFIC_SL_BYTES = 290.7e6            # dram__bytes_read + write of one dgemm_sl_kernel launch at chunk 512 (profiles/r01_ncu_dgemm_sl.txt)
+TRAFFIC_SL_BYTES_PLANNER = 1271.1e6   # the same launch (T1 = H A, 200 x 200 x 404352) at the planner's chunk (profiles/r01_ncu_dgemm_sl_exact746.txt)
 
 
 def parse():
@@ -357,12 +358,11 @@ def run_ours(args):
                      'kernel': 'FP64 DMMA (mma.sync m8n8k4.f64) contraction kernels: dgemm_sl_kernel (4 per chunk, '
                                'dominant), dgemm_sym_kernel (3 per chunk), dgemm_dmma_kernel (M x M algebra)',
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
-                     'traffic': TRAFFIC_SL_BYTES if (args.n == 100000 and args.m == 200 and args.chunk == 512) else None,
-                     'traffic_per': 'dgemm_sl_kernel launch of 200 x 200 x 102400 (chunk 512); the planner\'s chunks hold '
-                                    '2 - 4 x as many columns with the same bytes per column',
-                     'traffic_note': 'dram read + write bytes of one dgemm_sl_kernel launch (T1 = H A, 200 x 200 times '
-                                     '200 x ~102400: the same shape with and without windows) from the ncu --set full '
-                                     'captures in profiles/; algorithmic bytes of that launch: 328 MB',
+                     'traffic': (TRAFFIC_SL_BYTES_PLANNER if (args.chunk <= 0 and args.cull == 746.0) else
+                                 TRAFFIC_SL_BYTES if args.chunk == 512 else None) if (args.n == 100000 and args.m == 200) else None,
+                     'traffic_note': 'dram read + write bytes of one dgemm_sl_kernel launch (T1 = H A: 200 x 200 times '
+                                     '200 x 404352 at the planner\'s chunk, 200 x 102400 at chunk 512) from the ncu '
+                                     '--set full captures in profiles/; algorithmic bytes of that launch: 1294 MB / 328 MB',
                      'peak_source': peak_src,
                      'launches_per_step': gemm_launches / args.steps,
                      'flops_per_step': gemm_flops / args.steps,
