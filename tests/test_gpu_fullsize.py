@@ -50,8 +50,10 @@ def test_dense_equals_culled_and_terms_sum(wl, eng):
     eng.set_option('cull', 0.0)
     dense = eng.elbo_grad(wl['params'], reg=wl['reg'])
     eng.set_option('cull', 80.0)
-    # rounding noise of one evaluation is ~1e-11 relative here (cond(Kh) ~ 1/reg = 1e6 amplifies summation order)
-    assert abs(dense[0] - culled[0]) <= 2e-10 * abs(dense[0])
+    # two evaluations that differ only in their summation order (other chunk plans, windows, K-splits) differ by up to
+    # ~3e-10 relative here: cond(Kh) ~ 1/reg = 1e6 amplifies the order (observed spread over the plans of this round:
+    # -1039747.43782 .. -1039747.43811)
+    assert abs(dense[0] - culled[0]) <= 6e-10 * abs(dense[0])
     assert np.abs(dense[2] - culled[2]).max() <= 1e-9 * np.abs(dense[2]).max()
     assert dense[1].sum() == pytest.approx(dense[0], rel=1e-13)
     assert t_c['total_ms'] > 0
@@ -62,7 +64,7 @@ def test_dense_equals_culled_and_terms_sum(wl, eng):
     exact = eng.elbo_grad(wl['params'], reg=wl['reg'])
     t_e = eng.last_timing()
     eng.set_option('cull', 80.0)
-    assert abs(dense[0] - exact[0]) <= 2e-10 * abs(dense[0])
+    assert abs(dense[0] - exact[0]) <= 6e-10 * abs(dense[0])
     assert np.abs(dense[2] - exact[2]).max() <= 1e-9 * np.abs(dense[2]).max()
     assert t_e['gemm_flops'] < 0.5 * t_d['gemm_flops']
 
