@@ -90,7 +90,9 @@ def test_grad_mask_and_value_only():
 def test_chunking_and_culling_do_not_change_the_result(name):
     c = make_case(name)
     ref = _engine(c, cull=0.0, chunk=4096).elbo_grad(c['params'], reg=c['reg'])
-    for opts in [dict(cull=0.0, chunk=32), dict(cull=80.0, chunk=64), dict(cull=80.0, chunk=1024)]:
+    # chunk = 0: the planner's choice (512 / 1024 / 2048 columns x nx, window-snapped or not, by its cost model)
+    for opts in [dict(cull=0.0, chunk=32), dict(cull=80.0, chunk=64), dict(cull=80.0, chunk=1024), dict(cull=80.0, chunk=0),
+                 dict(cull=746.0, chunk=0)]:
         got = _engine(c, **opts).elbo_grad(c['params'], reg=c['reg'])
         assert abs(got[0] - ref[0]) <= 1e-11 * abs(ref[0]), opts
         assert np.abs(got[2] - ref[2]).max() <= 1e-10 * np.abs(ref[2]).max(), opts

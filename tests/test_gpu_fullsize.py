@@ -122,3 +122,26 @@ def test_oracle_parity_at_m200_through_the_large_shape_kernels():
         assert np.abs(t1 - t0).max() <= 1e-9 * scale + 3 * tn, opts
         assert np.abs(g1 - g0).max() <= 1e-9 * np.abs(g0).max() + 3 * gn, opts
         e.close()
+
+
+def test_chunk_planner_at_the_bench_shape(wl, eng):
+    """Option chunk = 0 (default): with exact-zero windows the planner takes larger chunks than 512 (fewer, longer GEMM
+    launches) for the same result up to the summation order; in the precomputed regime it plans the same chunks at
+    every evaluation (the resident Ahx blocks are laid out by the plan)."""
+    eng.set_option('cull', 746.0)
+    eng.set_option('chunk', 512)
+    fixed = eng.elbo_grad(wl['params'], reg=wl['reg'])
+    t_fixed = eng.last_timing()
+    eng.set_option('chunk', 0)
+    auto = eng.elbo_grad(wl['params'], reg=wl['reg'])
+    t_auto = eng.last_timing()
+    assert t_auto['gemm_launches'] < 0.5 * t_fixed['gemm_launches']
+    assert t_auto['gemm_flops'] < 1.2 * t_fixed['gemm_flops']
+    assert abs(auto[0] - fixed[0]) <= 6e-10 * abs(fixed[0])
+    assert np.abs(auto[2] - fixed[2]).max() <= 1e-9 * np.abs(fixed[2]).max()
+    eng.precompute(*wl['hyp'], reg=wl['reg'])
+    a = eng.elbo_grad(wl['params'], mode=cgpcm_b200.MODE_FROZEN, reg=wl['reg'])
+    b = eng.elbo_grad(wl['params'], mode=cgpcm_b200.MODE_FROZEN, reg=wl['reg'])
+    assert a[0] == b[0] and np.array_equal(a[2], b[2])
+    assert abs(a[0] - auto[0]) <= 2e-9 * abs(auto[0])           # frozen == full at the freeze point
+    eng.set_option('cull', 80.0)
