@@ -393,7 +393,7 @@ def run_ours(args):
                               'statistics at the same cull setting; device time, max over ranks'},
         'wall_s_timed_region': wall,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:           # the CPU leg runs beside the 1-GPU line only
         line['cpu_baseline'] = cpu_baseline_eval(wl, args.cpu_sample)
     print(json.dumps(line))
     if dist is not None:
