@@ -54,3 +54,33 @@ def test_gpu_reproduces_fixture(f):
     scale = max(abs(float(d['elbo_frozen'])), np.abs(d['terms_frozen']).max())
     assert abs(e - float(d['elbo_frozen'])) <= 1e-9 * scale
     assert np.abs(g - d['grad_frozen']).max() <= 1e-9 * np.abs(d['grad_frozen']).max()
+
+
+AKM_FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'akm', '*.npz')))
+
+
+@pytest.mark.parametrize('f', AKM_FILES, ids=[os.path.basename(f)[:-4] for f in AKM_FILES])
+def test_oracle_reproduces_akm_fixture(f):
+    """AKM.f() (src/core/cgpcm.py:382-392) from the reference's pair integrands: covariance and draw."""
+    d = _load(f)
+    om.PW_DISTS_EXACT = True
+    try:
+        f1, K1 = om.akm_f(d['params'], d['th'], float(d['reg']), d['t'], d['h'], d['e'], causal=bool(d['causal']))
+    finally:
+        om.PW_DISTS_EXACT = False
+    assert len(AKM_FILES) == 2
+    np.testing.assert_allclose(K1, d['K'], rtol=0, atol=1e-9 * np.abs(d['K']).max())
+    np.testing.assert_allclose(f1, d['f'], rtol=0, atol=1e-6 * np.abs(d['f']).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('f', AKM_FILES, ids=[os.path.basename(f)[:-4] for f in AKM_FILES])
+def test_gpu_reproduces_akm_fixture(f):
+    import cgpcm_b200
+    d = _load(f)
+    eng = cgpcm_b200.Engine(len(d['th']), len(d['tx']), causal=bool(d['causal']))
+    eng.set_data(np.zeros(1), np.zeros(1), d['th'], d['tx'])
+    f1, K1 = eng.akm_sample(d['params'], d['t'], d['h'], d['e'], reg=float(d['reg']), want_cov=True)
+    # tr(iKh Ahh) sums nh^2 products 1/reg times larger than the result (tests/test_gpu_akm.py)
+    assert np.abs(K1 - d['K']).max() <= 1e-6 * np.abs(d['K']).max()
+    assert np.abs(f1 - d['f']).max() <= 1e-6 * np.linalg.cond(d['K']) * np.abs(d['f']).max()

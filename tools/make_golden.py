@@ -32,3 +32,17 @@ for name in ['toy_test', 'ou', 'hrir', 'crude', 'sweep', 'sweep_hi', 'toy_acausa
                         sum_Ahx_y=m['sum_Ahx_y'].numpy(), elbo=e, terms=terms, grad=g,
                         params_frozen=p2, elbo_frozen=ef, terms_frozen=tf, grad_frozen=gf)
     print(name, e, ef)
+
+# AKM sampler (third part): covariance and draw of AKM.f() from the reference's pair integrands
+akm_dir = os.path.join(out_dir, 'akm')
+os.makedirs(akm_dir, exist_ok=True)
+for name in ['toy_small', 'toy_acausal_model']:
+    c = make_case(name)
+    rng = np.random.default_rng(4)
+    t = np.sort(rng.uniform(0., 1., 19))
+    h = c['params'][5:5 + c['nh']] + .3 * rng.standard_normal(c['nh'])
+    e = rng.standard_normal(19)
+    f, K = om.akm_f(c['params'], c['th'], c['reg'], t, h, e, causal=c['causal'])
+    np.savez_compressed(os.path.join(akm_dir, name + '.npz'), params=c['params'], th=c['th'], tx=c['tx'], reg=c['reg'],
+                        causal=c['causal'], t=t, h=h, e=e, f=f, K=K)
+    print('akm', name, np.abs(f).max())
