@@ -45,10 +45,17 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     const double djj = D[j][j];
     for (int r = j + 1 + tid; r < jb; r += blockDim.x) D[r][j] /= djj;
     __syncthreads();
-    const int m = jb - j - 1;
-    for (int e = tid; e < m * m; e += blockDim.x) {
-      int r = j + 1 + e / m, c = j + 1 + e % m;
-      if (c <= r) D[r][c] -= D[r][j] * D[c][j];
+    // trailing update of the block: thread (ty, tx) takes rows j + 1 + ty (+8 ..), column j + 1 + tx -- no index
+    // divisions (ncu: the e / m, e % m form of this loop was 36 k of the kernel's 47 k warp instructions, 70 k cycles
+    // per panel); every element still receives its updates in the order j = 0, 1, ..: the factor is bit-identical
+    {
+      const int tx = tid & 31, ty = tid >> 5;
+      const int cc = j + 1 + tx;
+      if (cc < jb) {
+        const double lc = D[cc][j];
+        for (int r = j + 1 + ty; r < jb; r += 8)
+          if (cc <= r) D[r][cc] -= D[r][j] * lc;
+      }
     }
     __syncthreads();
   }
