@@ -383,8 +383,14 @@ class VCGPCM(CGPCM):
         self.engine = Engine(self.nh, self.nx, causal=self.causal, causal_id=self.causal_id,
                              device=getattr(sess, 'device', 0))
         rank, world = getattr(sess, 'rank', 0), getattr(sess, 'world', 1)
+        # Every host-side random draw (mu_u, q(u) / prior samples, prediction noise, the slice sampler's angles) must
+        # be the SAME on every rank: the ranks contract their shards with these values and NCCL sums the partials.
+        # One process: numpy's global generator, as in the reference (np.random.seed controls it).  Several ranks: a
+        # private generator seeded with a value rank 0 draws from ITS global generator and broadcasts.
+        self._rng = np.random
         if world > 1:
             self._init_comm(rank, world)
+            self._rng = np.random.RandomState(self._shared_seed(rank))
         cost = None
         if world > 1:
             # balance the shards at the recipe's hyper-parameters and the library's default cull (80)
@@ -393,6 +399,12 @@ class VCGPCM(CGPCM):
         lo, hi = shard_bounds(self.n, rank, world, cost)
         self.engine.set_data(self.e.x[lo:hi], self.e.y[lo:hi], self.th, self.tx)
         self._init_inducing_points()
+        if world > 1:
+            # host LAPACK is not guaranteed to be bit-identical across ranks (thread counts differ): rank 0's q(u) wins
+            import torch.distributed as dist
+            box = [(self.vars['mu_u'].value, self.vars['var_u'].value) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self.vars['mu_u'].value, self.vars['var_u'].value = box[0][0].copy(), box[0][1].copy()
         self._cache = None
         self._frozen_hyp = None
 
@@ -401,6 +413,13 @@ class VCGPCM(CGPCM):
         box = [Engine.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         self.engine.comm_init(box[0], rank, world)
+
+    @staticmethod
+    def _shared_seed(rank):
+        import torch.distributed as dist
+        box = [int(np.random.randint(0, 2 ** 31 - 1)) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
 
     def _init_inducing_points(self):
         """``src/core/cgpcm.py:435-445``: ``mu_u ~ N(0, reg(iKh))``, ``var_u = tril_to_vec(chol(reg(iKh)))``.
@@ -414,7 +433,8 @@ class VCGPCM(CGPCM):
         iLh = np.linalg.solve(Lh, np.eye(self.nh))
         iKh = iLh.T @ iLh
         Lp = np.linalg.cholesky(iKh + r * np.eye(self.nh))
-        self.vars['mu_u'] = Var('mu_u', Lp @ np.random.randn(self.nh, 1))
+        self.vars['mu_u'] = Var('mu_u', Lp @ self._rng.randn(self.nh, 1))
+        self._prior_factor_cache = ((alpha, gamma, r), Lp)
         self.vars['var_u'] = Var('var_u', tril_to_vec(Lp))
 
     # -- parameter vector of the C-ABI
@@ -520,17 +540,26 @@ class VCGPCM(CGPCM):
 
     def sample_q(self):
         """A draw from q(u) = N(mu_u, reg(L L^T)) (``Normal.sample``, ``src/core/distribution.py:44-58``)."""
-        return self.vars['mu_u'].value.reshape(-1, 1) + self._q_cov_factor() @ np.random.randn(self.nh, 1)
+        return self.vars['mu_u'].value.reshape(-1, 1) + self._q_cov_factor() @ self._rng.randn(self.nh, 1)
+
+    def _prior_factor(self):
+        """Cholesky factor of ``reg(iKh)`` (``src/core/cgpcm.py:216-220``), cached per (alpha, gamma, reg): the slice
+        sampler asks for one prior draw per step and the factor only changes with the hyper-parameters."""
+        alpha, gamma, r = self.alpha.eval(), self.gamma.eval(), config.reg
+        cache = getattr(self, '_prior_factor_cache', None)
+        if cache is not None and cache[0] == (alpha, gamma, r):
+            return cache[1]
+        th = self.th
+        Kh = np.exp(-alpha * (th[:, None] ** 2 + th[None, :] ** 2) - gamma * (th[:, None] - th[None, :]) ** 2)
+        Lh = np.linalg.cholesky(Kh + r * np.eye(self.nh))
+        iLh = np.linalg.solve(Lh, np.eye(self.nh))
+        Lp = np.linalg.cholesky(iLh.T @ iLh + r * np.eye(self.nh))
+        self._prior_factor_cache = ((alpha, gamma, r), Lp)
+        return Lp
 
     def sample_prior(self):
         """A draw from the prior of ``K_u^-1 u``: ``N(0, reg(iKh))`` (``src/core/cgpcm.py:219-220``)."""
-        alpha, gamma = self.alpha.eval(), self.gamma.eval()
-        th = self.th
-        Kh = np.exp(-alpha * (th[:, None] ** 2 + th[None, :] ** 2) - gamma * (th[:, None] - th[None, :]) ** 2)
-        Lh = np.linalg.cholesky(Kh + config.reg * np.eye(self.nh))
-        iLh = np.linalg.solve(Lh, np.eye(self.nh))
-        Lp = np.linalg.cholesky(iLh.T @ iLh + config.reg * np.eye(self.nh))
-        return Lp @ np.random.randn(self.nh, 1)
+        return self._prior_factor() @ self._rng.randn(self.nh, 1)
 
     def elbo_smf(self, samples_h):
         """Monte-Carlo estimate of the SMF bound: ``(mean, standard error)`` (``src/core/cgpcm.py:594-608``)."""
@@ -542,7 +571,7 @@ class VCGPCM(CGPCM):
         from .sample import ESS
         if burn is None:
             burn = iters
-        ess = ESS(lambda x: self._evaluate_smf(x)[2], self.sample_prior)
+        ess = ESS(lambda x: self._evaluate_smf(x)[2], self.sample_prior, rng=self._rng)
         ess.move(self.vars['mu_u'].value.reshape(-1, 1))
         if burn > 0:
             ess.sample(burn)
@@ -600,7 +629,7 @@ class VCGPCM(CGPCM):
         else:
             samples = list(samples_h)
         samples = np.stack([np.asarray(x, dtype=np.float64).ravel() for x in samples])
-        noise = np.random.randn(t.shape[0], samples.shape[0])
+        noise = self._rng.randn(t.shape[0], samples.shape[0])
         return self.engine.filter_samples(self._pack(), t, samples, noise, reg=config.reg)       # [n, B]
 
     @staticmethod

@@ -130,6 +130,7 @@ struct cgpcm_handle {
   double cull = 80.0;       // 0 = dense
   bool chunk_auto = true;   // option "chunk" <= 0 (default): plan_chunks picks 512 / 1024 / 2048 by its cost model
   int profile = 0;          // 1 = CUDA events around every GEMM launch (roofline measurement)
+  int pw_dists = 0;         // 1 = prior kernels from |x|^2 - 2xy + |y|^2 as the reference forms them (psi_kernels.cuh)
   std::vector<cudaEvent_t> pev;
   size_t pev_used = 0;
   std::vector<char> pev_kind;  // per event pair: 0 = contraction GEMMs (a run of consecutive launches), 1 = Ahx generation
@@ -579,12 +580,13 @@ int axx_sweep(cgpcm_handle* h, const PsiConst& c, const BvnTab& T, bool tangents
       deg = bvn_make_cheb(T, B);
       CK(cudaMemcpyAsync(h->cheb_d, B, (size_t)(deg + 1) * 20 * sizeof(double), cudaMemcpyHostToDevice, h->st));
       smem = (size_t)(deg + 1) * (20 + BVN_PAIR_THREADS) * sizeof(double);
-      static bool attr_done = false;
-      if (!attr_done) {
+      static DeviceOnce attr_once;
+      unsigned long long attr_bit;
+      if (attr_once.need(&attr_bit)) {
         const int mx = (BVN_CHEB_MAXDEG + 1) * (20 + BVN_PAIR_THREADS) * 8;
         cudaFuncSetAttribute((const void*)axx_sum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute((const void*)axx_sum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        attr_done = true;
+        attr_once.done(attr_bit);
       }
     }
 #define CG_AXX(TG, HO)                                                                                            \
@@ -884,7 +886,7 @@ int prior_stage(cgpcm_handle* h, const PsiConst& c, double reg, bool reuse = fal
   // Kh0, Kh(+jitter) -> M_LH ; Kx0, Kx(+jitter) -> M_KX ; Ahh and tangents
   prior_kernels_kernel<<<148 * 2, 256, 0, h->st>>>(h->th, h->nh, ld, h->tx, h->nx, ld, reg, h->M(M_KH0), h->M(M_LH),
                                                     h->M(M_KX0), h->M(M_KX), h->M(M_AHH), h->M(M_DAHH_A),
-                                                    h->M(M_DAHH_G), c);
+                                                    h->M(M_DAHH_G), c, h->pw_dists);
   L(h);
   CK(cudaMemcpyAsync(h->M(M_LX), h->M(M_KX), ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
   if (chol_inv(h, h->M(M_LH), h->M(M_IKH), h->nh, h->nhp, nullptr, 1)) return -2;
@@ -1031,6 +1033,11 @@ int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
     if (!h->gram_opt && h->gram) { cudaFree(h->gram); h->gram = nullptr; h->gram_elems = 0; }
     return 0;
   }
+  if (!strcmp(key, "pw_dists")) {
+    h->pw_dists = value != 0.0;
+    h->prior_valid = false;
+    return 0;
+  }
   if (!strcmp(key, "sl")) {
     h->sl_opt = (int)value;
     return 0;
@@ -1149,7 +1156,7 @@ int cgpcm_psi(cgpcm_handle* h, const double hyp[3], double* sum_Axx, double* Ahh
   h->prior_valid = false;      // the slots of the prior kernels are overwritten below (without jitter)
   prior_kernels_kernel<<<148 * 2, 256, 0, h->st>>>(h->th, h->nh, ld, h->tx, h->nx, ld, 0.0, h->M(M_KH0), h->M(M_LH),
                                                     h->M(M_KX0), h->M(M_KX), h->M(M_AHH), h->M(M_DAHH_A),
-                                                    h->M(M_DAHH_G), c);
+                                                    h->M(M_DAHH_G), c, h->pw_dists);
   L(h);
   if (sum_Axx) {
     if (axx_sweep(h, c, T, false, h->M(M_AXX0))) return -2;
@@ -1311,6 +1318,10 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   }
   CK(cudaEventRecord(h->ev[2], st));
   const bool want_hyp = full && !freeze && grad && (grad_mask & (CGPCM_GRAD_ALPHA | CGPCM_GRAD_GAMMA | CGPCM_GRAD_OMEGA));
+  // Precomputed regime: the reference freezes `mats` only (src/core/cgpcm.py:270-284); Kx, Lx and the prior of q(u)
+  // (cgpcm.py:214-229) stay functions of the current (alpha, gamma, omega), so the value follows them (prior_stage
+  // rebuilds them when they change) and tf.gradients returns the derivative through them: no sweep is involved.
+  const bool want_hyp_prior = !full && grad && (grad_mask & (CGPCM_GRAD_ALPHA | CGPCM_GRAD_GAMMA | CGPCM_GRAD_OMEGA));
   if ((full || !h->gram_valid) && plan_store(h, chunks, want_hyp)) return -2;
   if (full) h->storeA_frozen_valid = false;      // a full-regime sweep overwrites the resident Ahx blocks
   if (!full && h->gram_valid) {
@@ -1537,12 +1548,13 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
       });
       L(h);
     }
-    if (want_hyp) {
+    if (want_hyp || want_hyp_prior) {
       // Sobar = 1/2 (iSo var iSo + (iSo mu)(iSo mu)^T - iSo)
       if (mm(h, h->M(M_ISO), false, h->M(M_VAR), false, h->M(M_T2), nhp, nhp, nhp)) return -2;
       if (mm(h, h->M(M_T2), false, h->M(M_ISO), false, h->M(M_T3), nhp, nhp, nhp)) return -2;
-      // iKhbar = -Hbar + 1/2 r N Ahh - 1/2 r Q + Sobar  -> M_T2
+      // iKhbar = -Hbar + 1/2 r N Ahh - 1/2 r Q + Sobar  -> M_T2   (precomputed regime: Sobar alone, the sums are constants)
       {
+        const double wsum = want_hyp ? 1.0 : 0.0;
         const double* t3 = h->M(M_T3);
         const double* iso = h->M(M_ISO);
         const double* ismu = h->V(V_ISOMU);
@@ -1551,7 +1563,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
         ew(st, l2, [=] __device__(long idx) {
           int i = (int)(idx / ld), j = (int)(idx % ld);
           double sobar = 0.5 * (t3[idx] + ismu[i] * ismu[j] - iso[idx]);
-          out[idx] = -hbar[idx] + 0.5 * r * bhh[idx] + sobar;
+          out[idx] = wsum * (-hbar[idx] + 0.5 * r * bhh[idx]) + sobar;
         });
         L(h);
       }
@@ -1574,9 +1586,13 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
         }, h->sc + S_G_KH_G);
         L(h, 2);
       }
-      // Kxbar = -iKx iKxbar iKx + Pbar + 1/2 iKx,  iKxbar = 1/2 r S
-      if (mm(h, h->M(M_IKX), false, S, false, h->M(M_T3), nxp, nxp, nxp)) return -2;
-      if (mm(h, h->M(M_T3), false, h->M(M_IKX), false, h->M(M_T2), nxp, nxp, nxp, -0.5 * r)) return -2;
+      // Kxbar = -iKx iKxbar iKx + Pbar + 1/2 iKx,  iKxbar = 1/2 r S   (precomputed regime: Pbar + 1/2 iKx)
+      if (want_hyp) {
+        if (mm(h, h->M(M_IKX), false, S, false, h->M(M_T3), nxp, nxp, nxp)) return -2;
+        if (mm(h, h->M(M_T3), false, h->M(M_IKX), false, h->M(M_T2), nxp, nxp, nxp, -0.5 * r)) return -2;
+      } else {
+        zero(h, h->M(M_T2), l2);
+      }
       {
         const double* t2 = h->M(M_T2);
         const double* pbar = h->M(M_PBAR);
@@ -1592,7 +1608,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
         L(h);
       }
       // <Ahhbar, dAhh>,  Ahhbar = 1/2 r N (iKh - m2)
-      {
+      if (want_hyp) {
         const double* ikh = h->M(M_IKH);
         const double* m2 = h->M(M_M2);
         const double* da = h->M(M_DAHH_A);
@@ -1608,7 +1624,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
         L(h, 2);
       }
       // <Axxbar, dAxx>,  Axxbar = r Pbar + 1/2 r iKx
-      {
+      if (want_hyp) {
         const double* pbar = h->M(M_PBAR);
         const double* ikx = h->M(M_IKX);
         for (int k3 = 0; k3 < 3; ++k3) {
@@ -1667,6 +1683,11 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     double g5[5] = {0, 0, 0, 0, 0};
     if (grad_mask & CGPCM_GRAD_S2) g5[0] = -r * rbar - c0 * c0bar - 0.5 * Ng + 0.5 * sum_y2 / s2;
     if (grad_mask & CGPCM_GRAD_S2F) g5[1] = r * rbar + 0.5 * c0 * c0bar;
+    if (want_hyp_prior) {
+      if (grad_mask & CGPCM_GRAD_ALPHA) g5[2] = alpha * hs[S_G_KH_A];
+      if (grad_mask & CGPCM_GRAD_GAMMA) g5[3] = gamma * hs[S_G_KH_G];
+      if (grad_mask & CGPCM_GRAD_OMEGA) g5[4] = omega * hs[S_G_KX_O];
+    }
     if (want_hyp) {
       const double abar = -0.5 * r * Ng;
       const double* gA = hs + S_COUNT + 2;
@@ -2172,7 +2193,7 @@ int filter_run(cgpcm_handle* h, const double* params_host, double reg, const dou
   PRC(gemm(h, true, false, false, nhp, ldn, nhp, 1.0, h->M(M_T1), ld, d_kuh, ldn, 0.0, d_a, ldn));
   PRC(gemm(h, false, false, false, ldn, ldn, nhp, -1.0, d_a, ldn, d_a, ldn, 1.0, d_ktt, ldn));
   {
-    cudaError_t e = potrf_lower(st, d_ktt, ldn, ldn, h->info, 5);
+    cudaError_t e = potrf_lower(st, d_ktt, ldn, ldn, h->info, 5, h->M(M_XW));
     L(h, 20);
     if (e != cudaSuccess) { h->err = "potrf launch failed"; cleanup(); return -2; }
   }
@@ -2256,7 +2277,7 @@ int akm_run(cgpcm_handle* h, const double* params_host, double reg, const double
     PCK(cudaMemcpy2DAsync(K_out, (size_t)n * sizeof(double), d_K, (size_t)ldn * sizeof(double), (size_t)n * sizeof(double),
                           n, cudaMemcpyDefault, st));
   {
-    cudaError_t e = potrf_lower(st, d_K, ldn, ldn, h->info, 6);
+    cudaError_t e = potrf_lower(st, d_K, ldn, ldn, h->info, 6, h->M(M_XW));
     L(h, 2 * ((ldn + LA_NB - 1) / LA_NB));
     if (e != cudaSuccess) { h->err = "potrf launch failed"; cleanup(); return -2; }
   }

@@ -23,6 +23,8 @@
 
 #include <algorithm>
 
+#include "device_once.cuh"
+
 namespace cg {
 
 constexpr int G_BM = 104;      // max rows per CTA tile
@@ -303,16 +305,17 @@ inline cudaError_t dgemm(cudaStream_t st, bool a_kc, bool b_kc, bool c_tr, int M
   dim3 grid((N + G_BN - 1) / G_BN, (M + rows - 1) / rows, splits);
   // last row tile exactly 12 blocks high (M = 200, 408, ...): use the 13 / 12 pair
   const bool pair12 = mb == 13 && (M - (int)(grid.y - 1) * rows) == 96;
-  static bool attr_done = false;
+  static DeviceOnce attr_once;
+  unsigned long long attr_bit;
 #define CG_ATTR(MBV, MBLV, AK, BK, CT) \
   cudaFuncSetAttribute((const void*)dgemm_dmma_kernel<MBV, MBLV, AK, BK, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
 #define CG_ATTR4(MBV, MBLV) CG_ATTR(MBV, MBLV, true, true, false) CG_ATTR(MBV, MBLV, true, false, false) \
   CG_ATTR(MBV, MBLV, false, false, false) CG_ATTR(MBV, MBLV, true, true, true)
-  if (!attr_done) {
+  if (attr_once.need(&attr_bit)) {
     CG_ATTR4(4, 4) CG_ATTR4(7, 7) CG_ATTR4(13, 13) CG_ATTR4(13, 12)
     CG_ATTR(13, 13, false, true, false) CG_ATTR(13, 13, true, false, true) CG_ATTR(13, 13, false, true, true)
     CG_ATTR(13, 13, false, false, true)
-    attr_done = true;
+    attr_once.done(attr_bit);
   }
 #undef CG_ATTR4
 #undef CG_ATTR

@@ -279,12 +279,13 @@ inline int dgemm_sl_blocks(int mb) { return mb <= 5 ? 5 : mb <= 9 ? 9 : mb <= 12
 
 template <int MB0, int MB1>
 inline void dgemm_sl_launch(cudaStream_t st, bool b_kc, const SlArgs& g, int sms, size_t smem) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  unsigned long long attr_bit;
+  if (attr_once.need(&attr_bit)) {
     const int mx = 232448;
     cudaFuncSetAttribute((const void*)dgemm_sl_kernel<MB0, MB1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute((const void*)dgemm_sl_kernel<MB0, MB1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    attr_done = true;
+    attr_once.done(attr_bit);
   }
   if (b_kc) dgemm_sl_kernel<MB0, MB1, true><<<sms, SL_NT, smem, st>>>(g);
   else dgemm_sl_kernel<MB0, MB1, false><<<sms, SL_NT, smem, st>>>(g);

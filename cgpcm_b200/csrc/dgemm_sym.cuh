@@ -314,13 +314,14 @@ inline cudaError_t dgemm_sym(cudaStream_t st, bool kc, int M, int K, const doubl
   dgemm_sym_pick(M, &G, &TB);
 #define CG_SYM_LAUNCH(GG, KS, TT)                                                                                      \
   do {                                                                                                             \
-    static bool attr_done = false;                                                                                 \
-    if (!attr_done) {                                                                                              \
+    static DeviceOnce attr_once;                                                                                   \
+    unsigned long long attr_bit;                                                                                   \
+    if (attr_once.need(&attr_bit)) {                                                                               \
       cudaFuncSetAttribute((const void*)dgemm_sym_kernel<true, GG, KS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            SymCfg<GG, TT>::SMEM_BYTES);                                                                \
       cudaFuncSetAttribute((const void*)dgemm_sym_kernel<false, GG, KS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            SymCfg<GG, TT>::SMEM_BYTES);                                                                \
-      attr_done = true;                                                                                            \
+      attr_once.done(attr_bit);                                                                                    \
     }                                                                                                              \
     constexpr int NT = (GG * (GG + 1) / 2 * KS + 1) * 32;                                                          \
     if (kc) dgemm_sym_kernel<true, GG, KS, TT><<<splits, NT, SymCfg<GG, TT>::SMEM_BYTES, st>>>(g);                         \

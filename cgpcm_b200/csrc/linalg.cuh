@@ -11,6 +11,10 @@
 //   potrf_lower   blocked right-looking Cholesky, NB = 32: a panel kernel (diagonal block factored in
 //                 shared memory by every CTA, row blocks solved one thread per row) + DMMA trailing
 //                 update.  Leaves a clean lower-triangular factor (upper triangle zeroed).
+//                 Every CTA of a panel launch reads the UNFACTORED diagonal block from A; CTA 0 therefore does not
+//                 write the factored block into A (a late-scheduled CTA would read it half-written) but into a
+//                 scratch slot, and the next panel launch copies it into place before doing anything else (the
+//                 last panel has a single CTA and writes A directly).  No launch is added.
 //   trtri_lower   inverse of the factor: diagonal blocks in shared memory, block rows by two DMMA GEMMs.
 //   cholinv       A^{-1} = X^T X with X = L^{-1}.
 #pragma once
@@ -23,12 +27,21 @@ constexpr int LA_ROWS = 128;  // panel rows per CTA
 
 // grid.x = 1 + ceil(rows_below / LA_ROWS); block = 256
 __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A, int np, long ld, int j0, int jb,
-                                                          int* __restrict__ info, int info_tag) {
+                                                          int* __restrict__ info, int info_tag,
+                                                          double* __restrict__ scratch, int flush_j0, int flush_jb,
+                                                          int defer) {
   __shared__ double D[LA_NB][LA_NB + 1];
   __shared__ double P[LA_ROWS][LA_NB + 1];
   __shared__ int bad;
   const int tid = threadIdx.x;
   if (tid == 0) bad = 0;
+  if (blockIdx.x == 0 && flush_jb > 0) {
+    // the previous panel's factored diagonal block: scratch -> A (nobody reads that block during this launch)
+    for (int e = tid; e < flush_jb * flush_jb; e += blockDim.x) {
+      int r = e / flush_jb, c = e % flush_jb;
+      A[(long)(flush_j0 + r) * ld + flush_j0 + c] = scratch[r * LA_NB + c];
+    }
+  }
   for (int e = tid; e < LA_NB * LA_NB; e += blockDim.x) {
     int r = e / LA_NB, c = e % LA_NB;
     D[r][c] = (r < jb && c < jb && c <= r) ? A[(long)(j0 + r) * ld + j0 + c] : (r == c ? 1.0 : 0.0);
@@ -63,7 +76,9 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     if (tid == 0 && bad && info) atomicCAS(info, 0, info_tag * 100000 + j0 + bad);
     for (int e = tid; e < jb * jb; e += blockDim.x) {
       int r = e / jb, c = e % jb;
-      A[(long)(j0 + r) * ld + j0 + c] = (c <= r) ? D[r][c] : 0.0;
+      const double v = (c <= r) ? D[r][c] : 0.0;
+      if (defer) scratch[r * LA_NB + c] = v;
+      else A[(long)(j0 + r) * ld + j0 + c] = v;
     }
     return;
   }
@@ -91,12 +106,17 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
   }
 }
 
-inline cudaError_t potrf_lower(cudaStream_t st, double* A, int np, long ld, int* info, int info_tag) {
+// scratch: LA_NB * LA_NB doubles (not aliased with A)
+inline cudaError_t potrf_lower(cudaStream_t st, double* A, int np, long ld, int* info, int info_tag, double* scratch) {
+  int flush_j0 = 0, flush_jb = 0;
   for (int j0 = 0; j0 < np; j0 += LA_NB) {
     int jb = np - j0 < LA_NB ? np - j0 : LA_NB;
     int below = np - j0 - jb;
     int nblk = 1 + (below + LA_ROWS - 1) / LA_ROWS;
-    potrf_panel_kernel<<<nblk, 256, 0, st>>>(A, np, ld, j0, jb, info, info_tag);
+    const int defer = nblk > 1;       // other CTAs of this launch read the unfactored block from A
+    potrf_panel_kernel<<<nblk, 256, 0, st>>>(A, np, ld, j0, jb, info, info_tag, scratch, flush_j0, flush_jb, defer);
+    flush_j0 = j0;
+    flush_jb = defer ? jb : 0;
     if (below > 0) {
       const double* Pn = A + (long)(j0 + jb) * ld + j0;
       double* C = A + (long)(j0 + jb) * ld + (j0 + jb);
@@ -185,7 +205,7 @@ inline cudaError_t cholinv(cudaStream_t st, double* A, double* Ainv, double* X, 
                            double* logdet_out, int* info, int info_tag) {
   int blocks = (int)(((long)np * np + 255) / 256);
   pad_block_kernel<<<blocks, 256, 0, st>>>(A, n, np, ld, 1.0);
-  cudaError_t e = potrf_lower(st, A, np, ld, info, info_tag);
+  cudaError_t e = potrf_lower(st, A, np, ld, info, info_tag, X);
   if (e != cudaSuccess) return e;
   if (logdet_out) logdet_kernel<<<1, 256, 0, st>>>(A, n, ld, logdet_out);
   if (Ainv) {

@@ -395,7 +395,12 @@ __global__ void ahx_user_kernel(const double* __restrict__ t, int n_obs, const d
 __global__ void prior_kernels_kernel(const double* __restrict__ th, int nh, long ldh, const double* __restrict__ tx,
                                      int nx, long ldx, double reg, double* __restrict__ Kh0, double* __restrict__ Kh,
                                      double* __restrict__ Kx0, double* __restrict__ Kx, double* __restrict__ Ahh,
-                                     double* __restrict__ dAhh_a, double* __restrict__ dAhh_g, const PsiConst c) {
+                                     double* __restrict__ dAhh_a, double* __restrict__ dAhh_g, const PsiConst c,
+                                     const int pw_dists) {
+  // pw_dists = 1: squared distances as the reference forms them, |x|^2 - 2 x y + |y|^2 (pw_dists2,
+  // src/core/tf_util.py:24-31, used by DEQ._call, src/core/kernel.py:43-46), operation by operation and without FMA
+  // contraction; default: (x - y)^2, the value that expression approximates (it loses ~eps x^2 gamma: 1e-7 relative at
+  // the crude-oil time stamps t ~ 2010).
   const long nh2 = ldh * ldh, nx2 = ldx * ldx;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < nh2 + nx2; idx += (long)gridDim.x * blockDim.x) {
     if (idx < nh2) {
@@ -404,7 +409,13 @@ __global__ void prior_kernels_kernel(const double* __restrict__ th, int nh, long
       if (i < nh && j < nh) {
         double ti = th[i], tj = th[j];
         double q2 = ti * ti + tj * tj, s = ti + tj;
-        k0 = exp(-c.alpha * q2 - c.gamma * (ti - tj) * (ti - tj));
+        if (pw_dists) {
+          const double n2x = __dmul_rn(ti, ti), n2y = __dmul_rn(tj, tj);
+          const double d2 = __dadd_rn(__dsub_rn(n2x, __dmul_rn(2.0, __dmul_rn(ti, tj))), n2y);
+          k0 = exp(__dsub_rn(__dmul_rn(-c.alpha, __dadd_rn(n2x, n2y)), __dmul_rn(c.gamma, d2)));
+        } else {
+          k0 = exp(-c.alpha * q2 - c.gamma * (ti - tj) * (ti - tj));
+        }
         // Ahh: D = 2B, b = -2 gamma s, cc = -B q2, E = cc + b^2/(4D), z = b / (2 sqrt D)
         double B = c.alpha + c.gamma, D = 2.0 * B;
         double b = -2.0 * c.gamma * s;
@@ -434,7 +445,12 @@ __global__ void prior_kernels_kernel(const double* __restrict__ th, int nh, long
       double k0 = 0.0;
       if (k < nx && l < nx) {
         double d = tx[k] - tx[l];
-        k0 = sqrt(1.5707963267948966 / c.omega) * exp(-0.5 * c.omega * d * d);
+        double d2 = d * d;
+        if (pw_dists) {
+          const double xk = tx[k], xl = tx[l];
+          d2 = __dadd_rn(__dsub_rn(__dmul_rn(xk, xk), __dmul_rn(2.0, __dmul_rn(xk, xl))), __dmul_rn(xl, xl));
+        }
+        k0 = sqrt(1.5707963267948966 / c.omega) * exp(-(0.5 * c.omega) * d2);
       }
       Kx0[id2] = k0;
       Kx[id2] = k0 + ((k == l && k < nx) ? reg : 0.0);

@@ -72,6 +72,9 @@ int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_
  * "store" (1 = default: keep the Ahx blocks and H*Ahx of the forward sweep resident in HBM for the backward sweep
  * when they fit -- 2 x 8 nh N nx bytes; 0 = always regenerate / recompute per chunk),
  * "sl" (1 = default: products with a small left operand run on the persistent bulk-copy kernel; 0 = tiled kernel),
+ * "pw_dists" (0 = default: the prior kernels Kh, Kx use (x - y)^2; 1 = they use |x|^2 - 2xy + |y|^2 exactly as the
+ * reference's pw_dists2 forms it, src/core/tf_util.py:24-31 -- for bit-level comparisons with the reference at inputs with a
+ * large offset, where that expression loses ~eps x^2 gamma, e.g. 1e-7 relative at decimal-year time stamps),
  * "gram" (0 = default: off; 1: cgpcm_precompute also builds the fourth-order tensor G = sum_n Ahx_n (x) Ahx_n, 8 (nh nx)^2
  * bytes, when it fits and pays, and MODE_FROZEN evaluations / fpi / SMF / predict_f contract with it instead of
  * sweeping over the observations; 2 = whenever it fits.  Opt-in because it is noisier: the cancellation against
@@ -85,7 +88,12 @@ int cgpcm_set_option(cgpcm_handle* h, const char* key, double value);
 int cgpcm_psi(cgpcm_handle* h, const double hyp[3], double* sum_Axx, double* Ahh, double* a, double* sum_Ahx_y,
               double* Ahx, double* Axx);
 
-/* mod.precompute() (src/core/cgpcm.py:270-284): freeze the Psi statistics at hyp for MODE_FROZEN. */
+/* mod.precompute() (src/core/cgpcm.py:270-284): freeze the Psi statistics at hyp for MODE_FROZEN.
+ * As in the reference, only `mats` (the sums over observations, evaluated at hyp) are frozen: the prior kernels Kh, Kx,
+ * their factors and the prior of q(u) (src/core/cgpcm.py:214-229) stay functions of the CURRENT alpha, gamma, omega
+ * of every later MODE_FROZEN call.  The value of such a call follows them, and its gradient entries for
+ * CGPCM_GRAD_ALPHA / GAMMA / OMEGA are the derivatives through those kernels (what tf.gradients returns on the
+ * precomputed graph) -- not zero, and consistent with the value. */
 int cgpcm_precompute(cgpcm_handle* h, const double hyp[3], double reg);
 
 /* One `sess.run([elbo, grad] + terms)` (src/core/cgpcm.py:518-575 through

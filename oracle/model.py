@@ -318,20 +318,28 @@ def elbo_full(params, t, y, th, tx, r, causal=True, psi='closed'):
     return elbo_from_mats(m, k, y.shape[0], torch.sum(y ** 2), s2, s2_f, mu_u, var_u, r)
 
 
-def elbo_and_grad(params, t, y, th, tx, r, causal=True, psi='closed', frozen=None):
+def elbo_and_grad(params, t, y, th, tx, r, causal=True, psi='closed', frozen=None, frozen_kernels='detached'):
     """(elbo, terms[7], grad) as numpy.  ``frozen``: a ``(mats, kernels)`` pair of *detached*
-    constants = the reference's precomputed regime (``cgpcm.py:270-284``): then only
-    ``log s2, log s2_f, mu_u, var_u`` receive gradient and the hyper entries of ``grad`` are 0."""
+    constants = the reference's precomputed regime (``cgpcm.py:270-284``).
+
+    ``frozen_kernels='symbolic'`` is exactly what the reference does: ``precompute()`` replaces ``mats`` only; the
+    prior kernels ``Kx, Lx, iKh`` (``cgpcm.py:214-229``) stay functions of the current ``alpha, gamma, omega``, so the
+    value follows them and their gradient entries are not zero.  ``'detached'`` (the round-1 behaviour, kept for the
+    tests of the q(u)-only training phases, which never move the hyper-parameters) also holds the kernels of the
+    freeze point: then only ``log s2, log s2_f, mu_u, var_u`` receive gradient."""
     p = T(np.asarray(params, np.float64)).clone().requires_grad_(True)
     if frozen is None:
         e, terms = elbo_full(p, t, y, th, tx, r, causal, psi)
     else:
         m, k = frozen
         nh = len(th)
-        s2, s2_f, _, _, _, mu_u, var_u = unpack(p, nh)
+        s2, s2_f, alpha, gamma, omega, mu_u, var_u = unpack(p, nh)
+        if frozen_kernels == 'symbolic':
+            k = prior_kernels(th, tx, alpha, gamma, omega, r)
         yy = T(y)
         e, terms = elbo_from_mats(m, k, yy.shape[0], torch.sum(yy ** 2), s2, s2_f, mu_u, var_u, r)
-    g, = torch.autograd.grad(e, p)
+    g, = torch.autograd.grad(e, p, allow_unused=True)
+    g = torch.zeros_like(p) if g is None else g
     return float(e.detach()), np.array([float(x.detach()) for x in terms]), g.numpy().copy()
 
 

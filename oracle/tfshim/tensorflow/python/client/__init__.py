@@ -1,0 +1,1 @@
+"""Part of the TensorFlow stand-in under oracle/tfshim (TEST INFRASTRUCTURE ONLY)."""

@@ -68,9 +68,19 @@ def test_frozen_regime(name):
     p[1] -= .2
     p[5:] *= 1 + .05 * rng.standard_normal(p.shape[0] - 5)
     want = om.elbo_and_grad(p, c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'], frozen=fr)
-    got = eng.elbo_grad(p, mode=MODE_FROZEN, grad_mask=GRAD_ALL, reg=c['reg'])
+    qmask = GRAD_S2 | GRAD_S2F | GRAD_MU_U | GRAD_VAR_U          # what the precomputed training phases optimise
+    got = eng.elbo_grad(p, mode=MODE_FROZEN, grad_mask=qmask, reg=c['reg'])
     _check(got, want, name)
     assert np.all(got[2][2:5] == 0)
+    # all entries: in the reference only `mats` are frozen (src/core/cgpcm.py:270-284); the prior kernels stay
+    # functions of (alpha, gamma, omega), so tf.gradients through Kx, Lx and the prior of q(u) is not zero -- and the
+    # value follows the hyper-parameters when they move away from the freeze point
+    p[2:5] += np.array([.05, -.03, .04])
+    want = om.elbo_and_grad(p, c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'], frozen=fr,
+                            frozen_kernels='symbolic')
+    got = eng.elbo_grad(p, mode=MODE_FROZEN, grad_mask=GRAD_ALL, reg=c['reg'])
+    _check(got, want, name)
+    assert np.all(got[2][2:5] != 0)
 
 
 def test_grad_mask_and_value_only():

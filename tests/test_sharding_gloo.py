@@ -79,7 +79,10 @@ def _worker(rank, world, port, q):
         mod = cg.VCGPCM.from_recipe(sess, cgpcm_b200.Data(c['t'], c['y']), nx=c['nx'], nh=c['nh'], tau_w=.1,
                                     tau_f=.05, causal=True)
         uid, r, w = FakeEngine.ids[0]
-        q.put((rank, err, sess.rank, sess.world, uid[:15], r, w, mod.engine.n, mod.n))
+        # every host-side random draw must be identical on all ranks although they seed np.random differently
+        draws = np.concatenate([mod.vars['mu_u'].value.ravel(), mod.vars['var_u'].value.ravel(),
+                                mod.sample_q().ravel(), mod.sample_prior().ravel(), mod._rng.uniform(0, 1, 3)])
+        q.put((rank, err, sess.rank, sess.world, uid[:15], r, w, mod.engine.n, mod.n, draws.tobytes()))
     finally:
         dist.destroy_process_group()
 
@@ -96,7 +99,8 @@ def test_two_rank_reduction_and_bootstrap():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err, srank, sworld, uid, r, w, n_local, n in res:
+    assert res[0][9] == res[1][9], 'random draws differ between ranks'
+    for rank, err, srank, sworld, uid, r, w, n_local, n, _ in res:
         assert err < 1e-13                       # reduced partials == partials of the whole series
         assert (srank, sworld, r, w) == (rank, world, rank, world)
         assert uid == b'id-from-rank-0\0'        # every rank joined with rank 0's id

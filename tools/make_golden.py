@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz: seeded inputs and the CPU oracle's outputs (Psi sums, ELBO, 7 terms, gradient;
-full and frozen regime) at the named shapes.  The reference itself cannot run in this image (Python 2 +
-TensorFlow 1.x + bvn-cdf), so the vectors come from the oracle restatement, which is pinned by
-the reference's own known-answer tests (tests/test_oracle_golden.py) and by quadrature / scipy / mpmath.
+full and frozen regime) at the named shapes, with exact squared distances in the prior kernels (the product's
+default arithmetic).  The vectors of the REFERENCE'S OWN CODE on the same inputs are tests/golden/ref/*.npz
+(tools/make_ref_golden.py); tests/test_ref_parity.py holds the oracle to them.
 Run:  python tools/make_golden.py
 """
 import os
@@ -24,7 +24,9 @@ for name in ['toy_test', 'ou', 'hrir', 'crude', 'sweep', 'sweep_hi', 'toy_acausa
     p2 = c['params'].copy()
     p2[0] += .25
     p2[5:] *= 1.03
-    ef, tf, gf = om.elbo_and_grad(p2, c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'], frozen=fr)
+    # the reference freezes `mats` only: the prior kernels stay functions of the hyper-parameters (oracle/model.py)
+    ef, tf, gf = om.elbo_and_grad(p2, c['t'], c['y'], c['th'], c['tx'], c['reg'], c['causal'], frozen=fr,
+                                  frozen_kernels='symbolic')
     m = fr[0]
     np.savez_compressed(os.path.join(out_dir, name + '.npz'), t=c['t'], y=c['y'], th=c['th'], tx=c['tx'],
                         hyp=np.array(c['hyp']), reg=c['reg'], causal=c['causal'], params=c['params'],
