@@ -61,7 +61,10 @@ def test_train_schedule_toy():
     got_terms = np.array(sess.run([tm['tensor'] for tm in terms]))
     scale = np.abs(want[1]).max()
     assert np.abs(got_terms - want[1]).max() <= 1e-9 * scale + 3 * tnoise, (got_terms, want[1], tnoise)
-    assert abs(want[0] - e_post) <= 1e-9 * scale + 3 * enoise
+    # the ELBO is the sum of the 7 terms: its bar is the sum of theirs (the sampled noise of the sum alone is a 4-trial
+    # estimate and has been seen a few per cent below the actual difference); tests/test_gpu_quad.py compares both
+    # sides with a quad-precision evaluation at trained points
+    assert abs(want[0] - e_post) <= 1e-9 * scale + 3 * max(enoise, 7 * tnoise)
     gsel = mod._evaluate(True, ['mu_u', 'var_u', 's2_f', 's2', 'gamma', 'omega', 'alpha'])[2]
     assert np.abs(gsel - want[2]).max() <= 1e-9 * np.abs(want[2]).max() + 3 * gnoise, gnoise
     mats = mod.mats
