@@ -27,13 +27,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from tests.workload import sweep_workload  # noqa: E402
+from tests.workload import NAMED_SHAPES, named_workload, sweep_workload  # noqa: E402
 
 METRIC = 'VCGPCM ELBO+grad evals/sec (N=1e5, M=200)'
 UNIT = 'evals/s'
 FP64_PEAK_FALLBACK_TFLOPS = 37.16     # tools/fp64_peaks.cu on this pool's B200 (profiles/fp64_peaks_r01.json)
-TRAFFIC_SL_BYTES = 290.7e6            # dram__bytes_read + write of one dgemm_sl_kernel launch at chunk 512 (profiles/r01_ncu_dgemm_sl.txt)
-TRAFFIC_SL_BYTES_PLANNER = 1271.1e6   # the same launch (T1 = H A, 200 x 200 x 404352) at the planner's chunk (profiles/r01_ncu_dgemm_sl_exact746.txt)
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed summary of
+    the latest `ncu --set full` capture of the bench command (profiles/traffic.json, written by tools/ncu_summary.py)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
 
 
 def parse():
@@ -49,7 +57,16 @@ def parse():
                          'those that are exactly 0.0 in IEEE double (their Gaussian envelope exp(E), E < -745.2, '
                          'underflows); 0 = every tile multiplied, 80 = envelope < exp(-80) dropped; both reported beside')
     ap.add_argument('--chunk', type=int, default=0, help='0 = the library default: chosen per evaluation by the planner')
-    ap.add_argument('--cpu-sample', type=int, default=300, help='observations in the CPU baseline sample')
+    ap.add_argument('--cpu-sample', type=int, default=3000,
+                    help='observations in the CPU baseline sample of our arm (oracle port; large enough that the M^3 '
+                         'algebra does not dominate)')
+    ap.add_argument('--ref-sample', type=int, default=96,
+                    help='observations per step of the reference arm (the reference\'s own code, oracle/_ref: it '
+                         'materialises N x nx x nx tensors and keeps them for autodiff)')
+    ap.add_argument('--mode', default='sharded', choices=['sharded', 'restarts'],
+                    help='sharded: one evaluation, observations sharded over the GPUs (the headline); restarts: '
+                         'independent restarts / hyper-parameter batches, one replica per GPU, no communication')
+    ap.add_argument('--shape', default='sweep', help='restarts mode: sweep | toy | ou | hrir | crude | all')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -110,12 +127,27 @@ class ClockSampler(object):
         return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_baseline_eval(wl, sample, steps=1, warmup=0):
-    """Times the CPU oracle (numpy / torch-CPU restatement of the reference's algorithm) on the first
-    `sample` observations of the workload; the cost is linear in N, so evals/s at N = sample / N of that."""
+# ----------------------------------------------------------------------------- CPU baselines
+def host_threads():
+    """All the host threads the CPU arms may use: set explicitly, also under torchrun (which exports
+    OMP_NUM_THREADS=1 to every rank)."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    return max(1, n)
+
+
+def cpu_port_eval(wl, sample, steps=1, warmup=0):
+    """Times the CPU oracle PORT (oracle/model.py: numpy / torch-CPU restatement of the reference's algorithm with
+    closed-form Psi statistics, chunk-free) on the first `sample` observations of the workload with every host thread.
+    The cost of the path is linear in N (the M^3 algebra is a fixed 0.3 s at M = 200); evals/s at N is stated with the
+    extrapolation factor N / sample."""
     import torch
     from oracle import model as om
+    threads = host_threads()
+    torch.set_num_threads(threads)
     sl = slice(0, sample)
     times = []
     for it in range(warmup + steps):
@@ -125,11 +157,38 @@ def cpu_baseline_eval(wl, sample, steps=1, warmup=0):
         if it >= warmup:
             times.append(dt)
     per_eval_s = float(np.mean(times)) * wl['n'] / sample
-    return {'value': 1.0 / per_eval_s, 'unit': UNIT, 'cores': int(torch.get_num_threads()), 'kind': 'port',
-            'sample': 'oracle (numpy/torch-CPU FP64 restatement of the reference) on the first %d of %d observations, '
-                      'nh=nx=%d, full regime; %.2f s per sample evaluation, scaled linearly to N'
-                      % (sample, wl['n'], wl['nh'], float(np.mean(times))),
-            'seconds_per_sample_eval': float(np.mean(times))}
+    return {'value': 1.0 / per_eval_s, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': 'oracle port (numpy/torch-CPU FP64 restatement of the reference, closed-form Psi statistics) on the '
+                      'first %d of %d observations, nh=nx=%d, full regime, %d torch threads; %.2f s per sample '
+                      'evaluation, extrapolated x%.1f to N' % (sample, wl['n'], wl['nh'], threads,
+                                                              float(np.mean(times)), wl['n'] / sample),
+            'seconds_per_sample_eval': float(np.mean(times)), 'extrapolation_factor': wl['n'] / sample}
+
+
+def cpu_reference_eval(wl, sample, steps=1, warmup=1):
+    """Times the REFERENCE'S OWN CODE (oracle/_ref: py3-patched copies of /root/reference/src on the TensorFlow stand-in
+    oracle/tfshim, torch-CPU FP64 underneath; built by oracle/build_ref.py) through its own API --
+    VCGPCM.from_recipe, mod.elbo(), tf.gradients -- on the first `sample` observations, in a process of its own.
+    The reference materialises N x nx x nx and N x nh x nx tensors and keeps every intermediate for autodiff, so the
+    sample is what fits; its cost is linear in N."""
+    from oracle import ref
+    threads = host_threads()
+    sl = slice(0, sample)
+    t, m = wl['t'], wl['nh']
+    r = ref.call(threads=threads, timeout=3000, t=t[sl], y=wl['y'][sl], nx=m, nh=m, tau_w=.1, tau_f=.025, causal=True,
+                 causal_id=False, reg=wl['reg'], params=wl['params'], tx_range=np.array([t.min(), t.max()]),
+                 time=max(1, steps) + warmup, want_mats=False)
+    if not (np.array_equal(r['th'], wl['th']) and np.array_equal(r['tx'], wl['tx'])):
+        raise RuntimeError('reference recipe does not reproduce the workload\'s inducing inputs')
+    secs = np.asarray(r['seconds'])[warmup:]
+    per_eval_s = float(np.mean(secs)) * wl['n'] / sample
+    return {'value': 1.0 / per_eval_s, 'unit': UNIT, 'cores': threads, 'kind': 'reference',
+            'sample': "the reference's own code (oracle/_ref = /root/reference/src, py3-patched, on a torch-CPU TensorFlow "
+                      'stand-in) on the first %d of %d observations, nh=nx=%d, full regime: sess.run([elbo, '
+                      'tf.gradients]) %.2f s per sample evaluation with %d threads (graph construction excluded), '
+                      'extrapolated x%.1f to N' % (sample, wl['n'], m, float(np.mean(secs)), threads, wl['n'] / sample),
+            'seconds_per_sample_eval': float(np.mean(secs)), 'extrapolation_factor': wl['n'] / sample,
+            'elbo_of_sample': float(r['elbo'])}
 
 
 def run_reference(args):
@@ -137,17 +196,29 @@ def run_reference(args):
     if rank != 0:
         return
     wl = sweep_workload(args.n, args.m)
-    sample = args.cpu_sample
-    cb = cpu_baseline_eval(wl, sample, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    from oracle import ref
+    if ref.available():
+        cb = cpu_reference_eval(wl, args.ref_sample, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        port = None
+        try:
+            port = cpu_port_eval(wl, args.cpu_sample)
+        except Exception as exc:            # the port beside it is informative only
+            port = {'error': repr(exc)}
+    else:
+        cb = cpu_port_eval(wl, args.cpu_sample, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        port = None
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / cb['value'], 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': 'scaling sweep N=%d, nh=nx=%d, causal VCGPCM, full regime' % (args.n, args.m),
-                       'n': args.n, 'nh': args.m, 'nx': args.m},
+                       'n': args.n, 'nh': args.m, 'nx': args.m,
+                       'extrapolation_factor': cb['extrapolation_factor']},
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'note': 'the reference itself (Python 2 + TensorFlow 1.x + bvn-cdf) cannot run here; this is the CPU '
-                    'oracle port of its algorithm on %d host threads' % cb['cores']}
+            'note': 'CPU arm on %d host threads, kind = %s; each step evaluates a bounded sample of the observations '
+                    'and the rate is scaled to N (cost linear in N)' % (cb['cores'], cb['kind'])}
+    if port is not None:
+        line['cpu_baseline_port'] = port
     print(json.dumps(line))
 
 
@@ -297,7 +368,9 @@ def run_ours(args):
     eng.precompute(*wl['hyp'], reg=wl['reg'])
     fms = []
     for i in range(4):
-        eng.elbo_grad(p_h, mode=cgpcm_b200.MODE_FROZEN, reg=wl['reg'], out_grad=g_h)
+        # the unit SURVEY.md 8d names for the precomputed regime: gradient w.r.t. log s2, log s2_f, mu_u, var_u
+        eng.elbo_grad(p_h, mode=cgpcm_b200.MODE_FROZEN, reg=wl['reg'], out_grad=g_h,
+                      grad_mask=cgpcm_b200.GRAD_S2 | cgpcm_b200.GRAD_S2F | cgpcm_b200.GRAD_MU_U | cgpcm_b200.GRAD_VAR_U)
         if i >= 1:
             fms.append(eng.last_timing()['total_ms'])
     fdev = torch.tensor(fms, dtype=torch.float64, device='cuda')
@@ -329,6 +402,21 @@ def run_ours(args):
         if dist is not None:
             dist.destroy_process_group()
         return
+    # the sharded result against the unsharded one, same inputs, same process: rank 0 evaluates the whole series on a
+    # second handle without a communicator (outside every timed region)
+    elbo_vs_n1 = grad_vs_n1 = None
+    if world > 1:
+        eng.close()
+        del flush
+        torch.cuda.empty_cache()
+        eng1 = cgpcm_b200.Engine(args.m, args.m, causal=True, device=local_rank)
+        eng1.set_option('chunk', args.chunk)
+        eng1.set_option('cull', args.cull)
+        eng1.set_data(wl['t'], wl['y'], wl['th'], wl['tx'])
+        e1, _, g1 = eng1.elbo_grad(wl['params'], reg=wl['reg'])
+        elbo_vs_n1 = abs(last[0] - e1) / max(abs(e1), float(np.abs(last[1]).max()))
+        grad_vs_n1 = float(np.abs(last[2] - g1).max() / np.abs(g1).max())
+        eng1.close()
     peak, peak_src, peak_raw = fp64_peak()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     n, m = args.n, args.m
@@ -358,16 +446,18 @@ def run_ours(args):
                      'kernel': 'FP64 DMMA (mma.sync m8n8k4.f64) contraction kernels: dgemm_sl_kernel (4 per chunk, '
                                'dominant), dgemm_sym_kernel (3 per chunk), dgemm_dmma_kernel (M x M algebra)',
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
-                     'traffic': (TRAFFIC_SL_BYTES_PLANNER if (args.chunk <= 0 and args.cull == 746.0) else
-                                 TRAFFIC_SL_BYTES if args.chunk == 512 else None) if (args.n == 100000 and args.m == 200) else None,
-                     'traffic_note': 'dram read + write bytes of one dgemm_sl_kernel launch (T1 = H A: 200 x 200 times '
-                                     '200 x 404352 at the planner\'s chunk, 200 x 102400 at chunk 512) from the ncu '
-                                     '--set full captures in profiles/; algorithmic bytes of that launch: 1294 MB / 328 MB',
+                     'traffic': ((ncu_traffic() or {}).get('dgemm_sl_kernel_T1_bytes_per_launch')
+                                 if (args.n == 100000 and args.m == 200 and args.chunk <= 0 and args.cull == 746.0
+                                     and world == 1) else None),
+                     'traffic_note': (ncu_traffic() or {}).get('note'),
                      'peak_source': peak_src,
                      'launches_per_step': gemm_launches / args.steps,
                      'flops_per_step': gemm_flops / args.steps,
                      'avg_launch_ms': gemm_ms / max(1, gemm_launches),
                      'share_of_step': gemm_ms / total_ms if total_ms else None,
+                     # algorithmic GEMM flops of the step over the WHOLE step time (Psi kernels, M x M algebra,
+                     # collectives and launch gaps included) against the same peak, per GPU
+                     'whole_step_frac': (gemm_flops / (total_ms * 1e-3) / 1e12 / peak) if (total_ms and peak) else None,
                      'flops_executed_per_step': gemm_flops_exec / args.steps,
                      'note': 'MEASURED_PEAKS.json has no FP64 figure; peak = FP64 tensor (DMMA) rate measured by '
                              'tools/fp64_peaks.cu; flops are algorithmic: 2 K M N per launch, K M (M + 1) for the '
@@ -384,6 +474,7 @@ def run_ours(args):
                      'note': 'the statistics are never materialised: Axx is reduced in registers, Ahx is written once '
                              '(8 N nh nx bytes) for the contractions'},
         'elbo': last[0],
+        'elbo_rel_diff_vs_n1': elbo_vs_n1, 'grad_rel_diff_vs_n1': grad_vs_n1,
         'other_window_settings': other,
         'frozen_regime': {'value': frozen_value, 'unit': UNIT,
                           'note': 'Psi sums frozen by precompute(); gradient w.r.t. log s2, log s2_f, mu_u, var_u'},
@@ -394,8 +485,97 @@ def run_ours(args):
         'wall_s_timed_region': wall,
     }
     if not args.no_cpu_baseline and world == 1:           # the CPU leg runs beside the 1-GPU line only
-        line['cpu_baseline'] = cpu_baseline_eval(wl, args.cpu_sample)
+        line['cpu_baseline'] = cpu_port_eval(wl, args.cpu_sample)
     print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- independent restarts (replicas)
+def run_restarts(args):
+    """`--mode restarts`: independent restarts / hyper-parameter batches, one replica (handle) per GPU and no
+    communication (BASELINE.json north_star; the reference's unit is one controller.py process per resample index,
+    src/experiment_toy.sh:7-11).  Every replica evaluates its own parameter vector (a different seed per task) at the
+    requested shape(s); the aggregate evaluations/s is the sum over GPUs (weak scaling).  Under torchrun every rank is
+    one replica; in a single process with --gpus N the replicas are driven by cgpcm_b200.batch.run, one host thread
+    per GPU."""
+    import torch
+    import cgpcm_b200
+    from cgpcm_b200 import batch
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    shapes = (['sweep'] + list(NAMED_SHAPES)) if args.shape == 'all' else [args.shape]
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def workload(shape, seed):
+        wl = sweep_workload(args.n, args.m, seed=seed) if shape == 'sweep' else named_workload(shape, seed=seed)
+        return wl
+
+    def replica(shape, seed, device, steps, warmup):
+        """One restart: its own handle, data and variables; returns (device ms per step list, elbo)."""
+        wl = workload(shape, seed)
+        eng = cgpcm_b200.Engine(wl['nh'], wl['nx'], causal=True, device=device)
+        eng.set_option('cull', args.cull)
+        eng.set_data(wl['t'], wl['y'], wl['th'], wl['tx'])
+        out = None
+        for _ in range(warmup):
+            out = eng.elbo_grad(wl['params'], reg=wl['reg'])
+        ms, launches = [], 0
+        for _ in range(steps):
+            out = eng.elbo_grad(wl['params'], reg=wl['reg'])
+            tm = eng.last_timing()
+            ms.append(tm['total_ms'])
+            launches += tm['launches']
+        eng.close()
+        return ms, out[0], launches
+
+    res = {}
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for shape in shapes:
+        steps = args.steps if shape == 'sweep' else max(args.steps, 50)
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            w0 = time.perf_counter()
+            ms, elbo, launches = replica(shape, rank, local_rank, steps, args.warmup)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - w0
+            tt = torch.tensor([sum(ms), wall, float(launches)], dtype=torch.float64, device='cuda')
+            mx = tt.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tt.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            dev_s, n_rep, launches = float(mx[0]) * 1e-3, world, int(sm[2])
+        else:
+            devices = list(range(args.gpus))
+            tasks = [(lambda sess, k=k: replica(shape, k, sess.device, steps, args.warmup)) for k in range(args.gpus)]
+            outs = batch.run(tasks, devices=devices)
+            dev_s = max(sum(o[0]) for o in outs) * 1e-3
+            n_rep, launches = len(outs), sum(o[2] for o in outs)
+            elbo = outs[0][1]
+        res[shape] = {'value': n_rep * steps / dev_s, 'unit': UNIT, 'replicas': n_rep, 'steps_per_replica': steps,
+                      'ms_per_step_per_replica': dev_s * 1e3 / steps, 'gpu_launches': launches, 'elbo_replica0': elbo}
+    clocks = sampler.stop()
+    if rank == 0:
+        head = res[shapes[0]]
+        n_gpus = world if world > 1 else args.gpus
+        line = {'metric': 'VCGPCM ELBO+grad evals/sec, independent restarts (one replica per GPU, no communication)',
+                'value': head['value'], 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': head['ms_per_step_per_replica'], 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'mode': 'restarts',
+                'config': {'workload': 'independent restarts at shape %s (N=%d, M=%d for the sweep), full regime, one '
+                                       'replica per GPU, a different seed per replica' % (shapes[0], args.n, args.m),
+                           'cull': args.cull,
+                           'driver': 'torchrun ranks' if world > 1 else 'cgpcm_b200.batch.run, one host thread per GPU'},
+                'gpu_launches': head['gpu_launches'], 'clocks': clocks, 'shapes': res}
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -404,6 +584,8 @@ def main():
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.mode == 'restarts':
+        run_restarts(args)
     else:
         run_ours(args)
 

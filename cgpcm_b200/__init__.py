@@ -4,7 +4,7 @@ Drop-in for ONE path of wesselb/cgpcm (``VCGPCM.from_recipe`` / ``precompute`` /
 ``learn.minimise_lbfgs``); all arithmetic runs in ``lib/libcgpcm_b200.so`` (hand-written sm_100a CUDA,
 FP64) behind the C-ABI of ``include/cgpcm_b200.h``.  There is no CPU fallback.
 """
-from . import config, learn, sample, util
+from . import batch, config, experiment, learn, sample, util
 from .cgpcm import VCGPCM, CGPCM, AKM, Session, Var, Objective, shard_bounds, window_costs, window_radius
 from .data import Data, UncertainData
 from .engine import Engine, bvn_cdf, TERM_NAMES, n_params

@@ -20,8 +20,8 @@ GRAD_S2, GRAD_S2F, GRAD_ALPHA, GRAD_GAMMA, GRAD_OMEGA, GRAD_MU_U, GRAD_VAR_U = [
 GRAD_ALL = 0x7f
 MODE_FROZEN, MODE_FULL = 0, 1
 
-EXPORTS = ['cgpcm_create', 'cgpcm_destroy', 'cgpcm_last_error', 'cgpcm_comm_unique_id', 'cgpcm_comm_init',
-           'cgpcm_set_data', 'cgpcm_set_option', 'cgpcm_psi', 'cgpcm_precompute', 'cgpcm_elbo_grad', 'cgpcm_elbo_smf', 'cgpcm_predict_f', 'cgpcm_kernel_samples', 'cgpcm_filter_samples', 'cgpcm_akm_sample', 'cgpcm_fpi',
+EXPORTS = ['cgpcm_create', 'cgpcm_destroy', 'cgpcm_last_error', 'cgpcm_device_count', 'cgpcm_comm_unique_id', 'cgpcm_comm_init',
+           'cgpcm_set_data', 'cgpcm_set_option', 'cgpcm_psi', 'cgpcm_precompute', 'cgpcm_elbo_grad', 'cgpcm_elbo_smf', 'cgpcm_predict_f', 'cgpcm_kernel_samples', 'cgpcm_filter_samples', 'cgpcm_akm_sample', 'cgpcm_fpi', 'cgpcm_fpi_qz', 'cgpcm_elbo_qz',
            'cgpcm_last_timing', 'cgpcm_bvn_cdf', 'cgpcm_dgemm', 'cgpcm_dgemm_sym', 'cgpcm_cholinv', 'cgpcm_math_test']
 
 
@@ -68,6 +68,7 @@ def lib():
     L.cgpcm_destroy.argtypes = [vp]
     L.cgpcm_last_error.argtypes = [vp]
     L.cgpcm_last_error.restype = ctypes.c_char_p
+    L.cgpcm_device_count.argtypes = [ctypes.POINTER(i32)]
     L.cgpcm_comm_unique_id.argtypes = [vp]
     L.cgpcm_comm_init.argtypes = [vp, vp, i32, i32]
     L.cgpcm_set_data.argtypes = [vp, dp, dp, i64, dp, dp]
@@ -81,6 +82,8 @@ def lib():
     L.cgpcm_filter_samples.argtypes = [vp, dp, dbl, dp, i64, dp, ctypes.c_int32, dp, dp]
     L.cgpcm_akm_sample.argtypes = [vp, dp, dbl, dp, i64, dp, dp, dp, dp]
     L.cgpcm_fpi.argtypes = [vp, dp, ctypes.c_int32, ctypes.c_int32, dbl, dp, dp, dp, dp]
+    L.cgpcm_fpi_qz.argtypes = [vp, dp, dp, dp, ctypes.c_int32, ctypes.c_int32, dbl, dp, dp, dp, dp]
+    L.cgpcm_elbo_qz.argtypes = [vp, dp, dp, dp, dbl, dp, dp]
     L.cgpcm_last_timing.argtypes = [vp, dp]
     L.cgpcm_bvn_cdf.argtypes = [dp, dp, dp, dp, ctypes.c_size_t, vp]
     L.cgpcm_dgemm.argtypes = [i32, i32, i32, i32, i32, i32, dbl, dp, i64, dp, i64, dbl, dp, i64, i32, i64, i32, vp]

@@ -101,6 +101,27 @@ class Objective(object):
         return self.sign * e, self.sign * self.mod._slice_grad(g, names)
 
 
+class QzObjective(object):
+    """``elbo(z=False)`` (``src/core/cgpcm.py:518-575``): the bound saturated for q(u) as a lazy scalar.  Value and
+    terms; no task of the reference optimises q(z) directly, and no gradient is provided."""
+
+    def __init__(self, mod, sign=1.0):
+        self.mod, self.sign = mod, sign
+
+    def __neg__(self):
+        return QzObjective(self.mod, -self.sign)
+
+    def _run(self):
+        return self.mod._evaluate_qz()
+
+    def eval(self):
+        return self.sign * self._run()[0]
+
+    def value_and_grad(self, var_list):
+        raise NotImplementedError('the gradient of elbo(z=False) is not available: train q(u) with z=True '
+                                  '(experiment.train does), or iterate fpi(z=False)')
+
+
 class SmfObjective(object):
     """``elbo(smf=True, sample=...)`` (``src/core/cgpcm.py:527-531``) as a lazy scalar; no gradient."""
 
@@ -287,8 +308,6 @@ class AKM(CGPCM):
 
     def __init__(self, **kw_args):
         CGPCM.__init__(self, **kw_args)
-        if self.causal_id:
-            raise NotImplementedError('causal_id=True is not on the accelerated path (no task enables it)')
         self.th = np.ascontiguousarray(self.th, dtype=np.float64)
         self.nh = self.th.shape[0]
         # the engine wants a noise side: eight dummy inducing inputs and omega = 1, none of which the AKM's
@@ -296,6 +315,7 @@ class AKM(CGPCM):
         self.engine = Engine(self.nh, 8, causal=self.causal, causal_id=False, device=getattr(self.sess, 'device', 0))
         self.engine.set_data(np.zeros(1), np.zeros(1), self.th, np.linspace(0., 1., 8))
         self.h_draw = self.e_draw = self.t = None
+        self._rng = getattr(self.sess, 'rng', None) or np.random
 
     def _pack5(self):
         return np.array([float(self.vars['s2'].value), float(self.vars['s2_f'].value), float(self.vars['alpha'].value),
@@ -313,14 +333,14 @@ class AKM(CGPCM):
     def sample_h(self, h=None):
         """Sample filter (``cgpcm.py:353-362``); ``h``: a draw in the parametrisation of the filter."""
         if h is None:
-            self.h_draw = self._prior_factor() @ np.random.randn(self.nh, 1)
+            self.h_draw = self._prior_factor() @ self._rng.randn(self.nh, 1)
         else:
             self.h_draw = np.asarray(h, dtype=np.float64).reshape(self.nh, 1)
 
     def sample_f(self, t):
         """Sample function (``cgpcm.py:364-371``)."""
         self.t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
-        self.e_draw = np.random.randn(self.t.shape[0], 1)
+        self.e_draw = self._rng.randn(self.t.shape[0], 1)
 
     def sample(self, t, h=None):
         """Sample filter and function (``cgpcm.py:373-380``)."""
@@ -352,7 +372,7 @@ class AKM(CGPCM):
         from .data import Data
         from .util import fft_spectrum
         t = np.asarray(getattr(t, 'x', t), dtype=np.float64).ravel()
-        hs = (self._prior_factor() @ np.random.randn(self.nh, int(iters))).T
+        hs = (self._prior_factor() @ self._rng.randn(self.nh, int(iters))).T
         samples = self.engine.kernel_samples(self._pack5(), t, hs, reg=config.reg)                # [n, iters]
         x = t
         if psd:
@@ -372,8 +392,6 @@ class VCGPCM(CGPCM):
         CGPCM.__init__(self, **kw_args)
         if np.size(self.tx) == 0:
             raise ValueError('nx must be positive')
-        if self.causal_id:
-            raise NotImplementedError('causal_id=True is not on the accelerated path (no task enables it)')
         self.th = np.ascontiguousarray(self.th, dtype=np.float64)
         self.tx = np.ascontiguousarray(self.tx, dtype=np.float64)
         self.nh, self.nx = self.th.shape[0], self.tx.shape[0]
@@ -387,7 +405,7 @@ class VCGPCM(CGPCM):
         # be the SAME on every rank: the ranks contract their shards with these values and NCCL sums the partials.
         # One process: numpy's global generator, as in the reference (np.random.seed controls it).  Several ranks: a
         # private generator seeded with a value rank 0 draws from ITS global generator and broadcasts.
-        self._rng = np.random
+        self._rng = getattr(sess, 'rng', None) or np.random       # batch.run gives every task a private generator
         if world > 1:
             self._init_comm(rank, world)
             self._rng = np.random.RandomState(self._shared_seed(rank))
@@ -402,9 +420,11 @@ class VCGPCM(CGPCM):
         if world > 1:
             # host LAPACK is not guaranteed to be bit-identical across ranks (thread counts differ): rank 0's q(u) wins
             import torch.distributed as dist
-            box = [(self.vars['mu_u'].value, self.vars['var_u'].value) if rank == 0 else None]
+            names = ('mu_u', 'var_u', 'mu_z', 'var_z')
+            box = [tuple(self.vars[k].value for k in names) if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
-            self.vars['mu_u'].value, self.vars['var_u'].value = box[0][0].copy(), box[0][1].copy()
+            for k, v in zip(names, box[0]):
+                self.vars[k].value = v.copy()
         self._cache = None
         self._frozen_hyp = None
 
@@ -436,6 +456,14 @@ class VCGPCM(CGPCM):
         self.vars['mu_u'] = Var('mu_u', Lp @ self._rng.randn(self.nh, 1))
         self._prior_factor_cache = ((alpha, gamma, r), Lp)
         self.vars['var_u'] = Var('var_u', tril_to_vec(Lp))
+        # q(z) (cgpcm.py:447-456): mu_z ~ N(0, reg(iKx)), var_z = tril_to_vec(chol(reg(iKx))); only the z = False
+        # variants read it before convert() assigns it
+        omega, tx = self.omega.eval(), self.tx
+        Kx = (.5 * np.pi / omega) ** .5 * np.exp(-.5 * omega * (tx[:, None] - tx[None, :]) ** 2) + r * np.eye(self.nx)
+        iLx = np.linalg.solve(np.linalg.cholesky(Kx), np.eye(self.nx))
+        Lz = np.linalg.cholesky(iLx.T @ iLx + r * np.eye(self.nx))
+        self.vars['mu_z'] = Var('mu_z', Lz @ self._rng.randn(self.nx, 1))
+        self.vars['var_z'] = Var('var_z', tril_to_vec(Lz))
 
     # -- parameter vector of the C-ABI
     def _pack(self):
@@ -492,7 +520,13 @@ class VCGPCM(CGPCM):
         (``src/core/cgpcm.py:518-575``).  ``smf=True``: the stochastic SMF bound at ``sample`` (a fresh draw from
         q(u) per evaluation if ``None``); value only."""
         if not z:
-            raise NotImplementedError('only the bound saturated for q(z) (z=True) is accelerated')
+            if smf:
+                raise NotImplementedError('the SMF bound is only available saturated for q(z) (z=True)')
+            obj = QzObjective(self)
+            names = ['s2 complexity', 'p(u) complexity', 'q*(u) complexity', 'q*(u) fit',
+                     'general conditioning penalty', 'q(z conditioning penalty', '-KL[q(u)||p(u)]']   # sic: cgpcm.py:559-564
+            terms = [{'name': nm, 'tensor': Term(obj, i), 'modifier': '.2e'} for i, nm in enumerate(names)]
+            return obj, terms
         if smf:
             obj = SmfObjective(self, sample)
             terms = [{'name': nm, 'tensor': Term(obj, i), 'modifier': '.2e'} for i, nm in enumerate(TERM_NAMES)]
@@ -501,21 +535,35 @@ class VCGPCM(CGPCM):
         terms = [{'name': nm, 'tensor': Term(obj, i), 'modifier': '.2e'} for i, nm in enumerate(TERM_NAMES)]
         return obj, terms
 
-    def _fpi(self, num, high_reg):
+    def _with_frozen_stats(self, fn):
         temporary = not self._precomputed
         if temporary:                      # symbolic mats in the reference = statistics at the current hyper-parameters
             self.precompute()
         try:
-            return self.engine.fpi(self._pack(), num, high_reg=high_reg, reg=config.reg)
+            return fn()
         finally:
             if temporary:
                 self.undo_precompute()
+
+    def _fpi(self, num, high_reg, z=True):
+        if z:
+            return self._with_frozen_stats(lambda: self.engine.fpi(self._pack(), num, high_reg=high_reg, reg=config.reg))
+        return self._with_frozen_stats(lambda: self.engine.fpi_qz(
+            self._pack(), self.vars['mu_z'].value, self.vars['var_z'].value, num, high_reg=high_reg, reg=config.reg))
+
+    def _evaluate_qz(self):
+        return self._with_frozen_stats(lambda: self.engine.elbo_qz(
+            self._pack(), self.vars['mu_z'].value, self.vars['var_z'].value, reg=config.reg))
 
     def fpi(self, num=50, z=True, high_reg=False):
         """Fixed-point iteration on q(u) (``src/core/cgpcm.py:479-516``): ``num`` rounds of optimal q(z) given q(u),
         optimal q(u) given q(z); assigns ``mu_u`` and ``var_u``."""
         if not z:
-            raise NotImplementedError('fpi on q(z) (z=False) is not on the accelerated path')
+            # fixed-point iteration on q(z): q(z) -> optimal q(u) -> optimal q(z); assigns mu_z and var_z
+            _, _, mu_z, var_z = self._fpi(num, high_reg, z=False)
+            self.vars['mu_z'].value = mu_z.reshape(self.vars['mu_z'].value.shape)
+            self.vars['var_z'].value = var_z
+            return
         mu_u, var_u, _, _ = self._fpi(num, high_reg)
         self.vars['mu_u'].value = mu_u.reshape(self.vars['mu_u'].value.shape)
         self.vars['var_u'].value = var_u
@@ -524,7 +572,12 @@ class VCGPCM(CGPCM):
     def convert(self, z=True):
         """Assign q(z) after optimising q(u) (``src/core/cgpcm.py:577-592``): ``vars['mu_z']``, ``vars['var_z']``."""
         if not z:
-            raise NotImplementedError('convert(z=False) is not on the accelerated path')
+            # assign q(u) after optimising q(z)
+            mu_u, var_u, _, _ = self._fpi(0, False, z=False)
+            self.vars['mu_u'].value = mu_u.reshape(self.vars['mu_u'].value.shape)
+            self.vars['var_u'].value = var_u
+            self._cache = None
+            return
         _, _, mu_z, var_z = self._fpi(0, False)
         self.vars['mu_z'] = Var('mu_z', mu_z.reshape(-1, 1))
         self.vars['var_z'] = Var('var_z', var_z)

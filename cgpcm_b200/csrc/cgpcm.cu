@@ -99,7 +99,7 @@ enum Vec { V_MU, V_YTMU, V_LAM, V_LBAR, V_ISOMU, V_MUBAR, V_YLBAR, V_M2BMU, V_MU
 enum Sc {
   S_LOGDET_KX, S_LOGDET_P, S_LOGDET_SO, S_LOGDET_VAR, S_TR_IKH_AHH, S_TR_IKX_AXX, S_TR_IKH_Q, S_TR_BHH_M2,
   S_TR_ISO_VAR, S_MU_ISO_MU, S_LAM_LBAR, S_PBAR_S, S_C0BAR, S_G_KH_A, S_G_KH_G, S_G_KX_O, S_G_AHH_A,
-  S_G_AHH_G, S_G_AXX_A, S_G_AXX_G, S_G_AXX_O, S_LOGDET_P0, S_LAM_LBAR0, S_S_BHH_S, S_COUNT
+  S_G_AHH_G, S_G_AXX_A, S_G_AXX_G, S_G_AXX_O, S_LOGDET_P0, S_LAM_LBAR0, S_S_BHH_S, S_LOGDET_KH, S_COUNT
 };
 
 struct Chunk {
@@ -572,7 +572,7 @@ int axx_sweep(cgpcm_handle* h, const PsiConst& c, const BvnTab& T, bool tangents
   dim3 grid(ntiles, slices);
   if (h->n_local > 0) {
     // pair-hoisted Genz branch: causal model, rho >= 0.925 (rho = gamma / A is always positive here)
-    const bool hoist = c.causal && T.high && T.rho > 0.0 && T.as_ > 0.0 && T.ng == 20;
+    const bool hoist = c.causal && !c.causal_id && T.high && T.rho > 0.0 && T.as_ > 0.0 && T.ng == 20;
     int deg = 0;
     size_t smem = 0;
     if (hoist) {
@@ -889,7 +889,7 @@ int prior_stage(cgpcm_handle* h, const PsiConst& c, double reg, bool reuse = fal
                                                     h->M(M_DAHH_G), c, h->pw_dists);
   L(h);
   CK(cudaMemcpyAsync(h->M(M_LX), h->M(M_KX), ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-  if (chol_inv(h, h->M(M_LH), h->M(M_IKH), h->nh, h->nhp, nullptr, 1)) return -2;
+  if (chol_inv(h, h->M(M_LH), h->M(M_IKH), h->nh, h->nhp, h->sc + S_LOGDET_KH, 1)) return -2;
   if (chol_inv(h, h->M(M_LX), h->M(M_IKX), h->nx, h->nxp, h->sc + S_LOGDET_KX, 2)) return -2;
   h->prior_key[0] = c.alpha; h->prior_key[1] = c.gamma; h->prior_key[2] = c.omega; h->prior_key[3] = reg;
   h->prior_valid = true;      // withdrawn by the caller when the info word reports a failed factorisation
@@ -921,7 +921,6 @@ int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int
   h->ld = std::max(h->nhp, h->nxp);
   h->causal = causal ? 1 : 0;
   h->causal_id = causal_id ? 1 : 0;
-  if (causal_id) { delete h; return -1; }   // never enabled by any task
   auto fail = [&](int code) { cgpcm_destroy(h); return code; };
   if (cudaSetDevice(device) != cudaSuccess) return fail(-2);
   if (cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->sms < 2) h->sms = 148;
@@ -977,6 +976,14 @@ int cgpcm_destroy(cgpcm_handle* h) {
 
 const char* cgpcm_last_error(const cgpcm_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
+int cgpcm_device_count(int* out) {
+  if (!out) return -1;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); *out = 0; return -2; }
+  *out = count;
+  return 0;
+}
+
 int cgpcm_comm_unique_id(void* id128) {
   if (!id128) return -1;
   if (!nccl().ok) return -2;
@@ -1009,6 +1016,7 @@ int cgpcm_comm_init(cgpcm_handle* h, const void* id128, int rank, int world) {
 
 int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
   if (!h || !key) return -1;
+  cudaSetDevice(h->device);
   if (!strcmp(key, "chunk")) {
     if (value > (1 << 20) || (value > 0 && value < 8)) { h->err = "chunk out of range"; return -1; }
     h->chunk_auto = value <= 0;
@@ -1148,7 +1156,7 @@ int cgpcm_psi(cgpcm_handle* h, const double hyp[3], double* sum_Axx, double* Ahh
   if (ensure_sweep_buffers(h)) return -2;
   h->launches = 0;
   PsiConst c;
-  psi_make_const(hyp[0], hyp[1], hyp[2], h->causal, h->cull, &c);
+  psi_make_const(hyp[0], hyp[1], hyp[2], h->causal, h->cull, &c, h->causal_id);
   BvnTab T;
   bvn_make_tab(hyp[1] / (hyp[0] + hyp[1] + hyp[2]), &T);
   CK(cudaEventRecord(h->ev[0], h->st));
@@ -1252,7 +1260,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   h->gemm_launches = 0;
 
   PsiConst c;
-  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c, h->causal_id);
   BvnTab T;
   bvn_make_tab(gamma / (alpha + gamma + omega), &T);
   const PsiConst& ca = full ? c : h->fc;       // constants that generate A
@@ -1708,8 +1716,11 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
 // Psi statistics: num rounds of  q(u) -> optimal q(z) -> optimal q(u)  (Normal.from_natural,
 // src/core/distribution.py:20-33), then the optimal q(z) of the final q(u).  Per round one C1-type sweep
 // (sum_n A_n^T m2_u A_n) and one Q-type sweep (sum_n A_n m2_z A_n^T) over the resident Ahx blocks.
+// `qz_mean` / `qz_chol` (host, nx and nx (nx + 1) / 2 values, or NULL): the z = False variants -- the iteration starts
+// from the explicit q(z) = N(qz_mean, reg(Lz Lz^T)), every round is  q(z) -> optimal q(u) -> optimal q(z), and the
+// closing half round is convert(z=False): the optimal q(u) of the final q(z)  (cgpcm.py:499,584-592).
 int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, double reg, double* mu_u, double* var_u,
-            double* mu_z, double* var_z) {
+            double* mu_z, double* var_z, const double* qz_mean = nullptr, const double* qz_chol = nullptr) {
   const int nh = h->nh, nx = h->nx, nhp = h->nhp, nxp = h->nxp;
   const long ld = h->ld, l2 = ld * ld;
   const long nvar = (long)nh * (nh + 1) / 2;
@@ -1728,7 +1739,7 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
   h->gemm_flops = h->gemm_flops_exec = 0.0;
   h->gemm_launches = 0;
   PsiConst c;
-  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c, h->causal_id);
   std::vector<Chunk> chunks;
   plan_chunks(h, h->fc, chunks);
   cudaStream_t st = h->st;
@@ -1757,8 +1768,34 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
     });
     L(h);
   }
-  for (int it = 0; it <= num; ++it) {
-    // optimal q(z) given q(u)
+  const bool start_z = qz_mean != nullptr && qz_chol != nullptr;
+  if (start_z) {
+    // q(z) from the caller: mean, and covariance reg(Lz Lz^T) into M_PINV (the slot the q(z) covariance lives in)
+    const long nvz = (long)nx * (nx + 1) / 2;
+    for (long i = 0; i < nx; ++i)
+      if (!std::isfinite(qz_mean[i])) { h->err = "non-finite mu_z"; return -4; }
+    for (long i = 0; i < nvz; ++i)
+      if (!std::isfinite(qz_chol[i])) { h->err = "non-finite var_z"; return -4; }
+    CK(cudaMemsetAsync(muz, 0, ld * sizeof(double), st));
+    CK(cudaMemcpyAsync(muz, qz_mean, nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->gvar_d, qz_chol, nvz * sizeof(double), cudaMemcpyHostToDevice, st));
+    double* Lz = h->M(M_T1);
+    const double* pz = h->gvar_d;
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      Lz[idx] = (i < nx && j <= i) ? pz[(long)i * (i + 1) / 2 + j] : 0.0;
+    });
+    L(h);
+    if (mm(h, Lz, false, Lz, true, h->M(M_PINV), nxp, nxp, nxp)) return -2;
+    double* vz = h->M(M_PINV);
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      if (i == j && i < nx) vz[idx] += reg;
+    });
+    L(h);
+  }
+  // one half round each: A = optimal q(z) given q(u) (z = True), B = optimal q(u) given q(z) (z = False)
+  auto half_a = [&](double hrz) -> int {
     ew(st, l2, [=] __device__(long idx) {
       int i = (int)(idx / ld), j = (int)(idx % ld);
       Hm[idx] = var[idx] + mu[i] * mu[j];
@@ -1771,7 +1808,6 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
       const double* kx = h->M(M_KX);
       const double* fb = h->M(M_F_AXX);      // frozen sum_Bxx
       const double* c1 = h->M(M_C1);
-      const double hrz = it < num ? hr : 0.0;      // convert() (the last half round) never uses high_reg
       ew(st, l2, [=] __device__(long idx) {
         int i = (int)(idx / ld), j = (int)(idx % ld);
         Pm[idx] = kx[idx] + r * (fb[idx] + c1[idx]) + ((i == j && i < nx) ? hrz + reg : 0.0);
@@ -1781,8 +1817,9 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
     if (chol_inv(h, h->M(M_LP), h->M(M_PINV), nx, nxp, nullptr, 3)) return -2;
     matvec(h, h->M(M_F_Y), nx, nh, 1, mu, c0, h->V(V_LAM));                  // lam = c0 Y^T mean_u
     matvec(h, h->M(M_PINV), nx, nx, 0, h->V(V_LAM), 1.0, muz);               // mean_z = var_z lam
-    if (it == num) break;
-    // optimal q(u) given q(z)
+    return 0;
+  };
+  auto half_b = [&](double hru) -> int {
     {
       double* W = h->M(M_WX);
       const double* vz = h->M(M_PINV);
@@ -1802,13 +1839,26 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
       const double* q = h->M(M_Q);
       ew(st, l2, [=] __device__(long idx) {
         int i = (int)(idx / ld), j = (int)(idx % ld);
-        Pu[idx] = kh0[idx] + r * (fb[idx] + q[idx]) + ((i == j && i < nh) ? reg + hr + reg : 0.0);   // Kh = reg(Kh0)
+        Pu[idx] = kh0[idx] + r * (fb[idx] + q[idx]) + ((i == j && i < nh) ? reg + hru + reg : 0.0);   // Kh = reg(Kh0)
       });
       L(h);
     }
     if (chol_inv(h, h->M(M_SO), var, nh, nhp, nullptr, 4)) return -2;
     matvec(h, h->M(M_F_Y), nh, nx, 0, muz, c0, h->V(V_LAM));                 // lam = c0 Y mean_z
     matvec(h, var, nh, nh, 0, h->V(V_LAM), 1.0, mu);                         // mean_u = var_u lam (padding stays 0)
+    return 0;
+  };
+  for (int it = 0; it <= num; ++it) {
+    const double hr_round = it < num ? hr : 0.0;      // convert() (the last half round) never uses high_reg
+    if (!start_z) {
+      if (half_a(hr_round)) return -2;
+      if (it == num) break;
+      if (half_b(hr)) return -2;
+    } else {
+      if (half_b(hr_round)) return -2;
+      if (it == num) break;
+      if (half_a(hr)) return -2;
+    }
   }
   // outputs: means, and the Cholesky factors of the covariances in np.tril_indices order
   auto emit = [&](const double* mean, const double* cov, int n, int npad, double* mean_out, double* chol_out, int tag) -> int {
@@ -1858,6 +1908,150 @@ int fpi_run(cgpcm_handle* h, const double* params_host, int num, int high_reg, d
   return 0;
 }
 
+// VCGPCM.elbo(z=False) (src/core/cgpcm.py:518-575 with the z = False branches :533-540,547-566 and _optimal_q(z=False)
+// :470-477): the bound saturated for q(u), with q(z) = N(mu_z, reg(Lz Lz^T)) the explicit variational distribution.
+// Value and the 7 terms, on the Psi statistics frozen by cgpcm_precompute (the prior kernels follow params, as in
+// evaluate()).  The one sum over observations is the Q-type sweep  sum_n A_n m2_z A_n^T.
+int qz_run(cgpcm_handle* h, const double* params_host, const double* qz_mean, const double* qz_chol, double reg,
+           double* elbo, double* terms) {
+  const int nh = h->nh, nx = h->nx, nhp = h->nhp, nxp = h->nxp;
+  const long ld = h->ld, l2 = ld * ld;
+  const long nvz = (long)nx * (nx + 1) / 2;
+  for (long i = 0; i < 5; ++i)
+    if (!std::isfinite(params_host[i])) { h->err = "non-finite parameter"; return -4; }
+  for (long i = 0; i < nx; ++i)
+    if (!std::isfinite(qz_mean[i])) { h->err = "non-finite mu_z"; return -4; }
+  for (long i = 0; i < nvz; ++i)
+    if (!std::isfinite(qz_chol[i])) { h->err = "non-finite var_z"; return -4; }
+  if (!h->frozen) { h->err = "cgpcm_elbo_qz requires cgpcm_precompute"; return -1; }
+  const double s2 = exp(params_host[0]), s2f = exp(params_host[1]);
+  const double alpha = exp(params_host[2]), gamma = exp(params_host[3]), omega = exp(params_host[4]);
+  const double r = s2f / s2, c0 = sqrt(s2f) / s2;
+  if (ensure_sweep_buffers(h)) return -2;
+  h->launches = 0;
+  h->pev_used = 0;
+  h->prof_open = false;
+  h->gemm_flops = h->gemm_flops_exec = 0.0;
+  h->gemm_launches = 0;
+  PsiConst c;
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c, h->causal_id);
+  std::vector<Chunk> chunks;
+  plan_chunks(h, h->fc, chunks);
+  cudaStream_t st = h->st;
+  CK(cudaEventRecord(h->ev[0], st));
+  CK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
+  if (prior_stage(h, c, reg, true)) return -2;
+  if (!h->gram_valid && plan_store(h, chunks, false)) return -2;
+  double* muz = h->V(V_MUZ);
+  double* varz = h->M(M_VAR);          // covariance of q(z) (the q(u) slots are free in this evaluation)
+  double* m2z = h->M(M_M2);
+  {
+    CK(cudaMemsetAsync(muz, 0, ld * sizeof(double), st));
+    CK(cudaMemcpyAsync(muz, qz_mean, nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->gvar_d, qz_chol, nvz * sizeof(double), cudaMemcpyHostToDevice, st));
+    double* Lz = h->M(M_LQ);
+    const double* pz = h->gvar_d;
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      Lz[idx] = (i < nx && j <= i) ? pz[(long)i * (i + 1) / 2 + j] : 0.0;
+    });
+    L(h);
+    if (mm(h, Lz, false, Lz, true, varz, nxp, nxp, nxp)) return -2;
+    double* lvar = h->M(M_LVAR);
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      const double v = varz[idx] + ((i == j && i < nx) ? reg : 0.0);
+      varz[idx] = v;
+      lvar[idx] = v;
+      m2z[idx] = v + muz[i] * muz[j];
+    });
+    L(h);
+  }
+  // S = sum_Bhh + sum_n A_n m2_z A_n^T ;  P = Kh + r S
+  if (h->gram_valid) { if (gram_q(h, m2z, h->M(M_Q))) return -2; }
+  else if (q_sweep(h, h->fc, chunks, m2z)) return -2;
+  if (allreduce(h, h->M(M_Q), l2)) return -2;
+  {
+    double* Pu = h->M(M_LP);
+    const double* kh0 = h->M(M_KH0);
+    const double* fb = h->M(M_F_BHH);
+    const double* q = h->M(M_Q);
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      Pu[idx] = kh0[idx] + r * (fb[idx] + q[idx]) + ((i == j && i < nh) ? reg + reg : 0.0);   // reg(Kh) + reg(P)
+    });
+    L(h);
+  }
+  if (chol_inv(h, h->M(M_LP), h->M(M_PINV), nh, nhp, h->sc + S_LOGDET_P, 3)) return -2;
+  matvec(h, h->M(M_F_Y), nh, nx, 0, muz, c0, h->V(V_LAM));                   // lam = c0 Y mean_z
+  matvec(h, h->M(M_PINV), nh, nh, 0, h->V(V_LAM), 1.0, h->V(V_LBAR));
+  dot(h, h->V(V_LAM), h->V(V_LBAR), nh, h->sc + S_LAM_LBAR);
+  frob(h, h->M(M_F_AXX), m2z, nx, nx, h->sc + S_TR_BHH_M2);                  // tr(sum_Bxx m2_z)
+  // -KL(q(z) || N(0, iKx + reg I))
+  {
+    double* so = h->M(M_SO);
+    const double* ikx = h->M(M_IKX);
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
+      so[idx] = ikx[idx] + ((i == j && i < nx) ? reg : 0.0);
+    });
+    L(h);
+  }
+  if (chol_inv(h, h->M(M_SO), h->M(M_ISO), nx, nxp, h->sc + S_LOGDET_SO, 4)) return -2;
+  if (chol_inv(h, h->M(M_LVAR), nullptr, nx, nxp, h->sc + S_LOGDET_VAR, 5)) return -2;
+  frob(h, h->M(M_ISO), varz, nx, nx, h->sc + S_TR_ISO_VAR);
+  matvec(h, h->M(M_ISO), nx, nx, 0, muz, 1.0, h->V(V_ISOMU));
+  dot(h, muz, h->V(V_ISOMU), nx, h->sc + S_MU_ISO_MU);
+  double hs[S_COUNT + 16];
+  int info[4];
+  CK(cudaMemcpyAsync(hs, h->sc, sizeof hs, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(info, h->info, sizeof info, cudaMemcpyDeviceToHost, st));
+  prof_close(h);
+  CK(cudaEventRecord(h->ev[6], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (info[0]) h->prior_valid = false;
+  if (info[0]) {
+    static const char* names[] = {"?", "Kh", "Kx", "P of q(u)", "iKx + reg I (prior of q(z))", "q(z) covariance"};
+    int tag = info[0] / 100000;
+    char b[160];
+    snprintf(b, sizeof b, "matrix %s is not positive definite (pivot %d)", tag >= 1 && tag <= 5 ? names[tag] : "?",
+             info[0] % 100000);
+    h->err = b;
+    return -3;
+  }
+  // N and sum y^2 of all ranks
+  double tail[2] = {(double)h->n_local, h->sum_y2_local};
+  if (h->world > 1) {
+    CK(cudaMemcpyAsync(h->fwd_tail, tail, sizeof tail, cudaMemcpyHostToDevice, st));
+    if (allreduce(h, h->fwd_tail, 2)) return -2;
+    CK(cudaMemcpyAsync(tail, h->fwd_tail, sizeof tail, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  const double KL = 0.5 * (hs[S_TR_ISO_VAR] + hs[S_MU_ISO_MU] - nx + hs[S_LOGDET_SO] - hs[S_LOGDET_VAR]);
+  double tm[7];
+  tm[0] = -0.5 * tail[0] * log(2.0 * 3.14159265358979323846 * s2) - 0.5 * tail[1] / s2;
+  tm[1] = 0.5 * hs[S_LOGDET_KH];
+  tm[2] = -0.5 * hs[S_LOGDET_P];
+  tm[3] = 0.5 * hs[S_LAM_LBAR];
+  tm[4] = -0.5 * r * h->f_sum_b;
+  tm[5] = -0.5 * r * hs[S_TR_BHH_M2];
+  tm[6] = -KL;
+  double e = 0.0;
+  for (int i = 0; i < 7; ++i) e += tm[i];
+  if (terms) memcpy(terms, tm, sizeof tm);
+  if (elbo) *elbo = e;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+  memset(h->timing, 0, sizeof h->timing);
+  h->timing[0] = ms;
+  h->timing[6] = (double)h->launches;
+  h->timing[7] = h->gemm_flops;
+  h->timing[8] = (double)h->gemm_launches;
+  h->timing[9] = h->gemm_flops_exec;
+  return 0;
+}
+
 // VCGPCM.predict_f (src/core/cgpcm.py:781-846) for given filter samples: posterior mean and variance of the function
 // at the test inputs, averaged over the samples.  smf = 0: one optimal q(z) from the moments of q(u); smf = 1: the
 // optimal q(z | h) per sample.  Training side: the frozen regime's sweeps; test side: predict_kernels.cuh.
@@ -1883,7 +2077,7 @@ int predict_run(cgpcm_handle* h, const double* params_host, double reg, const do
   h->gemm_flops = h->gemm_flops_exec = 0.0;
   h->gemm_launches = 0;
   PsiConst c;
-  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c, h->causal_id);
   PsiConst cd = c;                       // test-side statistics are evaluated densely (no windows)
   cd.cull = 746.0;
   BvnTab T;
@@ -2069,7 +2263,7 @@ int kernel_run(cgpcm_handle* h, const double* params_host, double reg, const dou
   h->pev_used = 0;
   h->prof_open = false;
   PsiConst c;
-  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c, h->causal_id);
   cudaStream_t st = h->st;
   const int nhl = round_up(nh, 2);
   const long K = (long)nh * nhl;
@@ -2151,7 +2345,7 @@ int filter_run(cgpcm_handle* h, const double* params_host, double reg, const dou
   h->pev_used = 0;
   h->prof_open = false;
   PsiConst c;
-  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c);
+  psi_make_const(alpha, gamma, omega, h->causal, h->cull, &c, h->causal_id);
   cudaStream_t st = h->st;
   const int ldn = round_up((int)n, 8);
   const int Bp = round_up(B, 8);
@@ -2431,6 +2625,39 @@ int cgpcm_fpi(cgpcm_handle* h, const double* params, int32_t num, int32_t high_r
   std::vector<double> host;
   if (fetch_params(h, params, np, host)) return -2;
   return fpi_run(h, host.data(), num, high_reg, reg, mu_u, var_u, mu_z, var_z);
+}
+
+int cgpcm_fpi_qz(cgpcm_handle* h, const double* params, const double* mu_z_in, const double* var_z_in, int32_t num,
+                 int32_t high_reg, double reg, double* mu_u, double* var_u, double* mu_z, double* var_z) {
+  if (!h || !params || !mu_z_in || !var_z_in || num < 0) return -1;
+  if (!h->t) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  if (!std::isfinite(reg) || reg < 0) { h->err = "reg must be finite and >= 0"; return -4; }
+  CK(cudaSetDevice(h->device));
+  const long np = 5 + h->nh + (long)h->nh * (h->nh + 1) / 2;
+  std::vector<double> host, mz, vz;
+  if (fetch_params(h, params, np, host)) return -2;
+  if (fetch_params(h, mu_z_in, h->nx, mz)) return -2;
+  if (fetch_params(h, var_z_in, (long)h->nx * (h->nx + 1) / 2, vz)) return -2;
+  return fpi_run(h, host.data(), num, high_reg, reg, mu_u, var_u, mu_z, var_z, mz.data(), vz.data());
+}
+
+int cgpcm_elbo_qz(cgpcm_handle* h, const double* params, const double* mu_z, const double* var_z, double reg,
+                  double* elbo, double* terms) {
+  if (!h || !params || !mu_z || !var_z || !elbo) return -1;
+  if (!h->t) { h->err = "cgpcm_set_data has not been called"; return -1; }
+  if (!std::isfinite(reg) || reg < 0) { h->err = "reg must be finite and >= 0"; return -4; }
+  CK(cudaSetDevice(h->device));
+  std::vector<double> host, mz, vz;
+  if (fetch_params(h, params, 5, host)) return -2;
+  if (fetch_params(h, mu_z, h->nx, mz)) return -2;
+  if (fetch_params(h, var_z, (long)h->nx * (h->nx + 1) / 2, vz)) return -2;
+  double e = 0.0, tm[7];
+  int rc = qz_run(h, host.data(), mz.data(), vz.data(), reg, &e, tm);
+  if (rc == 0) {
+    if (is_device_ptr(elbo)) cudaMemcpy(elbo, &e, sizeof e, cudaMemcpyHostToDevice); else *elbo = e;
+    if (terms) { if (is_device_ptr(terms)) cudaMemcpy(terms, tm, sizeof tm, cudaMemcpyHostToDevice); else memcpy(terms, tm, sizeof tm); }
+  }
+  return rc;
 }
 
 int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_t grad_mask, double reg, double* elbo,

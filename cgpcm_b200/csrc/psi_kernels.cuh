@@ -23,6 +23,14 @@ namespace cg {
 struct PsiConst {
   double alpha, gamma, omega, A;
   int causal;
+  // causal_id (src/core/cgpcm.py:168-180,194-203): upper integration limits min(t, tx) instead of t.  The Gaussian
+  // envelopes exp(E), exp(G) are the unconstrained maxima of the integrands and do not depend on the limits; only the
+  // arguments of erfc / Phi_2 move, by the distance max(t - tx, 0) from the limit to t in units of the conditional
+  // standard deviation:  z += max(d, 0) sqrt(A);  x_i -= max(d_i, 0) / sqrt(Sigma_11).
+  int causal_id;
+  double sqrtA;        // Ahx:  z(d > 0) = z_default + d sqrt(A) = ((alpha + gamma) d - gamma th) / sqrt(A)
+  double isq11;        // Axx:  1 / sqrt(Sigma_11)
+  double disq11[3];    // its derivatives w.r.t. alpha, gamma, omega
   // Ahx
   double pref_hx;      // causal: 0.5 sqrt(pi/A)   acausal: sqrt(pi/A)
   double e_hh, e_dd, e_hd;
@@ -38,10 +46,13 @@ struct PsiConst {
   double r_xx;         // |t - tx| beyond which every Axx element of that row / column is culled
 };
 
-inline void psi_make_const(double alpha, double gamma, double omega, int causal, double cull, PsiConst* c) {
+inline void psi_make_const(double alpha, double gamma, double omega, int causal, double cull, PsiConst* c,
+                           int causal_id = 0) {
   const double PI = 3.14159265358979323846;
   double A = alpha + gamma + omega;
   c->alpha = alpha; c->gamma = gamma; c->omega = omega; c->A = A; c->causal = causal;
+  c->causal_id = (causal && causal_id) ? 1 : 0;
+  c->sqrtA = sqrt(A);
   c->pref_hx = (causal ? 0.5 : 1.0) * sqrt(PI / A);
   c->e_hh = ((alpha + gamma) * A - gamma * gamma) / A;
   c->e_dd = omega * (alpha + gamma) / A;
@@ -67,7 +78,9 @@ inline void psi_make_const(double alpha, double gamma, double omega, int causal,
     c->dp[i] = 2.0 * dom[i] * sq + omega * dS11 / sq;
     c->dq[i] = 2.0 * dom[i] * S12 / sq + 2.0 * omega * dS12 / sq - omega * S12 * dS11 / (S11 * sq);
     c->drho[i] = dgam[i] / A - gamma / (A * A);
+    c->disq11[i] = -0.5 * dS11 / (S11 * sq);
   }
+  c->isq11 = 1.0 / sq;
   c->pref_hh = (causal ? 0.5 : 1.0) * sqrt(PI / (2.0 * (alpha + gamma)));
   // Element-wise threshold.  With culling off it is 746: exp(E) with E < -745.14 is exactly 0 in IEEE double (below
   // half the smallest subnormal), so such elements ARE 0 -- in the reference's TF arithmetic too -- and evaluating
@@ -166,7 +179,9 @@ __global__ void __launch_bounds__(256, HOIST ? 2 : 3) axx_sum_kernel(const doubl
       }
       continue;
     }
-    const double x1 = c.p * dk + c.q * dl, x2 = c.q * dk + c.p * dl;
+    double x1 = c.p * dk + c.q * dl, x2 = c.q * dk + c.p * dl;
+    const double ek = (!HOIST && c.causal_id) ? fmax(dk, 0.0) : 0.0, el = (!HOIST && c.causal_id) ? fmax(dl, 0.0) : 0.0;
+    if (!HOIST && c.causal_id) { x1 -= ek * c.isq11; x2 -= el * c.isq11; }
     if (!TANGENTS) {
       s0 += env * (HOIST ? bvn_cdf_pair(x1, x2, T, R, sA, deg) : bvnd_tab(-x1, -x2, T));
     } else {
@@ -179,12 +194,16 @@ __global__ void __launch_bounds__(256, HOIST ? 2 : 3) axx_sum_kernel(const doubl
       }
       const double V = env * cdf;
       s0 += V;
+      // causal_id: x_i also carries -e_i / sqrt(Sigma_11)  (ek = el = 0 otherwise)
       s1 += V * (-c.dg1[0] * q2 + c.dg2[0] * pr - c.dhalf_logdet[0]) +
-            env * (d1 * (c.dp[0] * dk + c.dq[0] * dl) + d2 * (c.dq[0] * dk + c.dp[0] * dl) + dr * c.drho[0]);
+            env * (d1 * (c.dp[0] * dk + c.dq[0] * dl - ek * c.disq11[0]) +
+                   d2 * (c.dq[0] * dk + c.dp[0] * dl - el * c.disq11[0]) + dr * c.drho[0]);
       s2 += V * (-c.dg1[1] * q2 + c.dg2[1] * pr - c.dhalf_logdet[1]) +
-            env * (d1 * (c.dp[1] * dk + c.dq[1] * dl) + d2 * (c.dq[1] * dk + c.dp[1] * dl) + dr * c.drho[1]);
+            env * (d1 * (c.dp[1] * dk + c.dq[1] * dl - ek * c.disq11[1]) +
+                   d2 * (c.dq[1] * dk + c.dp[1] * dl - el * c.disq11[1]) + dr * c.drho[1]);
       s3 += V * (-c.dg1[2] * q2 + c.dg2[2] * pr - c.dhalf_logdet[2]) +
-            env * (d1 * (c.dp[2] * dk + c.dq[2] * dl) + d2 * (c.dq[2] * dk + c.dp[2] * dl) + dr * c.drho[2]);
+            env * (d1 * (c.dp[2] * dk + c.dq[2] * dl - ek * c.disq11[2]) +
+                   d2 * (c.dq[2] * dk + c.dp[2] * dl - el * c.disq11[2]) + dr * c.drho[2]);
     }
   }
   const long mat = ld * ld;
@@ -206,7 +225,11 @@ __global__ void axx_user_kernel(const double* __restrict__ t, int n_obs, const d
     double v = 0.0;
     if (G >= -c.cull) {
       v = c.pref_xx * exp(G);
-      if (c.causal) v *= bvnd_tab(-(c.p * dk + c.q * dl), -(c.q * dk + c.p * dl), T);
+      if (c.causal) {
+        double x1 = c.p * dk + c.q * dl, x2 = c.q * dk + c.p * dl;
+        if (c.causal_id) { x1 -= fmax(dk, 0.0) * c.isq11; x2 -= fmax(dl, 0.0) * c.isq11; }
+        v *= bvnd_tab(-x1, -x2, T);
+      }
     }
     out[idx] = v;
   }
@@ -226,6 +249,7 @@ __device__ __forceinline__ void ahx_values(double th, const double (&d)[U], cons
   for (int u = 0; u < U; ++u) {
     E[u] = fma(d[u], fma(-c.e_dd, d[u], e1), e0);            // -e_hh th^2 - e_dd d^2 + e_hd th d
     z[u] = fma(z1, d[u], z0);                                // -(gamma th + omega d) / sqrt(A)
+    if (c.causal_id) z[u] = fma(fmax(d[u], 0.0), c.sqrtA, z[u]);   // limit min(t, tx): + max(d, 0) sqrt(A)
     any = any || (live[u] && E[u] >= -c.cull);
   }
   if (!any) {                                                // e.g. 80 % of the elements when no window is cut
@@ -336,6 +360,7 @@ __global__ void __launch_bounds__(256) ahx_dot_kernel(const double* __restrict__
           const double d = tv[u] - txk;
           Ev[u] = -c.e_hh * thi * thi - c.e_dd * d * d + c.e_hd * thi * d;
           zv[u] = -(c.gamma * thi + c.omega * d) * c.inv_sqrtA;
+          if (c.causal_id) zv[u] = fma(fmax(d, 0.0), c.sqrtA, zv[u]);
           ga[u] = Ev[u] - zv[u] * zv[u];
         }
         if (c.causal) cg_exp_neg<4>(ga, gx);
@@ -352,9 +377,11 @@ __global__ void __launch_bounds__(256) ahx_dot_kernel(const double* __restrict__
           const double F = av[u];
           const double X = c.causal ? gx[u] * c.inv_sqrtA : 0.0;
           const double zc = z * c.inv_2A;
-          const double da = F * (-thi * thi - uu * uu - c.inv_2A) + X * zc;
-          const double dg = F * (-(thi + uu) * (thi + uu) - c.inv_2A) + X * (thi * c.inv_sqrtA + zc);
-          const double dw = F * (-(d + uu) * (d + uu) - c.inv_2A) + X * (d * c.inv_sqrtA + zc);
+          // -X z_theta:  default z = -(gamma th + omega d) / sqrt(A);  causal_id, d > 0: z = ((alpha + gamma) d - gamma th) / sqrt(A)
+          const bool idr = c.causal_id && d > 0.0;
+          const double da = F * (-thi * thi - uu * uu - c.inv_2A) + X * ((idr ? -d * c.inv_sqrtA : 0.0) + zc);
+          const double dg = F * (-(thi + uu) * (thi + uu) - c.inv_2A) + X * ((idr ? thi - d : thi) * c.inv_sqrtA + zc);
+          const double dw = F * (-(d + uu) * (d + uu) - c.inv_2A) + X * ((idr ? 0.0 : d * c.inv_sqrtA) + zc);
           g0 += w * da; g1 += w * dg; g2 += w * dw;
         }
       }

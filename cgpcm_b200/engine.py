@@ -185,6 +185,31 @@ class Engine(object):
                                        _lib.ptr(mu_u), _lib.ptr(var_u), _lib.ptr(mu_z), _lib.ptr(var_z)))
         return mu_u, var_u, mu_z, var_z
 
+    def fpi_qz(self, params, mu_z, var_z, num, high_reg=False, reg=1e-8):
+        """``fpi(num, z=False)`` + ``convert(z=False)`` from the explicit q(z) = N(mu_z, reg(Lz Lz^T)):
+        ``(mu_u, var_u, mu_z, var_z)`` (``src/core/cgpcm.py:479-516,577-592`` with ``z=False``)."""
+        mu_z = np.ascontiguousarray(np.asarray(mu_z, dtype=np.float64).ravel())
+        var_z = np.ascontiguousarray(np.asarray(var_z, dtype=np.float64).ravel())
+        if mu_z.shape[0] != self.nx or var_z.shape[0] != self.nx * (self.nx + 1) // 2:
+            raise ValueError('shape mismatch in fpi_qz')
+        mu_u, var_u = np.empty(self.nh), np.empty(self.nh * (self.nh + 1) // 2)
+        mz, vz = np.empty(self.nx), np.empty(self.nx * (self.nx + 1) // 2)
+        self._ck(_lib.lib().cgpcm_fpi_qz(self._h, _lib.ptr(params), _lib.ptr(mu_z), _lib.ptr(var_z), int(num),
+                                          int(bool(high_reg)), float(reg), _lib.ptr(mu_u), _lib.ptr(var_u),
+                                          _lib.ptr(mz), _lib.ptr(vz)))
+        return mu_u, var_u, mz, vz
+
+    def elbo_qz(self, params, mu_z, var_z, reg=1e-8):
+        """``elbo(z=False)``: ``(elbo, terms[7])`` of the bound saturated for q(u) (``src/core/cgpcm.py:518-575``)."""
+        mu_z = np.ascontiguousarray(np.asarray(mu_z, dtype=np.float64).ravel())
+        var_z = np.ascontiguousarray(np.asarray(var_z, dtype=np.float64).ravel())
+        if mu_z.shape[0] != self.nx or var_z.shape[0] != self.nx * (self.nx + 1) // 2:
+            raise ValueError('shape mismatch in elbo_qz')
+        elbo, terms = np.empty(1), np.empty(7)
+        self._ck(_lib.lib().cgpcm_elbo_qz(self._h, _lib.ptr(np.ascontiguousarray(params[:5])), _lib.ptr(mu_z),
+                                           _lib.ptr(var_z), float(reg), _lib.ptr(elbo), _lib.ptr(terms)))
+        return float(elbo[0]), terms
+
     def last_timing(self):
         t = np.zeros(12)
         self._ck(_lib.lib().cgpcm_last_timing(self._h, _lib.ptr(t)))

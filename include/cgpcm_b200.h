@@ -55,6 +55,11 @@ int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int
 int cgpcm_destroy(cgpcm_handle* h);
 const char* cgpcm_last_error(const cgpcm_handle* h);
 
+/* Number of CUDA devices visible to the process: the multi-restart driver (cgpcm_b200/batch.py; the reference's unit
+ * is one controller.py process per resample index, src/experiment_toy.sh:7-11) opens one handle per device.
+ * Handles on different devices are independent and may be driven from different host threads. */
+int cgpcm_device_count(int* out);
+
 /* Multi-GPU: rank 0 makes a 128-byte NCCL unique id, every rank joins with it (one process per GPU).
  * After this, the sums over observations (src/core/cgpcm.py:240-267,473-475) are all-reduced. */
 int cgpcm_comm_unique_id(void* id128);
@@ -154,6 +159,20 @@ int cgpcm_fpi(cgpcm_handle* h, const double* params, int32_t num, int32_t high_r
  * launches (2 K M N; symmetric results K M (M + 1)), out[8] number of GEMM launches, out[9] flops of the CTA /
  * warp tiles the launches actually computed, out[10] Ahx generation kernels (option "profile" only);
  * out[11] reserved. */
+/* The z = False variants (src/core/cgpcm.py:472-476,499,537-540,584-592): q(z) = N(mu_z, reg(Lz Lz^T)) is the explicit
+ * variational distribution (mu_z[nx], var_z[nx(nx+1)/2] = Lz in np.tril_indices order) and q(u) is the optimal one.
+ * Both use the Psi statistics frozen by cgpcm_precompute; params supplies s2, s2_f and the hyper-parameters of the prior
+ * kernels (its q(u) part is not read).
+ *   cgpcm_fpi_qz   mod.fpi(num, z=False, high_reg) followed by mod.convert(z=False): num rounds of
+ *                  q(z) -> optimal q(u) -> optimal q(z), then the optimal q(u) of the final q(z).  Outputs as cgpcm_fpi.
+ *   cgpcm_elbo_qz  mod.elbo(z=False): the bound saturated for q(u); value and the 7 terms ('p(u) complexity',
+ *                  'q*(u) complexity', 'q*(u) fit', ..., -KL[q(z)||p(z)]).  No gradient: no task of the reference
+ *                  optimises q(z) directly (src/core/experiment.py:209-250 trains q(u) with z = True throughout). */
+int cgpcm_fpi_qz(cgpcm_handle* h, const double* params, const double* mu_z_in, const double* var_z_in, int32_t num,
+                 int32_t high_reg, double reg, double* mu_u, double* var_u, double* mu_z, double* var_z);
+int cgpcm_elbo_qz(cgpcm_handle* h, const double* params, const double* mu_z, const double* var_z, double reg,
+                  double* elbo, double* terms);
+
 int cgpcm_last_timing(cgpcm_handle* h, double out[12]);
 
 /* The reference's native op: Phi_2(x1, x2; rho) element-wise on three FP64 vectors of length n

@@ -201,8 +201,10 @@ def psi_Ahh(th, alpha, gamma, causal=True):
     return pref
 
 
-def psi_Ahx(t, th, tx, alpha, gamma, omega, causal=True):
-    """[n, nh, nx]; SURVEY.md App. A.3."""
+def psi_Ahx(t, th, tx, alpha, gamma, omega, causal=True, causal_id=False):
+    """[n, nh, nx]; SURVEY.md App. A.3.  ``causal_id`` (``cgpcm.py:194-203``): upper limit ``min(t, tx)``; the
+    envelope ``exp(E)`` is the unconstrained maximum of the integrand and does not change, the argument of ``erfc``
+    moves by the distance from the limit to ``t`` in conditional standard deviations: ``z += max(d, 0) sqrt(A)``."""
     t, th, tx = T(t), T(th), T(tx)
     A = alpha + gamma + omega
     d = t[:, None, None] - tx[None, None, :]
@@ -211,12 +213,16 @@ def psi_Ahx(t, th, tx, alpha, gamma, omega, causal=True):
     E = -(alpha + gamma) * thi ** 2 - omega * d ** 2 + b ** 2 / (4 * A)
     pref = torch.sqrt(math.pi / A) * torch.exp(E)
     if causal:
-        return .5 * pref * torch.special.erfc(b / (2 * torch.sqrt(A)))
+        z = b / (2 * torch.sqrt(A))
+        if causal_id:
+            z = z + torch.clamp(d, min=0.) * torch.sqrt(A)
+        return .5 * pref * torch.special.erfc(z)
     return pref
 
 
-def psi_Axx(t, tx, alpha, gamma, omega, causal=True):
-    """[n, nx, nx]; SURVEY.md App. A.4 (default causal case, ``causal_id=False``)."""
+def psi_Axx(t, tx, alpha, gamma, omega, causal=True, causal_id=False):
+    """[n, nx, nx]; SURVEY.md App. A.4.  ``causal_id`` (``cgpcm.py:168-180``): limits ``min(t, tx_k)``, ``min(t, tx_l)``;
+    as for ``Ahx`` only the arguments of the CDF move: ``x_i -= max(d_i, 0) / sqrt(Sigma_11)``."""
     t, tx = T(t), T(tx)
     A = alpha + gamma + omega
     det = 4 * (A * A - gamma * gamma)
@@ -233,15 +239,18 @@ def psi_Axx(t, tx, alpha, gamma, omega, causal=True):
     q = 2 * omega * S12 / torch.sqrt(S11)
     x1 = p * dk + q * dl
     x2 = q * dk + p * dl
+    if causal_id:
+        x1 = x1 - torch.clamp(dk, min=0.) / torch.sqrt(S11)
+        x2 = x2 - torch.clamp(dl, min=0.) / torch.sqrt(S11)
     rho = (gamma / A) * torch.ones_like(x1)
     return pref * _bvn_cdf_torch(x1, x2, rho)
 
 
-def psi_closed(t, th, tx, alpha, gamma, omega, causal=True):
+def psi_closed(t, th, tx, alpha, gamma, omega, causal=True, causal_id=False):
     alpha, gamma, omega = T(alpha), T(gamma), T(omega)
     return (psi_a(alpha, causal), psi_Ahh(th, alpha, gamma, causal),
-            psi_Axx(t, tx, alpha, gamma, omega, causal),
-            psi_Ahx(t, th, tx, alpha, gamma, omega, causal))
+            psi_Axx(t, tx, alpha, gamma, omega, causal, causal_id),
+            psi_Ahx(t, th, tx, alpha, gamma, omega, causal, causal_id))
 
 
 # ----------------------------------------------------------------------------- model matrices
@@ -305,20 +314,21 @@ def elbo_from_mats(m, k, n, sum_y2, s2, s2_f, mu_u, var_u, r):
     return sum(terms), terms
 
 
-def elbo_full(params, t, y, th, tx, r, causal=True, psi='closed'):
+def elbo_full(params, t, y, th, tx, r, causal=True, psi='closed', causal_id=False):
     """Full regime: Psi statistics rebuilt from the hyper-parameters in ``params``."""
     nh = len(th)
     p = T(params)
     s2, s2_f, alpha, gamma, omega, mu_u, var_u = unpack(p, nh)
     k = prior_kernels(th, tx, alpha, gamma, omega, r)
     fn = psi_closed if psi == 'closed' else psi_generic
-    a, Ahh, Axx, Ahx = fn(t, th, tx, alpha, gamma, omega, causal)
+    a, Ahh, Axx, Ahx = fn(t, th, tx, alpha, gamma, omega, causal, causal_id)
     m = model_matrices(y, a, Ahh, Axx, Ahx, k['iKh'], k['iKx'])
     y = T(y)
     return elbo_from_mats(m, k, y.shape[0], torch.sum(y ** 2), s2, s2_f, mu_u, var_u, r)
 
 
-def elbo_and_grad(params, t, y, th, tx, r, causal=True, psi='closed', frozen=None, frozen_kernels='detached'):
+def elbo_and_grad(params, t, y, th, tx, r, causal=True, psi='closed', frozen=None, frozen_kernels='detached',
+                  causal_id=False):
     """(elbo, terms[7], grad) as numpy.  ``frozen``: a ``(mats, kernels)`` pair of *detached*
     constants = the reference's precomputed regime (``cgpcm.py:270-284``).
 
@@ -329,7 +339,7 @@ def elbo_and_grad(params, t, y, th, tx, r, causal=True, psi='closed', frozen=Non
     freeze point: then only ``log s2, log s2_f, mu_u, var_u`` receive gradient."""
     p = T(np.asarray(params, np.float64)).clone().requires_grad_(True)
     if frozen is None:
-        e, terms = elbo_full(p, t, y, th, tx, r, causal, psi)
+        e, terms = elbo_full(p, t, y, th, tx, r, causal, psi, causal_id)
     else:
         m, k = frozen
         nh = len(th)
@@ -343,13 +353,13 @@ def elbo_and_grad(params, t, y, th, tx, r, causal=True, psi='closed', frozen=Non
     return float(e.detach()), np.array([float(x.detach()) for x in terms]), g.numpy().copy()
 
 
-def precompute(params, t, y, th, tx, r, causal=True):
+def precompute(params, t, y, th, tx, r, causal=True, causal_id=False):
     """Detached model matrices + kernels at the hyper-parameters in ``params``."""
     with torch.no_grad():
         nh = len(th)
         s2, s2_f, alpha, gamma, omega, mu_u, var_u = unpack(T(np.asarray(params, np.float64)), nh)
         k = prior_kernels(th, tx, alpha, gamma, omega, r)
-        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal)
+        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal, causal_id)
         m = model_matrices(y, a, Ahh, Axx, Ahx, k['iKh'], k['iKx'])
     return m, k
 
@@ -387,7 +397,7 @@ def from_natural(P, lam, r):
     return torch.cholesky_solve(lam, L), cholinv(L)
 
 
-def fpi(params, t, y, th, tx, r, num, causal=True, high_reg=False):
+def fpi(params, t, y, th, tx, r, num, causal=True, high_reg=False, causal_id=False):
     """``VCGPCM.fpi(num, z=True, high_reg)`` (``cgpcm.py:479-516``): ``num`` rounds of
     q(u) -> optimal q(z) -> optimal q(u).  Returns ``(mu_u, var_u)`` as the reference assigns them
     (``var_u = tril_to_vec(cholesky(var))``) plus the last q(z) as ``(mu_z, var_z)`` in the same packing (what
@@ -396,7 +406,7 @@ def fpi(params, t, y, th, tx, r, num, causal=True, high_reg=False):
         nh = len(th)
         s2, s2_f, alpha, gamma, omega, mu_u, var_u = unpack(T(np.asarray(params, np.float64)), nh)
         k = prior_kernels(th, tx, alpha, gamma, omega, r)
-        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal)
+        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal, causal_id)
         m = model_matrices(y, a, Ahh, Axx, Ahx, k['iKh'], k['iKx'])
         Lq = vec_to_tril(var_u)
         mean, var = mu_u, reg(Lq @ Lq.T, r)                       # self.h (cgpcm.py:444-445)
@@ -416,15 +426,70 @@ def fpi(params, t, y, th, tx, r, num, causal=True, high_reg=False):
     return out
 
 
+def elbo_qz(params, mu_z, var_z, t, y, th, tx, r, causal=True, causal_id=False):
+    """``VCGPCM.elbo(z=False)`` (``cgpcm.py:518-575``, the ``z=False`` branches): the bound saturated for q(u) with the
+    explicit ``q(z) = N(mu_z, reg(Lz Lz^T))``.  Returns ``(elbo, terms[7])``."""
+    with torch.no_grad():
+        nh = len(th)
+        s2, s2_f, alpha, gamma, omega, _, _ = unpack(T(np.asarray(params, np.float64)), nh)
+        k = prior_kernels(th, tx, alpha, gamma, omega, r)
+        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal, causal_id)
+        m = model_matrices(y, a, Ahh, Axx, Ahx, k['iKh'], k['iKx'])
+        yy = T(y)
+        n, sum_y2 = yy.shape[0], torch.sum(yy ** 2)
+        mz = T(np.asarray(mu_z, np.float64)).reshape(-1, 1)
+        Lz = vec_to_tril(T(np.asarray(var_z, np.float64)))
+        x_var = reg(Lz @ Lz.T, r)
+        x_m2 = x_var + mz @ mz.T
+        lam, P = optimal_q(m, k, s2, s2_f, mz, x_m2, False)
+        L = torch.linalg.cholesky(reg(P, r))
+        zero = torch.zeros(mz.shape, dtype=DT)
+        terms = [-.5 * n * torch.log(2 * math.pi * s2) - .5 * sum_y2 / s2,
+                 .5 * log_det(k['Lh']),
+                 -.5 * log_det(L),
+                 .5 * torch.sum(trisolve(L, lam) ** 2),
+                 -.5 * s2_f / s2 * m['sum_b'],
+                 -.5 * s2_f / s2 * trmul(m['sum_Bxx'], x_m2),
+                 -normal_kl(x_var, mz, reg(k['iKx'], r), zero)]
+    return float(sum(terms)), np.array([float(x) for x in terms])
+
+
+def fpi_qz(params, mu_z, var_z, t, y, th, tx, r, num, causal=True, high_reg=False, causal_id=False):
+    """``VCGPCM.fpi(num, z=False, high_reg)`` followed by ``convert(z=False)`` (``cgpcm.py:479-516,577-592``):
+    ``(mu_u, var_u, mu_z, var_z)`` in the reference's packing."""
+    with torch.no_grad():
+        nh = len(th)
+        s2, s2_f, alpha, gamma, omega, _, _ = unpack(T(np.asarray(params, np.float64)), nh)
+        k = prior_kernels(th, tx, alpha, gamma, omega, r)
+        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal, causal_id)
+        m = model_matrices(y, a, Ahh, Axx, Ahx, k['iKh'], k['iKx'])
+        mean = T(np.asarray(mu_z, np.float64)).reshape(-1, 1)
+        Lz = vec_to_tril(T(np.asarray(var_z, np.float64)))
+        var = reg(Lz @ Lz.T, r)
+        for _ in range(num):
+            lam, P = optimal_q(m, k, s2, s2_f, mean, var + mean @ mean.T, False)
+            if high_reg:
+                P = reg(P, 1e-4)
+            mu, vu = from_natural(P, lam, r)
+            lam, P = optimal_q(m, k, s2, s2_f, mu, vu + mu @ mu.T, True)
+            if high_reg:
+                P = reg(P, 1e-4)
+            mean, var = from_natural(P, lam, r)
+        lam, P = optimal_q(m, k, s2, s2_f, mean, var + mean @ mean.T, False)    # convert(z=False)
+        mu, vu = from_natural(P, lam, r)
+        return [mu.numpy().ravel().copy(), tril_to_vec(torch.linalg.cholesky(vu)).numpy().copy(),
+                mean.numpy().ravel().copy(), tril_to_vec(torch.linalg.cholesky(var)).numpy().copy()]
+
+
 # ----------------------------------------------------------------------------- SMF bound and sampler target (SURVEY §8f rank 2)
-def elbo_smf(params, t, y, th, tx, r, sample, causal=True):
+def elbo_smf(params, t, y, th, tx, r, sample, causal=True, causal_id=False):
     """``VCGPCM.elbo(smf=True, sample=sample)`` (``cgpcm.py:518-575``) and the pseudo-log-likelihood of
     ``VCGPCM.sample`` (``cgpcm.py:848-866``) at ``h = sample``: ``(elbo, terms[7], log_lik)``."""
     with torch.no_grad():
         nh = len(th)
         s2, s2_f, alpha, gamma, omega, mu_u, var_u = unpack(T(np.asarray(params, np.float64)), nh)
         k = prior_kernels(th, tx, alpha, gamma, omega, r)
-        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal)
+        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal, causal_id)
         m = model_matrices(y, a, Ahh, Axx, Ahx, k['iKh'], k['iKx'])
         yy = T(y)
         n, sum_y2 = yy.shape[0], torch.sum(yy ** 2)
@@ -449,7 +514,7 @@ def elbo_smf(params, t, y, th, tx, r, sample, causal=True):
 
 
 # ----------------------------------------------------------------------------- function prediction
-def predict_f(params, t, y, th, tx, r, t_star, samples_h, smf=False, causal=True):
+def predict_f(params, t, y, th, tx, r, t_star, samples_h, smf=False, causal=True, causal_id=False):
     """``VCGPCM.predict_f`` (``cgpcm.py:781-846``) for given filter samples ``samples_h`` ([B][nh]): posterior mean
     and variance of the function at ``t_star``, averaged over the samples.  ``smf=False``: q(z) is the optimal q(z) of
     q(u) (the reference's numeric ``samples_h``: draws from q(u)); ``smf=True``: q(z | h) per sample."""
@@ -457,10 +522,10 @@ def predict_f(params, t, y, th, tx, r, t_star, samples_h, smf=False, causal=True
         nh = len(th)
         s2, s2_f, alpha, gamma, omega, mu_u, var_u = unpack(T(np.asarray(params, np.float64)), nh)
         k = prior_kernels(th, tx, alpha, gamma, omega, r)
-        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal)
+        a, Ahh, Axx, Ahx = psi_closed(t, th, tx, alpha, gamma, omega, causal, causal_id)
         m = model_matrices(y, a, Ahh, Axx, Ahx, k['iKh'], k['iKx'])
         # test-side statistics (cgpcm.py:793: _construct_model_matrices(Data(t)))
-        a_s, Ahh_s, Axx_s, Ahx_s = psi_closed(t_star, th, tx, alpha, gamma, omega, causal)
+        a_s, Ahh_s, Axx_s, Ahx_s = psi_closed(t_star, th, tx, alpha, gamma, omega, causal, causal_id)
         Lq = vec_to_tril(var_u)
         h_var = reg(Lq @ Lq.T, r)
         mus, vars_ = [], []

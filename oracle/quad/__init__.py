@@ -26,7 +26,7 @@ def lib():
         L = ctypes.CDLL(_LIB)
         dp, i32, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
         L.elbo_quad.argtypes = [i32, dp, dp, i32, dp, i32, dp, dp, dbl, i32, dp, dp]
-        L.elbo_quad_dderiv.argtypes = [i32, dp, dp, i32, dp, i32, dp, dp, dp, dbl, dbl, i32, dp]
+        L.elbo_quad_dderiv.argtypes = [i32, dp, dp, i32, dp, i32, dp, dp, dp, dbl, dbl, i32, i32, dp]
         L.bvn_quad.argtypes = [dp, dp, dp, ctypes.c_long, dp]
         L.bvn_quad.restype = None
         _lib = L
@@ -48,13 +48,15 @@ def elbo(params, t, y, th, tx, reg, causal=True):
     return e[0], e[1], tm[0::2].copy(), tm[1::2].copy()
 
 
-def dderiv(params, direction, t, y, th, tx, reg, causal=True, h=1e-17):
-    """Directional derivative of the ELBO along ``direction``: ``(richardson, D(h), D(2h))``."""
+def dderiv(params, direction, t, y, th, tx, reg, causal=True, h=1e-9, richardson=False):
+    """Directional derivative of the ELBO along ``direction`` by central differences in binary128 (the function is
+    smooth at this scale: D(1e-8) and D(1e-10) agree to 17 digits, h < 1e-14 only adds round-off):
+    ``(value, D(h), D(2h))``; with ``richardson`` the value is ``(4 D(h) - D(2h)) / 3`` (4 evaluations instead of 2)."""
     t, y, th, tx, params, direction = _c(t), _c(y), _c(th), _c(tx), _c(params), _c(direction)
     out = np.zeros(3)
     rc = lib().elbo_quad_dderiv(len(t), t.ctypes.data, y.ctypes.data, len(th), th.ctypes.data, len(tx),
                                 tx.ctypes.data, params.ctypes.data, direction.ctypes.data, float(h), float(reg),
-                                int(bool(causal)), out.ctypes.data)
+                                int(bool(causal)), int(bool(richardson)), out.ctypes.data)
     if rc:
         raise RuntimeError('elbo_quad_dderiv: Cholesky failed (code %d)' % rc)
     return out[0], out[1], out[2]

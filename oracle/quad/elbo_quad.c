@@ -64,6 +64,25 @@ static void gl_init(void) {
 
 static Q phi_cdf(Q x) { return 0.5Q * erfcq(-x * M_SQRT1_2q); }
 
+/* sin / cos at the nodes of the single-panel rule for the last rho seen (rho is one constant per model) */
+static Q tab_rho = -2, tab_sn[NQ], tab_cs2[NQ];
+static void bvn_table(Q rho) {
+  if (rho == tab_rho) return;
+#pragma omp critical(bvn_tab)
+  {
+    if (rho != tab_rho) {
+      Q as = asinq(rho);
+      for (int i = 0; i < NQ; ++i) {
+        Q u = 0.5Q * as * (1 + gl_x[i]);
+        tab_sn[i] = sinq(u);
+        Q c = cosq(u);
+        tab_cs2[i] = 2 * c * c;
+      }
+      tab_rho = rho;
+    }
+  }
+}
+
 /* Phi2(x, y; rho), |rho| < 1 */
 static Q bvn_cdf_q(Q x, Q y, Q rho) {
   Q base = phi_cdf(x) * phi_cdf(y);
@@ -92,6 +111,11 @@ static Q bvn_cdf_q(Q x, Q y, Q rho) {
   if (panels > 64) panels = 64;
   Q sum = 0;
   Q hw = as / panels;
+  if (panels == 1 && rho == tab_rho) {
+    Q acc = 0;
+    for (int i = 0; i < NQ; ++i) acc += gl_w[i] * expq(-(s2 - 2 * xy * tab_sn[i]) / tab_cs2[i]);
+    return base + acc * 0.5Q * as / (2 * QPI);
+  }
   for (int p = 0; p < panels; ++p) {
     Q c = hw * (p + 0.5Q), r = 0.5Q * hw;
     Q acc = 0;
@@ -240,6 +264,7 @@ static int elbo_core(int n, const double* t, const double* y, int nh, const doub
   const Q pref_xx = 2 * QPI / sqrtq(det);
   const Q pref_hx = (causal ? 0.5Q : 1) * sqrtq(QPI / A);
   const Q CUT = 110;
+  bvn_table(rho);
 
   /* sums over observations */
 #pragma omp parallel
@@ -419,21 +444,24 @@ int elbo_quad(int n, const double* t, const double* y, int nh, const double* th,
 /* Directional derivative d/ds ELBO(params + s dir) at s = 0 by central differences in binary128 with steps h and 2h:
  * out[0] = Richardson-extrapolated value (4 D(h) - D(2h)) / 3, out[1] = D(h), out[2] = D(2h). */
 int elbo_quad_dderiv(int n, const double* t, const double* y, int nh, const double* th, int nx, const double* tx,
-                     const double* params, const double* dir, double h, double reg, int causal, double out[3]) {
+                     const double* params, const double* dir, double h, double reg, int causal, int richardson,
+                     double out[3]) {
   const long np = 5 + nh + (long)nh * (nh + 1) / 2;
   Q* p = (Q*)malloc(sizeof(Q) * np);
   Q vals[4], tm[7];
   const Q steps[4] = {(Q)h, -(Q)h, 2 * (Q)h, -2 * (Q)h};
-  for (int s = 0; s < 4; ++s) {
+  const int nsteps = richardson ? 4 : 2;
+  vals[2] = vals[3] = 0;
+  for (int s = 0; s < nsteps; ++s) {
     for (long i = 0; i < np; ++i) p[i] = (Q)params[i] + steps[s] * (Q)dir[i];
     int rc = elbo_core(n, t, y, nh, th, nx, tx, p, reg, causal, &vals[s], tm);
     if (rc) { free(p); return rc; }
   }
   free(p);
   Q d1 = (vals[0] - vals[1]) / (2 * (Q)h), d2 = (vals[2] - vals[3]) / (4 * (Q)h);
-  out[0] = (double)((4 * d1 - d2) / 3);
+  out[0] = richardson ? (double)((4 * d1 - d2) / 3) : (double)d1;
   out[1] = (double)d1;
-  out[2] = (double)d2;
+  out[2] = richardson ? (double)d2 : (double)d1;
   return 0;
 }
 

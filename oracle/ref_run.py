@@ -53,8 +53,10 @@ def run(inp):
 
     sess = tf.Session()
     e = ref_data.Data(t, y)
+    tx_range = tuple(float(v) for v in inp['tx_range']) if 'tx_range' in inp else None
     mod = ref_cgpcm.VCGPCM.from_recipe(sess=sess, e=e, nx=nx, nh=nh, tau_w=float(inp['tau_w']),
-                                       tau_f=float(inp['tau_f']), causal=causal, causal_id=causal_id)
+                                       tau_f=float(inp['tau_f']), causal=causal, causal_id=causal_id,
+                                       tx_range=tx_range)
     nh = int(mod.nh)                                     # acausal: from_recipe makes nh odd
     res = {'th': sess.run(mod.th), 'tx': sess.run(mod.tx), 'nh': nh,
            'recipe_vars': np.array([float(sess.run(mod.vars[k])) for k in ('s2', 's2_f', 'alpha', 'gamma', 'omega')])}
@@ -105,13 +107,39 @@ def run(inp):
         grads_f = tf.gradients(elbo_f, var_list)
         ev, tv, gv = sess.run([elbo_f, [tm['tensor'] for tm in terms_f], grads_f])
         res.update(elbo_frozen=ev, terms_frozen=np.array(tv, dtype=np.float64), grad_frozen=pack(gv))
+        fpi_ok = True
         if 'fpi_num' in inp:
-            mod.fpi(num=int(inp['fpi_num']), z=True, high_reg=bool(inp.get('fpi_high_reg', False)))
-            mod.convert(z=True)
-            for k in ('mu_u', 'var_u', 'mu_z', 'var_z'):
-                res['fpi_' + k] = np.asarray(sess.run(mod.vars[k])).ravel()
-            res['fpi_elbo'] = sess.run(mod.elbo()[0])
-        if 't_star' in inp:
+            try:
+                mod.fpi(num=int(inp['fpi_num']), z=True, high_reg=bool(inp.get('fpi_high_reg', False)))
+                mod.convert(z=True)
+                for k in ('mu_u', 'var_u', 'mu_z', 'var_z'):
+                    res['fpi_' + k] = np.asarray(sess.run(mod.vars[k])).ravel()
+                res['fpi_elbo'] = sess.run(mod.elbo()[0])
+            except tf.InvalidArgumentError as exc:
+                # the reference's own iteration can leave the positive-definite cone (seen with causal_id=True, where
+                # sum_Bhh is not positive semi-definite): recorded, and the dependent outputs are left out
+                fpi_ok = False
+                res['fpi_error'] = str(exc)
+        if 'qz_mu' in inp:
+            # the z = False variants from a given q(z): elbo(z=False), then fpi(num, z=False) + convert(z=False)
+            sess.run([mod.vars['mu_z'].assign(np.asarray(inp['qz_mu'], dtype=np.float64).reshape(-1, 1)),
+                      mod.vars['var_z'].assign(np.asarray(inp['qz_var'], dtype=np.float64))])
+            elbo_z, terms_z = mod.elbo(z=False)
+            try:
+                ev, tv = sess.run([elbo_z, [tm['tensor'] for tm in terms_z]])
+                res.update(qz_elbo=ev, qz_terms=np.array(tv, dtype=np.float64))
+            except tf.InvalidArgumentError as exc:
+                res['qz_error'] = str(exc)
+            snapshot = {k: np.asarray(sess.run(mod.vars[k])).copy() for k in ('mu_u', 'var_u')}
+            try:
+                mod.fpi(num=int(inp.get('qz_fpi_num', 2)), z=False)
+                mod.convert(z=False)
+                for k in ('mu_u', 'var_u', 'mu_z', 'var_z'):
+                    res['qz_fpi_' + k] = np.asarray(sess.run(mod.vars[k])).ravel()
+            except tf.InvalidArgumentError as exc:
+                res['qz_fpi_error'] = str(exc)
+            sess.run([mod.vars[k].assign(v) for k, v in snapshot.items()])
+        if 't_star' in inp and fpi_ok:
             if not bool(inp.get('smf', False)):
                 # the reference takes the non-SMF branch only when it draws the filter samples itself
                 # (`is_numeric(samples_h)`, cgpcm.py:800-805): replay its draws (chol(var) eps + mean, one

@@ -27,7 +27,8 @@ def make_case(name, seed=0, n=None):
         t = np.linspace(0, 1, n)
         rec = _Rec.recipe(t, nx=60, nh=41, tau_w=.1, tau_f=.05, causal=True)
         y, reg = _unit(rng.standard_normal(n)), 1e-6
-    elif name == 'toy_small':       # a shrunken toy for finite differences
+    elif name in ('toy_small', 'toy_small_cid'):   # a shrunken toy for finite differences ('_cid': causal_id=True,
+                                                   #   the limits min(t, tx) of src/core/cgpcm.py:168-180,194-203)
         n = n or 40
         t = np.linspace(0, 1, n)
         rec = _Rec.recipe(t, nx=18, nh=11, tau_w=.1, tau_f=.05, causal=True)
@@ -91,7 +92,7 @@ def make_case(name, seed=0, n=None):
     params = om.pack(s2, rec['s2_f'], hyp[0], hyp[1], hyp[2], mu_u, var_u)
     return dict(name=name, t=np.ascontiguousarray(t), y=np.ascontiguousarray(y), th=rec['th'], tx=rec['tx'],
                 hyp=hyp, reg=reg, causal=causal, params=params, nh=len(rec['th']), nx=len(rec['tx']),
-                recipe=dict(rec_args))
+                recipe=dict(rec_args), causal_id=name.endswith('_cid'))
 
 
 CASES = ['toy_test', 'toy_small', 'toy_acausal_model', 'ou', 'hrir', 'crude', 'sweep', 'sweep_hi']

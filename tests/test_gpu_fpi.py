@@ -71,8 +71,19 @@ def test_fpi_api_raises_the_elbo_and_convert_assigns_qz():
     mod.convert()
     assert mod.vars['mu_z'].value.shape == (c['nx'], 1)
     assert mod.vars['var_z'].value.shape == (c['nx'] * (c['nx'] + 1) // 2,)
+    # the z = False variants (src/core/cgpcm.py:479-516,577-592): the iteration on q(z) raises the bound saturated for
+    # q(u); convert(z=False) then assigns the optimal q(u), which the z = True bound scores at least as high as before
+    ez, terms_z = mod.elbo(z=False)
+    assert [tm['name'] for tm in terms_z][1:4] == ['p(u) complexity', 'q*(u) complexity', 'q*(u) fit']
+    z0 = sess.run(ez)
+    assert sum(sess.run([tm['tensor'] for tm in terms_z])) == pytest.approx(z0, rel=1e-12)
+    mod.fpi(2, z=False)
+    z1 = sess.run(ez)
+    assert z1 >= z0 - 1e-9 * abs(z0)
+    mod.convert(z=False)
+    assert sess.run(elbo) >= e2 - 1e-6 * abs(e2)
     with pytest.raises(NotImplementedError):
-        mod.fpi(1, z=False)
+        (-ez).value_and_grad([mod.vars['mu_z']])
     # one more round from the fixed point of many rounds changes (almost) nothing
     mod.fpi(40)
     a = mod.vars['mu_u'].value.copy()

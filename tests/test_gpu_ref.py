@@ -24,7 +24,7 @@ REL = 1e-9
 
 
 def _engine(c, **opts):
-    eng = cgpcm_b200.Engine(c['nh'], c['nx'], causal=c['causal'])
+    eng = cgpcm_b200.Engine(c['nh'], c['nx'], causal=c['causal'], causal_id=c['causal_id'])
     eng.set_option('pw_dists', 1)
     for k, v in opts.items():
         eng.set_option(k, v)
@@ -84,6 +84,11 @@ def test_fpi_and_predict_f(name):
     f, c = load(name), make_case(name)
     eng = _engine(c)
     eng.precompute(*c['hyp'], reg=c['reg'])
+    if 'fpi_error' in f:
+        # the reference's own iteration leaves the positive-definite cone here (tf.cholesky raises): so must ours
+        with pytest.raises(cgpcm_b200.CgpcmError):
+            eng.fpi(f['params_frozen'], 3, reg=c['reg'])
+        return
     mu_u, var_u, mu_z, var_z = eng.fpi(f['params_frozen'], 3, reg=c['reg'])
     p_own = np.concatenate([f['params_frozen'][:5], mu_u, var_u])
     p_ref = np.concatenate([f['params_frozen'][:5], f['fpi_mu_u'], f['fpi_var_u']])
@@ -97,3 +102,31 @@ def test_fpi_and_predict_f(name):
     ptol = 1e-6 + 10 * REF_NOISE_GAIN * ref_noise(c)
     assert np.abs(mu - f['pred_mean']).max() <= ptol * sc
     assert np.abs(np.sqrt(var) - f['pred_std']).max() <= ptol * sc
+
+
+@pytest.mark.parametrize('name', REF_CASES)
+def test_z_false_variants(name):
+    """elbo(z=False), fpi(2, z=False) + convert(z=False) from an explicit q(z) against the reference's own outputs."""
+    f, c = load(name), make_case(name)
+    eng = _engine(c)
+    eng.precompute(*c['hyp'], reg=c['reg'])
+    if 'qz_error' in f:
+        with pytest.raises(cgpcm_b200.CgpcmError):       # the reference's tf.cholesky raises here: so must ours
+            eng.elbo_qz(f['params_frozen'], f['qz_mu'], f['qz_var'], reg=c['reg'])
+        return
+    rel = 10 * REL + REF_NOISE_GAIN * ref_noise(c)
+    e, terms = eng.elbo_qz(f['params_frozen'], f['qz_mu'], f['qz_var'], reg=c['reg'])
+    scale = np.abs(f['qz_terms']).max()
+    assert abs(e - f['qz_elbo']) <= rel * scale
+    assert np.abs(terms - f['qz_terms']).max() <= rel * scale
+    if 'qz_fpi_error' in f:
+        return
+    mu_u, var_u, mu_z, var_z = eng.fpi_qz(f['params_frozen'], f['qz_mu'], f['qz_var'], 2, reg=c['reg'])
+    e_own = eng.elbo_qz(f['params_frozen'], mu_z, var_z, reg=c['reg'])[0]
+    e_ref = eng.elbo_qz(f['params_frozen'], f['qz_fpi_mu_z'], f['qz_fpi_var_z'], reg=c['reg'])[0]
+    assert abs(e_own - e_ref) <= 1e-5 * abs(e_ref)
+    p_own = np.concatenate([f['params_frozen'][:5], mu_u, var_u])
+    p_ref = np.concatenate([f['params_frozen'][:5], f['qz_fpi_mu_u'], f['qz_fpi_var_u']])
+    eu_own = eng.elbo_grad(p_own, mode=MODE_FROZEN, reg=c['reg'], want_grad=False)[0]
+    eu_ref = eng.elbo_grad(p_ref, mode=MODE_FROZEN, reg=c['reg'], want_grad=False)[0]
+    assert abs(eu_own - eu_ref) <= 1e-5 * abs(eu_ref)

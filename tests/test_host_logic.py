@@ -93,8 +93,12 @@ def test_elbo_objective_modes_and_masks(model):
     assert model.s2.eval() == pytest.approx(.5)
     with pytest.raises(ValueError):
         model.vars['mu_u'].assign(np.zeros(3))
+    ez, terms_z = model.elbo(z=False)                    # value and terms only (cgpcm_elbo_qz): no gradient
+    assert len(terms_z) == 7 and terms_z[1]['name'] == 'p(u) complexity'
     with pytest.raises(NotImplementedError):
-        model.elbo(z=False)
+        ez.value_and_grad([model.vars['mu_u']])
+    with pytest.raises(NotImplementedError):
+        model.elbo(smf=True, z=False)
 
 
 def test_minimise_lbfgs_drives_objective(model):
