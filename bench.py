@@ -57,9 +57,10 @@ def parse():
                          'those that are exactly 0.0 in IEEE double (their Gaussian envelope exp(E), E < -745.2, '
                          'underflows); 0 = every tile multiplied, 80 = envelope < exp(-80) dropped; both reported beside')
     ap.add_argument('--chunk', type=int, default=0, help='0 = the library default: chosen per evaluation by the planner')
-    ap.add_argument('--cpu-sample', type=int, default=3000,
-                    help='observations in the CPU baseline sample of our arm (oracle port; large enough that the M^3 '
-                         'algebra does not dominate)')
+    ap.add_argument('--cpu-sample', type=int, default=300,
+                    help='observations in the CPU baseline sample of our arm (oracle port).  Its cost is linear in N '
+                         'already here: 20.8 s at 300 observations (69 ms each), 239 s at 3000 (80 ms each) on 8 '
+                         'threads at M = 200 -- the M^3 algebra is 0.3 s')
     ap.add_argument('--ref-sample', type=int, default=96,
                     help='observations per step of the reference arm (the reference\'s own code, oracle/_ref: it '
                          'materialises N x nx x nx tensors and keeps them for autodiff)')
@@ -142,8 +143,8 @@ def host_threads():
 def cpu_port_eval(wl, sample, steps=1, warmup=0):
     """Times the CPU oracle PORT (oracle/model.py: numpy / torch-CPU restatement of the reference's algorithm with
     closed-form Psi statistics, chunk-free) on the first `sample` observations of the workload with every host thread.
-    The cost of the path is linear in N (the M^3 algebra is a fixed 0.3 s at M = 200); evals/s at N is stated with the
-    extrapolation factor N / sample."""
+    The cost of the path is linear in N (measured at M = 200 on 8 threads: 69 ms per observation at 300 observations,
+    80 ms at 3000; the M^3 algebra is a fixed 0.3 s); evals/s at N is stated with the extrapolation factor N / sample."""
     import torch
     from oracle import model as om
     threads = host_threads()

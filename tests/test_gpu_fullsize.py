@@ -89,8 +89,10 @@ def test_gradient_directional_derivative(wl, eng):
         d /= np.linalg.norm(d)
         est = (4 * fd(d, 1e-3) - fd(d, 2e-3)) / 3
         an = float(g @ d)
-        # evaluation noise ~1e-10 * |ELBO| = 1e-4 over 2h = 2e-3 -> ~0.1 absolute = 4e-8 * |g|
-        assert abs(est - an) <= 2e-5 * abs(an) + 2e-7 * gnorm, (sl, est, an)
+        # evaluation noise ~1e-10 .. 5e-10 * |ELBO| = 1e-4 .. 5e-4 over 2h = 2e-3, amplified 5 / 3 by the extrapolation ->
+        # up to ~0.8 absolute = 3e-7 * |g|.  (A coarse check of the full-size path; the sharp ones are the oracle / binary128
+        # fixtures of the same shape at N = 1e4, tests/test_gpu_quad.py.)
+        assert abs(est - an) <= 2e-5 * abs(an) + 6e-7 * gnorm, (sl, est, an)
 
 
 def test_oracle_parity_at_m200_through_the_large_shape_kernels():

@@ -1,7 +1,8 @@
 """Generates tests/golden/quad/*.npz: the VCGPCM ELBO, its 7 terms and a set of directional derivatives evaluated in
 IEEE binary128 (oracle/quad/elbo_quad.c) at the reference's own experiment shapes (src/tasks/{toy,ou,hrir,crude}.py
-sizes, synthetic data of that shape), at two points each: the initial point of tools/named_shapes.py and a trained-like
-point (small noise variance, q(u) moved off the prior), where FP64 evaluations carry conditioning noise.
+sizes, synthetic data of that shape), at two points each: the initial point of tools/named_shapes.py and a TRAINED
+point (the variables after the reference's three-phase schedule, run on the GPU by tools/train_points.py), where FP64
+evaluations carry conditioning noise.
 These are the arbiter for "who is right" when two FP64 implementations differ by more than 1e-9
 (tests/test_quad_truth.py on the CPU, tests/test_gpu_quad.py on the GPU).
 Run:  python tools/make_quad_golden.py [shape ...]      (minutes per shape on 8 cores)
@@ -26,6 +27,11 @@ SHAPES = {  # name: (n, nx, nh, tau_w, tau_f, t-grid, reg)   -- tools/named_shap
 
 
 def make_point(name, kind):
+    if kind == 'trained':
+        # a point the GPU trained with the reference's schedule (tools/train_points.py -> gpurun_out/points/<name>.npz)
+        with np.load(os.path.join(ROOT, 'gpurun_out', 'points', name + '.npz')) as z:
+            return dict(t=z['t'], y=z['y'], th=z['th'], tx=z['tx'], reg=float(z['reg']), params=z['params'],
+                        nh=len(z['th']), nx=len(z['tx']))
     n, nx, nh, tau_w, tau_f, grid, reg = SHAPES[name]
     rng = np.random.default_rng(0)
     t = np.ascontiguousarray(grid(n))
@@ -35,13 +41,6 @@ def make_point(name, kind):
     hyp = (rec['alpha'], rec['gamma'], rec['omega'])
     mu_u, var_u = om.init_q(rec['th'], rec['alpha'], rec['gamma'], reg, rng)
     s2 = 0.1
-    if kind == 'trained':
-        # what training does to the variables: the noise variance collapses, the hyper-parameters drift, q(u) leaves
-        # the prior (its Cholesky factor is scaled and perturbed entry-wise)
-        s2 = 4e-3
-        hyp = (hyp[0] * 1.2, hyp[1] * 0.85, hyp[2] * 1.1)
-        var_u = var_u * (0.3 + 0.05 * rng.standard_normal(var_u.shape[0]))
-        mu_u = 3.0 * mu_u
     p = om.pack(s2, rec['s2_f'], hyp[0], hyp[1], hyp[2], mu_u, var_u)
     return dict(t=t, y=y, th=rec['th'], tx=rec['tx'], reg=reg, params=p, nh=len(rec['th']), nx=nx)
 
@@ -62,8 +61,12 @@ def directions(p, nh, rng):
 if __name__ == '__main__':
     out_dir = os.path.join(ROOT, 'tests', 'golden', 'quad')
     os.makedirs(out_dir, exist_ok=True)
-    for name in (sys.argv[1:] or list(SHAPES)):
-        for kind in ('init', 'trained'):
+    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    kinds = ('trained',) if '--trained' in sys.argv else ('init',) if '--init' in sys.argv else ('init', 'trained')
+    for name in (args or list(SHAPES)):
+        for kind in kinds:
+            if kind == 'trained' and not os.path.exists(os.path.join(ROOT, 'gpurun_out', 'points', name + '.npz')):
+                continue
             c = make_point(name, kind)
             t0 = time.time()
             e_hi, e_lo, t_hi, t_lo = quad.elbo(c['params'], c['t'], c['y'], c['th'], c['tx'], c['reg'], True)

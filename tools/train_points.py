@@ -34,8 +34,8 @@ np.random.seed(1005)
 config.reg = 1e-6
 t0 = time.time()
 f, k, h = load_akm(sess=sess, n=400, nh=41, tau_w=.05, tau_f=.05, causal=True, resample=0)
-mod, rep = experiment.train(sess, f, nx=150, nh=41, tau_w=.1, tau_f=.05, causal=True, reg=1e-6, iters_pre=100,
-                            iters=400, iters_post=60, iters_fpi_post=20)
+mod, rep = experiment.train(sess, f, nx=150, nh=41, tau_w=.1, tau_f=.05, causal=True, reg=1e-6, iters_pre=400,
+                            iters=2000, iters_post=200, iters_fpi_post=50)
 save('toy', mod, rep, 1e-6, t0)
 
 # hrir shape (src/tasks/hrir.py): white noise through a decaying random filter at 44.1 kHz, n = 400, nx = 300, nh = 151
@@ -48,5 +48,5 @@ y = np.convolve(rng.standard_normal(n + 176), filt, mode='valid')
 y = (y - y.mean()) / y.std()
 config.reg = 1e-8
 mod, rep = experiment.train(sess, Data(t, y), nx=300, nh=151, tau_w=1.5e-3, tau_f=5e-5, causal=True, reg=1e-8,
-                            iters_pre=100, iters=300, iters_post=50, iters_fpi_post=20)
+                            iters_pre=200, iters=350, iters_post=300, iters_fpi_post=50)
 save('hrir', mod, rep, 1e-8, t0)
