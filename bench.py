@@ -407,7 +407,8 @@ def run_ours(args):
     # second handle without a communicator (outside every timed region)
     elbo_vs_n1 = grad_vs_n1 = None
     if world > 1:
-        eng.close()
+        # (the sharded handle stays open: closing it here would destroy this rank's NCCL communicator while the other
+        # ranks have already left, and ncclCommDestroy waits for them)
         del flush
         torch.cuda.empty_cache()
         eng1 = cgpcm_b200.Engine(args.m, args.m, causal=True, device=local_rank)
@@ -419,6 +420,8 @@ def run_ours(args):
         grad_vs_n1 = float(np.abs(last[2] - g1).max() / np.abs(g1).max())
         eng1.close()
     peak, peak_src, peak_raw = fp64_peak()
+    headline_shape = args.n == 100000 and args.m == 200 and args.chunk <= 0 and args.cull == 746.0 and world == 1
+    psi_flops = (ncu_traffic() or {}).get('fp64_scalar_flops_executed_per_step') if headline_shape else None
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     n, m = args.n, args.m
     line = {
@@ -459,6 +462,13 @@ def run_ours(args):
                      # algorithmic GEMM flops of the step over the WHOLE step time (Psi kernels, M x M algebra,
                      # collectives and launch gaps included) against the same peak, per GPU
                      'whole_step_frac': (gemm_flops / (total_ms * 1e-3) / 1e12 / peak) if (total_ms and peak) else None,
+                     # every FP64 instruction of the step on the pipe DMMA and DFMA share: the DMMA flops the launches
+                     # executed (counted live) + the scalar FP64 flops of the Psi kernels (DFMA = 2, DMUL / DADD = 1;
+                     # ncu instruction counts of one step at this shape, profiles/traffic.json), over the step time
+                     'fp64_pipe_frac_whole_step': ((gemm_flops_exec / args.steps + psi_flops) / (total_ms / args.steps * 1e-3)
+                                                   / 1e12 / peak) if (total_ms and peak and psi_flops is not None) else None,
+                     'fp64_scalar_flops_per_step_ncu': psi_flops,
+                     'dram_bytes_per_step_ncu': (ncu_traffic() or {}).get('dram_bytes_per_step') if psi_flops is not None else None,
                      'flops_executed_per_step': gemm_flops_exec / args.steps,
                      'note': 'MEASURED_PEAKS.json has no FP64 figure; peak = FP64 tensor (DMMA) rate measured by '
                              'tools/fp64_peaks.cu; flops are algorithmic: 2 K M N per launch, K M (M + 1) for the '

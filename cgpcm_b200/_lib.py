@@ -21,7 +21,7 @@ GRAD_ALL = 0x7f
 MODE_FROZEN, MODE_FULL = 0, 1
 
 EXPORTS = ['cgpcm_create', 'cgpcm_destroy', 'cgpcm_last_error', 'cgpcm_device_count', 'cgpcm_comm_unique_id', 'cgpcm_comm_init',
-           'cgpcm_set_data', 'cgpcm_set_option', 'cgpcm_psi', 'cgpcm_precompute', 'cgpcm_elbo_grad', 'cgpcm_elbo_smf', 'cgpcm_predict_f', 'cgpcm_kernel_samples', 'cgpcm_filter_samples', 'cgpcm_akm_sample', 'cgpcm_fpi', 'cgpcm_fpi_qz', 'cgpcm_elbo_qz',
+           'cgpcm_set_data', 'cgpcm_set_option', 'cgpcm_psi', 'cgpcm_precompute', 'cgpcm_frozen_mats', 'cgpcm_elbo_grad', 'cgpcm_elbo_smf', 'cgpcm_predict_f', 'cgpcm_kernel_samples', 'cgpcm_filter_samples', 'cgpcm_akm_sample', 'cgpcm_fpi', 'cgpcm_fpi_qz', 'cgpcm_elbo_qz',
            'cgpcm_last_timing', 'cgpcm_bvn_cdf', 'cgpcm_dgemm', 'cgpcm_dgemm_sym', 'cgpcm_cholinv', 'cgpcm_math_test']
 
 
@@ -75,6 +75,7 @@ def lib():
     L.cgpcm_set_option.argtypes = [vp, ctypes.c_char_p, dbl]
     L.cgpcm_psi.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp]
     L.cgpcm_precompute.argtypes = [vp, dp, dbl]
+    L.cgpcm_frozen_mats.argtypes = [vp, dp, dp, dp, dp]
     L.cgpcm_elbo_grad.argtypes = [vp, dp, ctypes.c_int32, u32, dbl, dp, dp, dp]
     L.cgpcm_elbo_smf.argtypes = [vp, dp, ctypes.c_int32, dbl, dp, dp, dp, dp]
     L.cgpcm_predict_f.argtypes = [vp, dp, dbl, dp, i64, dp, ctypes.c_int32, ctypes.c_int32, dp, dp]

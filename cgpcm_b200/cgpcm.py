@@ -732,6 +732,13 @@ class VCGPCM(CGPCM):
 
     @property
     def mats(self):
-        """Psi statistics at the current (or frozen) hyper-parameters as numpy arrays."""
+        """The sums of ``mats`` the ELBO reads (``src/core/cgpcm.py:235-267``) at the current (or frozen)
+        hyper-parameters as numpy arrays: ``a, Ahh, sum_a, sum_Ahh, sum_Axx, sum_Ahx_y, sum_b, sum_Bxx, sum_Bhh``.
+        (The per-observation tensors ``Axx, Ahx, b, Bxx, Bhh`` that the reference also keeps are never materialised;
+        ``engine.psi(..., per_observation=True)`` returns ``Axx`` / ``Ahx`` on request.)"""
         hyp = self._frozen_hyp if self._precomputed else (self.alpha.eval(), self.gamma.eval(), self.omega.eval())
-        return self.engine.psi(*hyp)
+        out = self.engine.psi(*hyp)
+        out.update(self._with_frozen_stats(self.engine.frozen_mats))
+        out['sum_a'] = self.n * out['a']
+        out['sum_Ahh'] = self.n * out['Ahh']
+        return out

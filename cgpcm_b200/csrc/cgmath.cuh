@@ -42,6 +42,13 @@ namespace cg {
   X(-0x1.1df1ad154a28ep-3) X(0x1.3ba5916e9fd7fp+0)
 #define CG_ERFC_C26 0x1.7d604a7f621f4p-35
 
+// The erfc coefficients live in constant memory: ptxas then reads each with one uniform load (LDCU.64) instead of two
+// UMOVs of a literal -- ahx_gen_kernel: 888 -> 832 instructions, 0.8 ms per evaluation at the bench shape.  The exp
+// coefficients stay literals: the same change made ahx_dot_kernel (exp only, already short of registers) 0.9 ms slower.
+#define CG_LIST(c) c,
+__constant__ double cg_erfc_c[27] = {CG_ERFC_C26, CG_ERFC_COEFS(CG_LIST)};
+#undef CG_LIST
+
 template <int U>
 __device__ __forceinline__ void cg_exp_neg(const double (&x)[U], double (&out)[U]) {
   double r[U], p[U];
@@ -87,12 +94,13 @@ __device__ __forceinline__ void cg_erfc(const double (&z)[U], double (&out)[U]) 
     const double h = x[u] * x[u];
     l[u] = fma(x[u], x[u], -h);                                               // x^2 = h + l exactly
     mh[u] = -h;
-    g[u] = CG_ERFC_C26;
+    g[u] = cg_erfc_c[0];
   }
-#define CG_STEP(c)                  \
-  _Pragma("unroll") for (int u = 0; u < U; ++u) g[u] = fma(g[u], t[u], c);
-  CG_ERFC_COEFS(CG_STEP)
-#undef CG_STEP
+#pragma unroll
+  for (int k = 1; k < 27; ++k) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) g[u] = fma(g[u], t[u], cg_erfc_c[k]);
+  }
   cg_exp_neg<U>(mh, e);
 #pragma unroll
   for (int u = 0; u < U; ++u) {

