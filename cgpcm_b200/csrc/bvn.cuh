@@ -317,15 +317,21 @@ __device__ __forceinline__ bool bvn_pair_all(double G, double x1, double x2, con
   const double ea[5] = {G, -0.5 * hk, -0.5 * x1 * x1, -0.5 * x2 * x2, -q * T.inv_2om};
   const double is2 = 0.70710678118654752440;
   const double ca[3] = {-fmin(x1, x2) * is2, -((x2 - T.rho * x1) * T.inv_s) * is2, -((x1 - T.rho * x2) * T.inv_s) * is2};
-  double ev[5], cv[3];
+  double ev[5], cx[3];
   cg_exp_neg<5>(ea, ev);
-  cg_erfc<3>(ca, cv);
+  // The Gaussian factor of every erfc(z) = exp(-z^2) erfcx(|z|) here is one of the five exponentials above:
+  //   Phi(m), m = min(x1, x2):             exp(-z^2) = exp(-m^2 / 2) = ev[2] or ev[3]
+  //   phi(x1) Phi((x2 - rho x1) / s):      exp(-x1^2 / 2 - z^2) = exp(-q / (2 (1 - rho^2))) = ev[4]   (likewise for x2)
+  // so only the rational part erfcx(|z|) is evaluated (cgmath.cuh), and erfc(z) = 2 - erfc(-z) for z < 0.
+  cg_erfcx_abs<3>(ca, cx);
   envexp = ev[0];
   const double inv_sqrt_2pi = 0.39894228040143267794;
-  d1 = inv_sqrt_2pi * ev[2] * (0.5 * cv[1]);
-  d2 = inv_sqrt_2pi * ev[3] * (0.5 * cv[2]);
+  const double rb = ev[4] * cx[1], rc = ev[4] * cx[2];
+  d1 = (0.5 * inv_sqrt_2pi) * (ca[1] < 0.0 ? fma(2.0, ev[2], -rb) : rb);
+  d2 = (0.5 * inv_sqrt_2pi) * (ca[2] < 0.0 ? fma(2.0, ev[3], -rc) : rc);
   dr = ev[4] * T.inv_2pis;
-  const double tail = 0.5 * cv[0];
+  const double ra = (x1 <= x2 ? ev[2] : ev[3]) * cx[0];
+  const double tail = 0.5 * (ca[0] < 0.0 ? 2.0 - ra : ra);
   if (hk > BVN_CHEB_U) { cdf = tail; return true; }      // every remaining term is below exp(-100) (Genz's own cut)
   const double E1 = ev[1];
   const double c = (4.0 - hk) * 0.125, d = (12.0 - hk) * 0.0625;

@@ -75,6 +75,36 @@ __device__ __forceinline__ void cg_exp_neg(const double (&x)[U], double (&out)[U
   }
 }
 
+// erfcx(|z|) = exp(z^2) erfc(|z|) = g(t) / (1 + 2|z|): the polynomial part of cg_erfc without its exp(-z^2).  The
+// separable Psi kernels (psi_kernels.cuh: ahx_gen_sep_kernel) multiply it by exp(E - z^2), which factorises over the
+// filter and the noise inducing inputs, so no exponential of the erfc is evaluated per element.
+template <int U>
+__device__ __forceinline__ void cg_erfcx_abs(const double (&z)[U], double (&out)[U]) {
+  double t[U], inv[U], g[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double x = fmin(fabs(z[u]), 27.3);
+    const double a = x + 4.0, b = fma(2.0, x, 1.0);
+    const double den = a * b;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+    double err = fma(-den, y, 1.0);
+    y = fma(y, err, y);
+    err = fma(-den, y, 1.0);
+    y = fma(y, err, y);
+    t[u] = (x - 4.0) * (b * y);
+    inv[u] = a * y;
+    g[u] = cg_erfc_c[0];
+  }
+#pragma unroll
+  for (int k = 1; k < 27; ++k) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) g[u] = fma(g[u], t[u], cg_erfc_c[k]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) out[u] = g[u] * inv[u];
+}
+
 template <int U>
 __device__ __forceinline__ void cg_erfc(const double (&z)[U], double (&out)[U]) {
   double x[U], t[U], inv[U], g[U], mh[U], l[U], e[U];

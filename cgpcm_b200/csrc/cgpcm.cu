@@ -152,6 +152,7 @@ struct cgpcm_handle {
   // sweep stores (option "store", default on when they fit): the Ahx blocks of all chunks (storeA) and
   // T1 = H A of the forward sweep (storeT) stay resident in HBM for the backward sweep instead of being
   // regenerated / recomputed -- 8 nhp N nx bytes each (32 GB at N = 1e5, M = 200; the B200 has 180 GB).
+  int sep_opt = 1;             // 1: separable Ahx kernels for the default causal model (psi_kernels.cuh)
   int sl_opt = 1;              // 1: contractions with a small left operand run on the persistent kernel (dgemm_sl.cuh)
   int sms = 148;
   int store_opt = 1;
@@ -648,6 +649,18 @@ int y_slices_used(const std::vector<Chunk>& chunks) {
   return m;
 }
 
+// slice-private Y accumulators [slices][nhp][ld]: one slice per AHX_NSUB observations of the longest chunk of the plan
+int ensure_ypart(cgpcm_handle* h, int slices) {
+  if (slices > h->y_slices) {
+    if (h->ypart) cudaFree(h->ypart);
+    h->ypart = nullptr;
+    h->y_slices = 0;
+    CK(cudaMalloc(&h->ypart, (long)slices * h->nhp * h->ld * sizeof(double)));
+    h->y_slices = slices;
+  }
+  return 0;
+}
+
 int gen_chunk(cgpcm_handle* h, const PsiConst& c, const Chunk& ch, bool with_y, double* dstA = nullptr) {
   if (!dstA) dstA = h->wsA;
   const int threads = std::min(256, round_up(ch.kwp, 32));
@@ -655,9 +668,17 @@ int gen_chunk(cgpcm_handle* h, const PsiConst& c, const Chunk& ch, bool with_y, 
   if ((int)grid.y > h->y_slices) { h->err = "internal: y_slices too small"; return -1; }
   prof_close(h);
   if (h->profile) cudaEventRecord(prof_event(h, 1), h->st);
-  ahx_gen_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx, h->nx,
-                                              ch.k_lo, ch.kwp, dstA, with_y ? h->ypart : nullptr, h->ld,
-                                              (long)h->nhp * h->ld, c);
+  if (c.causal && !c.causal_id && h->sep_opt) {
+    // default causal model: separable form, AHX_IB filter rows per CTA (psi_kernels.cuh)
+    grid.x = (h->nhp + AHX_IB - 1) / AHX_IB;
+    ahx_gen_sep_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->nhp, h->tx,
+                                                    h->nx, ch.k_lo, ch.kwp, dstA, with_y ? h->ypart : nullptr, h->ld,
+                                                    (long)h->nhp * h->ld, c);
+  } else {
+    ahx_gen_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx, h->nx,
+                                                ch.k_lo, ch.kwp, dstA, with_y ? h->ypart : nullptr, h->ld,
+                                                (long)h->nhp * h->ld, c);
+  }
   if (h->profile) cudaEventRecord(prof_event(h, 1), h->st);
   L(h);
   return 0;
@@ -730,7 +751,8 @@ int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& 
   if (full) {
     zero(h, h->M(M_Q), h->ld * h->ld);
     if (sym_begin(h, 1)) return -2;
-    zero(h, h->ypart, (long)std::min(h->y_slices, y_slices_used(chunks)) * h->nhp * h->ld);
+    if (ensure_ypart(h, y_slices_used(chunks))) return -2;
+    zero(h, h->ypart, (long)y_slices_used(chunks) * h->nhp * h->ld);
   }
   // with the sweep stores the Ahx block (and T1 when the backward sweep will need it) go straight to their
   // resident slots; the frozen regime's blocks do not change between evaluations and are generated once
@@ -759,7 +781,7 @@ int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& 
   if (full) {
     if (sym_finish(h, 1, h->nhp, h->M(M_Q))) return -2;
     long total = (long)h->nhp * h->ld;
-    ypart_reduce_kernel<<<148, 256, 0, h->st>>>(h->ypart, std::min(h->y_slices, y_slices_used(chunks)), total, total,
+    ypart_reduce_kernel<<<148, 256, 0, h->st>>>(h->ypart, y_slices_used(chunks), total, total,
                                                 h->M(M_Y));
     L(h);
   }
@@ -800,9 +822,16 @@ int backward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>&
       const int threads = std::min(256, round_up(ch.kwp, 32));
       dim3 grid(h->nhp, (ch.nc + AHX_NSUB - 1) / AHX_NSUB);
       prof_close(h);
-      ahx_dot_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx,
-                                                  h->nx, ch.k_lo, ch.kwp, Ab, h->wsV, h->M(M_YBAR), h->ld, h->gpart,
-                                                  c);
+      if (c.causal && !c.causal_id && h->sep_opt) {
+        grid.x = (h->nhp + AHX_IB - 1) / AHX_IB;
+        ahx_dot_sep_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx,
+                                                        h->nx, ch.k_lo, ch.kwp, Ab, h->wsV, h->M(M_YBAR), h->ld,
+                                                        h->gpart, c);
+      } else {
+        ahx_dot_kernel<<<grid, threads, 0, h->st>>>(h->t + ch.n0, h->y + ch.n0, ch.nv, ch.nc, h->th, h->nh, h->tx,
+                                                    h->nx, ch.k_lo, ch.kwp, Ab, h->wsV, h->M(M_YBAR), h->ld, h->gpart,
+                                                    c);
+      }
       L(h);
     }
   }
@@ -1113,6 +1142,11 @@ int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
     h->sl_opt = (int)value;
     return 0;
   }
+  if (!strcmp(key, "sep")) {
+    h->sep_opt = (int)value;
+    h->storeA_frozen_valid = false;
+    return 0;
+  }
   if (!strcmp(key, "store")) {
     h->store_opt = value != 0.0;
     h->storeA_frozen_valid = false;
@@ -1182,14 +1216,7 @@ namespace cgimpl {
 
 int ensure_sweep_buffers(cgpcm_handle* h) {
   if (ensure_ws(h)) return -2;
-  int ys = std::max(16, (round_up(chunk_cap(h), 32) + 32) * h->nxp / 8 / AHX_NSUB + 2);   // narrowest window = 8 columns; >= the 16 slices of gram_q
-  if (ys > h->y_slices) {
-    if (h->ypart) cudaFree(h->ypart);
-    h->ypart = nullptr;
-    CK(cudaMalloc(&h->ypart, (long)ys * h->nhp * h->ld * sizeof(double)));
-    h->y_slices = ys;
-  }
-  return 0;
+  return ensure_ypart(h, 16);   // the 16 slices of gram_q; the sweeps grow it to their plan (y_slices_used)
 }
 
 // copy an (r x c) block of a padded ld-matrix to a dense user buffer (host or device)
@@ -1244,7 +1271,8 @@ int cgpcm_psi(cgpcm_handle* h, const double hyp[3], double* sum_Axx, double* Ahh
     // Y only: generate chunks with the fused y-reduction, no GEMMs
     std::vector<Chunk> chunks;
     plan_chunks(h, c, chunks);
-    const int ys = std::min(h->y_slices, y_slices_used(chunks));
+    const int ys = y_slices_used(chunks);
+    if (ensure_ypart(h, ys)) return -2;
     zero(h, h->ypart, (long)ys * h->nhp * ld);
     for (const Chunk& ch : chunks)
       if (gen_chunk(h, c, ch, true)) return -2;

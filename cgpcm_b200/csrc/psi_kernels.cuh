@@ -275,7 +275,7 @@ __device__ __forceinline__ double ahx_value(double th, double d, const PsiConst&
   return v[0];
 }
 
-constexpr int AHX_NSUB = 32;
+constexpr int AHX_NSUB = 16;      // observations per CTA (many short CTAs: the tail of the last wave stays small)
 constexpr int AHX_U = 4;          // observations a thread evaluates in lock-step
 
 // A[(i*nc + n)*kwp + k] for i < nhp, n < nc, k < kwp (zero outside the valid nh x n_valid x nx box).
@@ -313,6 +313,187 @@ __global__ void __launch_bounds__(256) ahx_gen_kernel(const double* __restrict__
       }
     }
     if (ok && Ypart) Ypart[(long)blockIdx.y * ypart_stride + (long)i * ldy + kg] += ysum;
+  }
+}
+
+// ---- separable variants (default causal model, causal_id = false) -----------------------------------------------
+// Ahx[n,i,k] = pref exp(E) erfc(z) with E = c + z^2 and c = -(alpha + gamma) th_i^2 - omega d_nk^2: the Gaussian factor
+// of erfc(z) = exp(-z^2) erfcx(|z|) cancels the cross term of the envelope, and exp(c) = f_i g_nk with
+//   f_i = exp(-(alpha + gamma) th_i^2)   (one per filter inducing point),   g_nk = exp(-omega d_nk^2)   (one per (n, k)).
+// So   z >= 0:  Ahx = pref f_i g_nk erfcx(z)          z < 0:  Ahx = pref (2 exp(E) - f_i g_nk erfcx(-z))
+// (both factors are <= 1: nothing overflows, and where f_i g_nk underflows the term is below the subnormals anyway), and
+// the Gaussian factor exp(E - z^2) of the erfc derivative in the adjoint is f_i g_nk itself.  A CTA covers AHX_IB filter
+// rows of the same (n, k) block, so g_nk costs one exp per AHX_IB elements: ahx_gen spends one exp per element instead of
+// two, ahx_dot none.  Padding (k >= nx, n >= n_valid) is expressed as d = 1e160, whose envelope is exactly 0.
+constexpr int AHX_IB = 8;
+constexpr double AHX_FAR = 1e160;
+
+struct AhxRow { double th, e0, e1, z0, pf, fx; };   // pf = pref f_i, fx = f_i / sqrt(A)
+
+__device__ __forceinline__ void ahx_row_init(AhxRow* rows, int i0, const double* __restrict__ th, int nh, const PsiConst& c) {
+  if (threadIdx.x < AHX_IB) {
+    const int i = i0 + threadIdx.x;
+    const double thi = i < nh ? th[i] : 0.0;
+    AhxRow r;
+    r.th = thi;
+    r.e0 = -c.e_hh * thi * thi;
+    r.e1 = c.e_hd * thi;
+    r.z0 = -(c.gamma * thi) * c.inv_sqrtA;
+    const double f = exp(-(c.alpha + c.gamma) * thi * thi);
+    r.pf = c.pref_hx * f;
+    r.fx = f * c.inv_sqrtA;
+    rows[threadIdx.x] = r;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) ahx_gen_sep_kernel(const double* __restrict__ t, const double* __restrict__ y,
+                                                          int n_valid, int nc, const double* __restrict__ th, int nh, int nhp,
+                                                          const double* __restrict__ tx, int nx, int k_lo, int kwp,
+                                                          double* __restrict__ A, double* __restrict__ Ypart,
+                                                          long ldy, long ypart_stride, const PsiConst c) {
+  __shared__ AhxRow rows[AHX_IB];
+  __shared__ double ys[AHX_IB][256];
+  const int i0 = blockIdx.x * AHX_IB;
+  const int n0 = blockIdx.y * AHX_NSUB;
+  const int n1 = min(nc, n0 + AHX_NSUB);
+  ahx_row_init(rows, i0, th, nh, c);
+  const int ib = min(AHX_IB, nhp - i0);
+  const double p2 = 2.0 * c.pref_hx, z1 = -c.omega * c.inv_sqrtA;
+  for (int k = threadIdx.x; k < kwp; k += blockDim.x) {
+    const int kg = k_lo + k;
+    const bool kok = kg < nx;
+    const double txk = kok ? tx[kg] : 0.0;
+#pragma unroll
+    for (int ii = 0; ii < AHX_IB; ++ii) ys[ii][threadIdx.x] = 0.0;
+    for (int n = n0; n < n1; n += AHX_U) {
+      double d[AHX_U], yv[AHX_U], w2[AHX_U], gk[AHX_U];
+#pragma unroll
+      for (int u = 0; u < AHX_U; ++u) {
+        const bool live = kok && n + u < n_valid;
+        d[u] = live ? __ldg(t + n + u) - txk : AHX_FAR;
+        yv[u] = live ? __ldg(y + n + u) : 0.0;
+        w2[u] = -c.omega * d[u] * d[u];
+      }
+      cg_exp_neg<AHX_U>(w2, gk);
+      double* dst = A + ((long)i0 * nc + n) * kwp + k;
+#pragma unroll 1
+      for (int ii = 0; ii < ib; ++ii, dst += (long)nc * kwp) {
+        const AhxRow r = rows[ii];
+        double E[AHX_U], z[AHX_U], ex[AHX_U], q[AHX_U];
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < AHX_U; ++u) {
+          E[u] = fma(d[u], fma(-c.e_dd, d[u], r.e1), r.e0);
+          z[u] = fma(z1, d[u], r.z0);
+          any = any || E[u] >= -c.cull;
+        }
+        double ysum = 0.0;
+        if (any && i0 + ii < nh) {
+          cg_exp_neg<AHX_U>(E, ex);
+          cg_erfcx_abs<AHX_U>(z, q);
+#pragma unroll
+          for (int u = 0; u < AHX_U; ++u) {
+            const double rr = (r.pf * gk[u]) * q[u];
+            double v = z[u] < 0.0 ? fma(p2, ex[u], -rr) : rr;
+            v = E[u] >= -c.cull ? v : 0.0;
+            ysum = fma(yv[u], v, ysum);
+            if (n + u < n1) dst[(long)u * kwp] = v;
+          }
+          ys[ii][threadIdx.x] += ysum;
+        } else {
+#pragma unroll
+          for (int u = 0; u < AHX_U; ++u)
+            if (n + u < n1) dst[(long)u * kwp] = 0.0;
+        }
+      }
+    }
+    if (kok && Ypart) {
+      for (int ii = 0; ii < ib; ++ii)
+        if (i0 + ii < nh) Ypart[(long)blockIdx.y * ypart_stride + (long)(i0 + ii) * ldy + kg] += ys[ii][threadIdx.x];
+    }
+  }
+}
+
+// gpart[(blockIdx.y * gridDim.x + blockIdx.x) * 3 + theta] += the block's part of sum (W + y Ybar) dA/dtheta (see ahx_dot_kernel)
+__global__ void __launch_bounds__(256) ahx_dot_sep_kernel(const double* __restrict__ t, const double* __restrict__ y,
+                                                          int n_valid, int nc, const double* __restrict__ th, int nh,
+                                                          const double* __restrict__ tx, int nx, int k_lo, int kwp,
+                                                          const double* __restrict__ A, const double* __restrict__ W,
+                                                          const double* __restrict__ Ybar, long ldy,
+                                                          double* __restrict__ gpart, const PsiConst c) {
+  __shared__ AhxRow rows[AHX_IB];
+  const int i0 = blockIdx.x * AHX_IB;
+  const int n0 = blockIdx.y * AHX_NSUB;
+  const int n1 = min(n_valid, n0 + AHX_NSUB);
+  ahx_row_init(rows, i0, th, nh, c);
+  const int ib = min(AHX_IB, nh - i0);
+  const double inv_A = 2.0 * c.inv_2A;
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+  for (int k = threadIdx.x; k < kwp; k += blockDim.x) {
+    const int kg = k_lo + k;
+    if (kg >= nx) continue;
+    const double txk = tx[kg];
+    for (int nb = n0; nb < n1; nb += 4) {
+      double d[4], yv[4], w2[4], gk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = nb + u < n1;
+        d[u] = ok ? __ldg(t + nb + u) - txk : 0.0;            // padding: W = y = 0, every factor stays finite
+        yv[u] = ok ? __ldg(y + nb + u) : 0.0;
+        w2[u] = -c.omega * d[u] * d[u];
+      }
+      cg_exp_neg<4>(w2, gk);
+      const long off = ((long)i0 * nc + nb) * kwp + k;
+      const double* src = W + off;
+      const double* asrc = A + off;
+#pragma unroll 4
+      for (int ii = 0; ii < ib; ++ii, src += (long)nc * kwp, asrc += (long)nc * kwp) {
+        const AhxRow r = rows[ii];
+        double wv[4], av[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = nb + u < n1;
+          wv[u] = ok ? src[(long)u * kwp] : 0.0;
+          av[u] = ok ? asrc[(long)u * kwp] : 0.0;
+        }
+        const double yb = Ybar[(long)(i0 + ii) * ldy + kg];
+        const double xf = r.fx;                                  // f_i / sqrt(A)
+        const double ca = -fma(r.th, r.th, c.inv_2A);            // -th^2 - 1/(2A)
+        const double gth = c.gamma * r.th, tis = r.th * c.inv_sqrtA;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double E = fma(d[u], fma(-c.e_dd, d[u], r.e1), r.e0);
+          const double w = E >= -c.cull ? fma(yv[u], yb, wv[u]) : 0.0;
+          const double bh = -fma(c.omega, d[u], gth);            // b / 2 = -(gamma th + omega d)
+          const double uu = bh * inv_A;                          // b / (2A)
+          const double zc = (bh * c.inv_sqrtA) * c.inv_2A;       // z / (2A)
+          const double F = av[u];
+          const double X = xf * gk[u];                           // exp(E - z^2) / sqrt(A)
+          const double su = r.th + uu, sd = d[u] + uu;
+          const double da = fma(F, fma(-uu, uu, ca), X * zc);
+          const double dg = fma(F, -fma(su, su, c.inv_2A), X * (tis + zc));
+          const double dw = fma(F, -fma(sd, sd, c.inv_2A), X * fma(d[u], c.inv_sqrtA, zc));
+          g0 = fma(w, da, g0); g1 = fma(w, dg, g1); g2 = fma(w, dw, g2);
+        }
+      }
+    }
+  }
+  __shared__ double sh[3][8];
+  for (int off = 16; off > 0; off >>= 1) {
+    g0 += __shfl_down_sync(0xffffffffu, g0, off);
+    g1 += __shfl_down_sync(0xffffffffu, g1, off);
+    g2 += __shfl_down_sync(0xffffffffu, g2, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][warp] = g0; sh[1][warp] = g1; sh[2][warp] = g2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int w = 0; w < nw; ++w) { a0 += sh[0][w]; a1 += sh[1][w]; a2 += sh[2][w]; }
+    double* o = gpart + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 3;
+    o[0] += a0; o[1] += a1; o[2] += a2;
   }
 }
 

@@ -8,7 +8,9 @@ import pytest
 
 from oracle import model as om
 
-FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.npz')))
+# (bench_m200.npz -- the bench shape's own fixture, M = 200 and N = 1e4 -- has its own schema and test: test_gpu_quad.py)
+FILES = [f for f in sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.npz')))
+         if os.path.basename(f) != 'bench_m200.npz']
 
 
 def _load(f):

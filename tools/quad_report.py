@@ -37,3 +37,31 @@ for f in sorted(glob.glob(os.path.join(ROOT, 'tests', 'golden', 'quad', '*.npz')
            'directions': [str(x) for x in d['dir_names']]}
     print(json.dumps(row), flush=True)
     eng.close()
+
+# the bench shape's own fixture (M = 200, N = 1e4; tools/make_bench_golden.py --quad): oracle values are stored in it
+f = os.path.join(ROOT, 'tests', 'golden', 'bench_m200.npz')
+if os.path.exists(f):
+    with np.load(f) as z:
+        d = {k: (z[k][()] if z[k].ndim == 0 else z[k]) for k in z.files}
+    if 'quad_elbo' in d:
+        sc = float(np.abs(d['quad_terms']).max())
+        gm = float(np.abs(d['grad']).max())
+        row = {'fixture': 'bench_m200', 'n': len(d['t']), 'nx': len(d['tx']), 'nh': len(d['th']), 'largest_term': sc,
+               'grad_max': gm, 'elbo_truth': float(d['quad_elbo']),
+               'oracle': {'elbo_err_rel_largest_term': abs(float(d['elbo']) - d['quad_elbo']) / sc,
+                          'terms_err': (d['terms'] - d['quad_terms']).tolist()}}
+        if 'quad_dderiv' in d:
+            row['oracle']['dderiv_err_rel_grad_max'] = abs(float(d['quad_dir'] @ d['grad']) - d['quad_dderiv']) / gm
+        for name, opts in [('gpu', {'cull': 746.0}), ('gpu_all_tiles', {'cull': 0.0}), ('gpu_sep0', {'cull': 746.0, 'sep': 0})]:
+            eng = cgpcm_b200.Engine(len(d['th']), len(d['tx']), causal=True)
+            for k, v in opts.items():
+                eng.set_option(k, v)
+            eng.set_data(d['t'], d['y'], d['th'], d['tx'])
+            e, terms, g = eng.elbo_grad(d['params'], reg=float(d['reg']))
+            row[name] = {'elbo_err_rel_largest_term': abs(e - d['quad_elbo']) / sc,
+                         'terms_err': (terms - d['quad_terms']).tolist(),
+                         'grad_vs_oracle_rel_grad_max': float(np.abs(g - d['grad']).max() / gm)}
+            if 'quad_dderiv' in d:
+                row[name]['dderiv_err_rel_grad_max'] = abs(float(d['quad_dir'] @ g) - d['quad_dderiv']) / gm
+            eng.close()
+        print(json.dumps(row), flush=True)
