@@ -318,7 +318,7 @@ __device__ __forceinline__ bool bvn_pair_all(double G, double x1, double x2, con
   const double is2 = 0.70710678118654752440;
   const double ca[3] = {-fmin(x1, x2) * is2, -((x2 - T.rho * x1) * T.inv_s) * is2, -((x1 - T.rho * x2) * T.inv_s) * is2};
   double ev[5], cx[3];
-  cg_exp_neg<5>(ea, ev);
+  cg_exp_neg<5, true>(ea, ev);
   // The Gaussian factor of every erfc(z) = exp(-z^2) erfcx(|z|) here is one of the five exponentials above:
   //   Phi(m), m = min(x1, x2):             exp(-z^2) = exp(-m^2 / 2) = ev[2] or ev[3]
   //   phi(x1) Phi((x2 - rho x1) / s):      exp(-x1^2 / 2 - z^2) = exp(-q / (2 (1 - rho^2))) = ev[4]   (likewise for x2)

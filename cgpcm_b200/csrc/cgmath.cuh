@@ -49,7 +49,10 @@ namespace cg {
 __constant__ double cg_erfc_c[27] = {CG_ERFC_C26, CG_ERFC_COEFS(CG_LIST)};
 #undef CG_LIST
 
-template <int U>
+// FLUSH = true: results below 2^-1021 (x < -708.05) are returned as 0 and the scaling is one integer add to the
+// exponent field instead of two exact multiplications (bit-identical for every normal result).  The Psi kernels use
+// it: an element below 5e-308 changes no bit of a sum whose terms are O(1).
+template <int U, bool FLUSH = false>
 __device__ __forceinline__ void cg_exp_neg(const double (&x)[U], double (&out)[U]) {
   double r[U], p[U];
   int ni[U];
@@ -69,9 +72,15 @@ __device__ __forceinline__ void cg_exp_neg(const double (&x)[U], double (&out)[U
 #undef CG_STEP
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const int k1 = ni[u] >> 1, k2 = ni[u] - k1;                               // both >= -541: normal powers of two
-    const double s1 = __hiloint2double((1023 + k1) << 20, 0), s2 = __hiloint2double((1023 + k2) << 20, 0);
-    out[u] = (p[u] * s1) * s2;
+    if (FLUSH) {
+      // p in [0.70, 1.42]: exponent field 1022 or 1023, so p 2^n is normal for n >= -1021
+      const double v = __hiloint2double(__double2hiint(p[u]) + (ni[u] << 20), __double2loint(p[u]));
+      out[u] = ni[u] >= -1021 ? v : 0.0;
+    } else {
+      const int k1 = ni[u] >> 1, k2 = ni[u] - k1;                             // both >= -541: normal powers of two
+      const double s1 = __hiloint2double((1023 + k1) << 20, 0), s2 = __hiloint2double((1023 + k2) << 20, 0);
+      out[u] = (p[u] * s1) * s2;
+    }
   }
 }
 

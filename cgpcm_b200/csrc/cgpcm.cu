@@ -2968,6 +2968,47 @@ int cgpcm_math_test(const double* x, int64_t n, double* out_exp, double* out_erf
   return rc;
 }
 
+// out_exp[i] = cg_exp_neg<4, FLUSH>(min(x[i], 0)), out_erfcx[i] = cg_erfcx_abs<4>(x[i]) = erfcx(|x[i]|)
+__global__ void math_test_fast_kernel(const double* __restrict__ x, long n, double* __restrict__ oe, double* __restrict__ oc) {
+  for (long i0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += (long)gridDim.x * blockDim.x * 4) {
+    double xe[4], xc[4], e4[4], c4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double v = i0 + u < n ? x[i0 + u] : 0.0;
+      xe[u] = fmin(v, 0.0);
+      xc[u] = v;
+    }
+    cg_exp_neg<4, true>(xe, e4);
+    cg_erfcx_abs<4>(xc, c4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u >= n) break;
+      oe[i0 + u] = e4[u];
+      oc[i0 + u] = c4[u];
+    }
+  }
+}
+
+int cgpcm_math_test_fast(const double* x, int64_t n, double* out_exp, double* out_erfcx) {
+  if (!x || n < 1 || !out_exp || !out_erfcx) return -1;
+  double *dx = nullptr, *de = nullptr, *dc = nullptr;
+  int rc = 0;
+  if (cudaMalloc(&dx, n * sizeof(double)) != cudaSuccess || cudaMalloc(&de, n * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&dc, n * sizeof(double)) != cudaSuccess) rc = -2;
+  if (!rc) {
+    cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyDefault);
+    math_test_fast_kernel<<<148 * 4, 256>>>(dx, n, de, dc);
+    if (cudaDeviceSynchronize() != cudaSuccess) rc = -2;
+    cudaMemcpy(out_exp, de, n * sizeof(double), cudaMemcpyDefault);
+    cudaMemcpy(out_erfcx, dc, n * sizeof(double), cudaMemcpyDefault);
+  }
+  cudaGetLastError();
+  if (dx) cudaFree(dx);
+  if (de) cudaFree(de);
+  if (dc) cudaFree(dc);
+  return rc;
+}
+
 int cgpcm_cholinv(double* A, double* Ainv, double* logdet, int n, int64_t ld, int* info_host) {
   if (!A || n < 1 || ld < n || (ld % 8)) return -1;
   int np = round_up(n, 8);

@@ -31,6 +31,8 @@ namespace cg {
 constexpr int SL_BN = 64;          // output columns per consumer group tile (4 warps x 16)
 constexpr int SL_BK = 16;
 constexpr int SL_STAGES = 3;
+constexpr int SL_MAX_STAGES = 8;
+constexpr int SL_BAR_BYTES = 384;   // [2 groups][full | empty][SL_MAX_STAGES] + stagger
 constexpr int SL_MB = 13;          // 8-row blocks of the resident half (104 rows)
 constexpr int SL_KMAX = 200;
 constexpr int SL_SK = SL_KMAX + 4;   // row stride of the resident operand: == 4 (mod 8), conflict-free fragment loads
@@ -46,6 +48,7 @@ struct SlArgs {
   long lds, ldb, ldc;
   double alpha;
   int ctas0;      // CTAs [0, ctas0) own rows [0, 8 MB0), the rest rows [8 MB0, M)
+  int stages;     // ring depth per consumer group (SL_STAGES .. SL_MAX_STAGES: whatever the resident operand leaves)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,7 +80,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // One consumer warp's work on one output tile: MB x 2 blocks, K in k-tiles streamed through the ring.
-template <int MB, bool B_KC>
+template <int MB, bool B_KC, int SKT>
 __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* Ssm, const double* ring,
                                                 uint64_t* full, uint64_t* empty, int& stage, uint32_t& phase,
                                                 int nkt, int m_base, int rows, int n0, int lane, int wq,
@@ -88,7 +91,7 @@ __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* S
   double acc[MB][2][2];
 #pragma unroll
   for (int i = 0; i < MB; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-  constexpr int sk = SL_SK;
+  constexpr int sk = SKT;
   const double* Sp = Ssm + grp * sk + tig;
   const int b_off = B_KC ? (nw + grp) * (SL_BK + 4) + tig : tig * (SL_BN + 4) + nw + grp;
 
@@ -129,7 +132,7 @@ __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* S
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + stage);
-    if (++stage == SL_STAGES) { stage = 0; phase ^= 1u; }
+    if (++stage == g.stages) { stage = 0; phase ^= 1u; }
   };
   const int nfull = g.K / SL_BK;
   for (int kt = 0; kt < nfull; ++kt) ktile(kt, std::integral_constant<int, 4>());
@@ -137,6 +140,32 @@ __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* S
 
   // epilogue
   const int cols = g.N - n0;
+  if (g.alpha == 1.0 && rows == MB * 8 && cols >= SL_BN) {
+    // Full tile, no scaling (every contraction of the sweeps): straight-line stores.  The general path below costs a
+    // bounds test, a branch and a reconvergence point per DMMA block plus a DMUL per accumulator that queues behind the
+    // other group's DMMAs in the shared FP64 pipe -- ncu: 11 % of the consumer warps' samples at K = 96.
+    if (!B_KC) {
+      double* p = g.C + (long)(m_base + grp) * g.ldc + n0 + nw + tig * 2;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb, p += 8 * g.ldc) {
+        *reinterpret_cast<double2*>(p) = make_double2(acc[mb][0][0], acc[mb][0][1]);
+        *reinterpret_cast<double2*>(p + 8) = make_double2(acc[mb][1][0], acc[mb][1][1]);
+      }
+    } else {
+      double* p0 = g.C + (long)(n0 + nw + tig * 2) * g.ldc + m_base + grp;
+      double* p1 = p0 + g.ldc;
+      double* p2 = p0 + 8 * g.ldc;
+      double* p3 = p2 + g.ldc;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        p0[mb * 8] = acc[mb][0][0];
+        p1[mb * 8] = acc[mb][0][1];
+        p2[mb * 8] = acc[mb][1][0];
+        p3[mb * 8] = acc[mb][1][1];
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int mb = 0; mb < MB; ++mb) {
     if (mb * 8 >= rows) continue;
@@ -157,14 +186,21 @@ __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* S
   }
 }
 
-template <int MB0, int MB1, bool B_KC>
+// NARROW (one-half variants whose K fits the half's own rows, e.g. the windowed right-multiplies M = K = window): the
+// resident operand is stored at row stride 8 MB0 + 4 instead of 204 (both == 4 or 12 mod 16: conflict-free fragment
+// loads), and the shared memory it leaves goes to a deeper ring (dgemm_sl_stages).
+template <int MB0, bool NARROW>
+struct SlSk { static constexpr int value = NARROW ? MB0 * 8 + 4 : SL_SK; };
+
+template <int MB0, int MB1, bool B_KC, bool NARROW>
 __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
   extern __shared__ __align__(128) unsigned char sl_smem_raw[];
   constexpr int TILE = B_KC ? SL_TILE_K : SL_TILE_N;
-  constexpr int sk = SL_SK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sl_smem_raw);          // [2 groups][full 3 | empty 3]
-  double* rings = reinterpret_cast<double*>(sl_smem_raw + 128);      // [2][SL_STAGES][TILE]
-  double* Ssm = rings + 2 * SL_STAGES * TILE;                         // [104][sk]
+  constexpr int sk = SlSk<MB0, NARROW>::value;
+  const int NS = g.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sl_smem_raw);          // [2 groups][full NS | empty NS], stagger
+  double* rings = reinterpret_cast<double*>(sl_smem_raw + SL_BAR_BYTES);   // [2][NS][TILE]
+  double* Ssm = rings + 2 * NS * TILE;                                // [8 MB][sk]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int half = (MB1 > 0 && (int)blockIdx.x >= g.ctas0) ? 1 : 0;
@@ -184,26 +220,26 @@ __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
   }
   if (tid == 0) {
     for (int gq = 0; gq < 2; ++gq)
-      for (int s = 0; s < SL_STAGES; ++s) {
-        mbar_init(bars + gq * 2 * SL_STAGES + s, B_KC ? 32 : 1);      // full: expect_tx arrival | 32 cp.async lanes
-        mbar_init(bars + gq * 2 * SL_STAGES + SL_STAGES + s, 4);      // empty: one arrival per consumer warp
+      for (int s = 0; s < NS; ++s) {
+        mbar_init(bars + gq * 2 * NS + s, B_KC ? 32 : 1);             // full: expect_tx arrival | 32 cp.async lanes
+        mbar_init(bars + gq * 2 * NS + NS + s, 4);                    // empty: one arrival per consumer warp
       }
-    mbar_init(bars + 4 * SL_STAGES, 4);                               // stagger: group 0's four warps
+    mbar_init(bars + 4 * NS, 4);                                      // stagger: group 0's four warps
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
   const int grpid = warp < 8 ? (warp >> 2) : warp - 8;    // consumer group / producer's group
-  uint64_t* full = bars + grpid * 2 * SL_STAGES;
-  uint64_t* empty = full + SL_STAGES;
-  double* ring = rings + grpid * SL_STAGES * TILE;
+  uint64_t* full = bars + grpid * 2 * NS;
+  uint64_t* empty = full + NS;
+  double* ring = rings + grpid * NS * TILE;
   int stage = 0;
   uint32_t phase = 0;
 
   // Group 1 starts half a tile (and half a k-tile) after group 0: its producer holds the first copy back until
   // group 0 is in the middle of k-tile 6 of its first tile.  From then on one group's epilogue and k-tile
   // hand-overs fall into the other's DMMA stream instead of coinciding with them.
-  uint64_t* stagger = bars + 4 * SL_STAGES;
+  uint64_t* stagger = bars + 4 * NS;
 
   if (warp >= 8) {
     // ---------------------------------------------------------------- producer warp of group grpid
@@ -241,7 +277,7 @@ __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
           }
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(full + stage)) : "memory");
         }
-        if (++stage == SL_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == NS) { stage = 0; phase ^= 1u; }
       }
     }
     return;
@@ -253,20 +289,29 @@ __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
     const int n0 = (q + it * cq) * SL_BN;
     uint64_t* sg = it == 0 ? stagger : nullptr;
     if constexpr (MB1 == 0 || MB1 == MB0) {
-      sl_consume_tile<MB0, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
+      sl_consume_tile<MB0, B_KC, sk>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
     } else {
       if (half == 0)
-        sl_consume_tile<MB0, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
+        sl_consume_tile<MB0, B_KC, sk>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
       else
-        sl_consume_tile<MB1, B_KC>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
+        sl_consume_tile<MB1, B_KC, sk>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
     }
   }
 }
 
-inline size_t dgemm_sl_smem(int K, bool b_kc) {
-  const int tile = b_kc ? SL_TILE_K : SL_TILE_N;
-  (void)K;
-  return 128 + (size_t)2 * SL_STAGES * tile * 8 + (size_t)SL_MB * 8 * SL_SK * 8;
+// Shared memory: barriers, the two rings, the resident operand at its own row stride K + 4.  A narrow resident operand
+// (the windowed right-multiplies: 96 x 96 instead of 104 x 200) leaves room for a deeper ring, which is what hides the
+// DRAM latency of the streamed operand (3 stages of 16 k = ~2 us of DMMA work; ncu showed 5 % of the consumer warps'
+// time waiting on `full` barriers at K = 96).
+inline int dgemm_sl_stages(int mb_rows8, int sk, bool b_kc) {
+  const size_t tile = (size_t)(b_kc ? SL_TILE_K : SL_TILE_N) * 8;
+  const size_t fixed = SL_BAR_BYTES + (size_t)mb_rows8 * 8 * sk * 8;
+  int st = (int)((232448 - fixed) / (2 * tile));
+  return st < SL_STAGES ? SL_STAGES : st > SL_MAX_STAGES ? SL_MAX_STAGES : st;
+}
+inline size_t dgemm_sl_smem(int mb_rows8, int sk, bool b_kc, int stages) {
+  const size_t tile = (size_t)(b_kc ? SL_TILE_K : SL_TILE_N) * 8;
+  return SL_BAR_BYTES + (size_t)2 * stages * tile + (size_t)mb_rows8 * 8 * sk * 8;
 }
 
 inline bool dgemm_sl_supported(int M, int N, int K) {
@@ -277,18 +322,21 @@ inline bool dgemm_sl_supported(int M, int N, int K) {
 // smallest instantiated number of 8-row blocks that covers mb blocks
 inline int dgemm_sl_blocks(int mb) { return mb <= 5 ? 5 : mb <= 9 ? 9 : mb <= 12 ? 12 : 13; }
 
-template <int MB0, int MB1>
-inline void dgemm_sl_launch(cudaStream_t st, bool b_kc, const SlArgs& g, int sms, size_t smem) {
+template <int MB0, int MB1, bool NARROW>
+inline void dgemm_sl_launch(cudaStream_t st, bool b_kc, SlArgs g, int sms) {
   static DeviceOnce attr_once;
   unsigned long long attr_bit;
   if (attr_once.need(&attr_bit)) {
     const int mx = 232448;
-    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<MB0, MB1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<MB0, MB1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<MB0, MB1, false, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<MB0, MB1, true, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     attr_once.done(attr_bit);
   }
-  if (b_kc) dgemm_sl_kernel<MB0, MB1, true><<<sms, SL_NT, smem, st>>>(g);
-  else dgemm_sl_kernel<MB0, MB1, false><<<sms, SL_NT, smem, st>>>(g);
+  constexpr int sk = SlSk<MB0, NARROW>::value;
+  g.stages = dgemm_sl_stages(MB0, sk, b_kc);
+  const size_t smem = dgemm_sl_smem(MB0, sk, b_kc, g.stages);
+  if (b_kc) dgemm_sl_kernel<MB0, MB1, true, NARROW><<<sms, SL_NT, smem, st>>>(g);
+  else dgemm_sl_kernel<MB0, MB1, false, NARROW><<<sms, SL_NT, smem, st>>>(g);
 }
 
 // b_kc = false: C[m*ldc + n] = alpha sum_k S[m*lds + k] B[k*ldb + n];  b_kc = true: C[n*ldc + m] = alpha sum_k S[m*lds + k] B[n*ldb + k]
@@ -296,16 +344,21 @@ inline cudaError_t dgemm_sl(cudaStream_t st, bool b_kc, int M, int N, int K, dou
                             const double* B, long ldb, double* C, long ldc, int sms = 148) {
   SlArgs g;
   g.S = S; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lds = lds; g.ldb = ldb; g.ldc = ldc; g.alpha = alpha;
-  const size_t smem = dgemm_sl_smem(K, b_kc);
   const int mb = M / 8;
   if (mb <= SL_MB) {
     g.ctas0 = sms;
-    switch (dgemm_sl_blocks(mb)) {
-      case 5: dgemm_sl_launch<5, 0>(st, b_kc, g, sms, smem); break;
-      case 9: dgemm_sl_launch<9, 0>(st, b_kc, g, sms, smem); break;
-      case 12: dgemm_sl_launch<12, 0>(st, b_kc, g, sms, smem); break;
-      default: dgemm_sl_launch<13, 0>(st, b_kc, g, sms, smem); break;
+    const int blocks = dgemm_sl_blocks(mb);
+    const bool narrow = K <= blocks * 8;
+#define CG_SL(MB)                                                           \
+  if (narrow) dgemm_sl_launch<MB, 0, true>(st, b_kc, g, sms);               \
+  else dgemm_sl_launch<MB, 0, false>(st, b_kc, g, sms)
+    switch (blocks) {
+      case 5: CG_SL(5); break;
+      case 9: CG_SL(9); break;
+      case 12: CG_SL(12); break;
+      default: CG_SL(13); break;
     }
+#undef CG_SL
   } else {
     // CTAs are shared between the two halves in proportion to their DMMA blocks (+1: per-tile overhead)
     const int mb1 = dgemm_sl_blocks(mb - SL_MB);
@@ -314,10 +367,10 @@ inline cudaError_t dgemm_sl(cudaStream_t st, bool b_kc, int M, int N, int K, dou
     if (ctas0 < 1) ctas0 = 1;
     g.ctas0 = ctas0;
     switch (mb1) {
-      case 5: dgemm_sl_launch<13, 5>(st, b_kc, g, sms, smem); break;
-      case 9: dgemm_sl_launch<13, 9>(st, b_kc, g, sms, smem); break;
-      case 12: dgemm_sl_launch<13, 12>(st, b_kc, g, sms, smem); break;
-      default: dgemm_sl_launch<13, 13>(st, b_kc, g, sms, smem); break;
+      case 5: dgemm_sl_launch<13, 5, false>(st, b_kc, g, sms); break;
+      case 9: dgemm_sl_launch<13, 9, false>(st, b_kc, g, sms); break;
+      case 12: dgemm_sl_launch<13, 12, false>(st, b_kc, g, sms); break;
+      default: dgemm_sl_launch<13, 13, false>(st, b_kc, g, sms); break;
     }
   }
   return cudaGetLastError();

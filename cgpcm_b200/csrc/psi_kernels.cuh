@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) ahx_gen_sep_kernel(const double* __restri
         yv[u] = live ? __ldg(y + n + u) : 0.0;
         w2[u] = -c.omega * d[u] * d[u];
       }
-      cg_exp_neg<AHX_U>(w2, gk);
+      cg_exp_neg<AHX_U, true>(w2, gk);
       double* dst = A + ((long)i0 * nc + n) * kwp + k;
 #pragma unroll 1
       for (int ii = 0; ii < ib; ++ii, dst += (long)nc * kwp) {
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256) ahx_gen_sep_kernel(const double* __restri
         }
         double ysum = 0.0;
         if (any && i0 + ii < nh) {
-          cg_exp_neg<AHX_U>(E, ex);
+          cg_exp_neg<AHX_U, true>(E, ex);
           cg_erfcx_abs<AHX_U>(z, q);
 #pragma unroll
           for (int u = 0; u < AHX_U; ++u) {
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(256) ahx_dot_sep_kernel(const double* __restri
         yv[u] = ok ? __ldg(y + nb + u) : 0.0;
         w2[u] = -c.omega * d[u] * d[u];
       }
-      cg_exp_neg<4>(w2, gk);
+      cg_exp_neg<4, true>(w2, gk);
       const long off = ((long)i0 * nc + nb) * kwp + k;
       const double* src = W + off;
       const double* asrc = A + off;

@@ -202,6 +202,9 @@ int cgpcm_cholinv(double* A, double* Ainv, double* logdet, int n, int64_t ld, in
  * out_exp[i] = exp(min(x[i], 0)), out_erfc[i] = erfc(x[i]), evaluated four at a time; *mismatch = elements whose
  * one-at-a-time evaluation differs in any bit (0 when the lock-step evaluation is faithful). */
 int cgpcm_math_test(const double* x, int64_t n, double* out_exp, double* out_erfc, int* mismatch_host);
+/* cgpcm_math_test_fast: the variants the separable Psi kernels use: out_exp[i] = exp(min(x[i], 0)) with results below
+ * 2^-1021 flushed to 0 (one integer add scales by 2^n), out_erfcx[i] = erfcx(|x[i]|) = exp(x^2) erfc(|x|). */
+int cgpcm_math_test_fast(const double* x, int64_t n, double* out_exp, double* out_erfcx);
 
 #ifdef __cplusplus
 }

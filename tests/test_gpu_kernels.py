@@ -209,3 +209,32 @@ def test_in_register_exp_and_erfc_against_mpmath():
     assert oe[i0] == 1.0 and oc[i0] == 1.0
     assert oc[np.where(x == -30.0)[0][0]] == 2.0 and oc[np.where(x == -6.5)[0][0]] == 2.0
     assert 0.0 <= oc[np.where(x == 27.2)[0][0]] <= 1e-320
+
+
+def test_flushing_exp_and_erfcx_against_mpmath():
+    """The variants the separable Psi kernels use (csrc/cgmath.cuh): exp with one integer scaling step -- bit-identical
+    to the two-step version wherever the result is normal, exactly 0 below 2^-1021 -- and erfcx(|x|) = exp(x^2) erfc(|x|),
+    the rational part of erfc, <= 4 ulp against mpmath on [0, 27]."""
+    import ctypes
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(12)
+    x = np.concatenate([-rng.uniform(0, 745, 1500), -10.0 ** rng.uniform(-12, 0, 300), [0.0, -1e-300, -707.0, -708.0, -709.0, -744.4],
+                        rng.uniform(-27, 27, 1500), rng.normal(0, 1.5, 700), [-6.5, 26.5, 27.2, 0.5, 4.0]])
+    x = np.ascontiguousarray(x)
+    oe, oc, oe2, oc2 = np.empty_like(x), np.empty_like(x), np.empty_like(x), np.empty_like(x)
+    mism = ctypes.c_int(-1)
+    assert _lib.lib().cgpcm_math_test_fast(_lib.ptr(x), x.shape[0], _lib.ptr(oe), _lib.ptr(oc)) == 0
+    assert _lib.lib().cgpcm_math_test(_lib.ptr(x), x.shape[0], _lib.ptr(oe2), _lib.ptr(oc2), ctypes.byref(mism)) == 0
+    xe = np.minimum(x, 0.0)
+    normal = oe2 >= 2.0 ** -1021
+    assert np.array_equal(oe[normal], oe2[normal])               # same bits as the exact-scaling version
+    assert np.all(oe[xe < -708.1] == 0.0) and np.all(oe[~normal] <= 2.0 ** -1021)
+    worst = 0.0
+    for xi, got in zip(x, oc):
+        a = abs(float(xi))
+        if a > 27.3:                                             # the argument is clamped there (erfc underflows)
+            continue
+        want = mp.erfc(mp.mpf(a)) * mp.exp(mp.mpf(a) ** 2)
+        worst = max(worst, float(abs(mp.mpf(float(got)) - want) / mp.mpf(float(np.spacing(float(want))))))
+    assert worst <= 4.0, worst

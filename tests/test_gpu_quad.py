@@ -74,8 +74,9 @@ def test_bench_shape_m200_against_oracle_and_quad():
             assert abs(e - d['quad_elbo']) <= REL * sc, (cull, abs(e - d['quad_elbo']) / sc)
             # single terms: the two trace terms -r/2 sum_b and -r/2 tr(sum_Bhh m2) each contain tr(iKh Q) with the
             # FP64 inverse of Kh (cond 1 / reg) and carry ~eps / reg of it with opposite signs -- measured against the
-            # arbiter: +7.0e-5 and -7.2e-5 (1.5e-9 of the largest term) on the CUDA path, whose ELBO is off by 4e-11;
-            # -4.6e-5 and +1.9e-5 for the FP64 oracle in the reference's operation order, whose ELBO is off by 5.5e-10
+            # arbiter (tools/quad_report.py): -5.7e-5 / +5.2e-5 (exact-zero windows), -7.0e-5 / +7.2e-5 (all tiles) on
+            # the CUDA path = 1.5e-9 of the largest term, while its ELBO is off by 6e-11 .. 8e-11; -4.6e-5 / +1.9e-5
+            # for the FP64 oracle in the reference's operation order, whose ELBO is off by 5.5e-10
             assert np.abs(terms - d['quad_terms']).max() <= 2 * bar(float(d['reg'])) * sc
         if 'quad_dderiv' in d:
             assert abs(d['quad_dir'] @ g - d['quad_dderiv']) <= REL * gs
