@@ -55,10 +55,77 @@ struct SymArgs {
   int accumulate;        // 1: C[z] += result, 0: C[z] = result
 };
 
+// DMMA tiles (i, j) of a warp block that a warp computes.  DIAG: only i >= j.  PART splits one diagonal 5 x 5 block
+// between two warps (balanced kernel below): part 1 = rows 0..2 and (3,0), (3,1) = 8 tiles, part 2 = (3,2), (3,3) and
+// row 4 = 7 tiles.
+template <bool DIAG, int PART>
+__device__ __forceinline__ constexpr bool sym_tile(int i, int j) {
+  return (!DIAG || i >= j) &&
+         (PART == 0 || (PART == 1 ? (i <= 2 || (i == 3 && j <= 1)) : (i == 4 || (i == 3 && j >= 2))));
+}
+
+// Copies of one operand panel (PANEL_B = false: A, true: B) of one k-tile into a stage, by one warp.
+template <bool KC, int G, int TB>
+struct SymLoader {
+  using Cfg = SymCfg<G, TB>;
+  const double* src;
+  const double* safe;
+  long ld;
+  int dst, kofs, kleft, lane, M;
+  __device__ __forceinline__ void init(const SymArgs& g, bool panel_b, int kbeg, int kend, int lane_) {
+    lane = lane_;
+    M = g.M;
+    ld = panel_b ? g.ldb : g.lda;
+    safe = panel_b ? g.B : g.A;
+    const int pofs = panel_b ? Cfg::PANEL : 0;
+    if (KC) {
+      const int r0 = lane >> 3, kc = (lane & 7) * 2;
+      src = safe + (long)r0 * ld + kbeg + kc;
+      dst = pofs + r0 * (SY_BK + 4) + kc;
+      kofs = kc;
+    } else {
+      src = safe + (long)kbeg * ld + lane * 2;
+      dst = pofs + lane * 2;
+      kofs = 0;
+    }
+    kleft = kend - kbeg;
+  }
+  __device__ __forceinline__ void issue(double* smem, int stage) {
+    double* base = smem + stage * Cfg::STAGE + dst;
+    if (KC) {
+      const bool kok = kofs < kleft;
+      const int r0 = lane >> 3;
+#pragma unroll 10
+      for (int r = 0; r < Cfg::GM / 4; ++r) {
+        const bool v = kok && r * 4 + r0 < M;
+        cp_async16(base + r * 4 * (SY_BK + 4), v ? src + (long)r * 4 * ld : safe, v);
+      }
+      src += SY_BK;
+    } else {
+#pragma unroll 4
+      for (int kk = 0; kk < SY_BK; ++kk) {
+        const bool kok = kk < kleft;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int m = (q * 32 + lane) * 2;
+          if (m < Cfg::GM) {
+            const bool v = kok && m < M;
+            cp_async16(base + kk * Cfg::LDN + q * 64, v ? src + (long)kk * ld + q * 64 : safe, v);
+          }
+        }
+      }
+      src += (long)SY_BK * ld;
+    }
+    kleft -= SY_BK;
+  }
+};
+
 // One consumer warp: block (gi, gj) of the lower triangle.  DIAG: gi == gj, only the DMMA tiles i >= j are computed.
-template <bool KC, bool DIAG, int G, int KSUB, int NCONS, int TB>
+// PART / PROD (balanced kernel): the warp computes one part of a split diagonal block and also feeds one operand panel
+// (PROD = 1: A, 2: B) through the cp.async pipeline.
+template <bool KC, bool DIAG, int G, int KSUB, int NCONS, int TB, int PART = 0, int PROD = 0>
 __device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int ktiles, int gi, int gj, int lane,
-                                            int sub, int blk) {
+                                            int sub, int blk, int kbeg = 0, int kend = 0) {
   constexpr int STEPS = (SY_BK / 4) / KSUB;      // k4 steps of a k-tile taken by this warp
   using Cfg = SymCfg<G, TB>;
   constexpr int LDN = Cfg::LDN, PANEL = Cfg::PANEL, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES;
@@ -82,9 +149,25 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int 
     return KC ? P[x * 8 * (SY_BK + 4) + k4 * 4] : P[k4 * 4 * LDN + x * 8];
   };
 
+  SymLoader<KC, G, TB> ldr;
+  if (PROD) {
+    ldr.init(g, PROD == 2, kbeg, kend, lane);
+#pragma unroll
+    for (int s0 = 0; s0 < STAGES - 1; ++s0) {
+      if (s0 < ktiles) ldr.issue(smem, s0);
+      cp_async_commit();
+    }
+  }
   int stage = 0;
   for (int kt = 0; kt < ktiles; ++kt) {
+    if (PROD) cp_async_wait<STAGES - 2>();
     __syncthreads();
+    if (PROD) {
+      int st2 = stage + STAGES - 1;
+      if (st2 >= STAGES) st2 -= STAGES;
+      if (kt + STAGES - 1 < ktiles) ldr.issue(smem, st2);
+      cp_async_commit();
+    }
     const double* Ap = smem + stage * STAGE + a_off;
     const double* Bp = smem + stage * STAGE + b_off;
     double fa[TB], fb[TB];
@@ -100,7 +183,7 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int 
         for (int i = 0; i < TB; ++i) {
 #pragma unroll
           for (int j = 0; j < TB; ++j) {
-            if (!DIAG || i >= j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            if (sym_tile<DIAG, PART>(i, j)) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
             if (more && i == TB - 1) fb[j] = ldf(Bp, k4 + 1, j);
           }
           if (more) fa[i] = ldf(Ap, k4 + 1, i);
@@ -110,7 +193,7 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int 
         for (int j = 0; j < TB; ++j) {
 #pragma unroll
           for (int i = 0; i < TB; ++i) {
-            if (!DIAG || i >= j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            if (sym_tile<DIAG, PART>(i, j)) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
             if (more && j == TB - 1) fa[i] = ldf(Ap, k4 + 1, i);
           }
           if (more) fb[j] = ldf(Bp, k4 + 1, j);
@@ -119,6 +202,7 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int 
     }
     if (++stage == STAGES) stage = 0;
   }
+  if (PROD) cp_async_wait<0>();
 
   if (KSUB > 1) {
     // add the KSUB partial accumulators of this block in a fixed order (sub 1, 2, .. into sub 0) through the drained
@@ -158,7 +242,7 @@ __device__ __forceinline__ void sym_consume(const SymArgs& g, double* smem, int 
 #pragma unroll
     for (int j = 0; j < TB; ++j) {
       const int col = gj * BLK + j * 8 + tig * 2;
-      if (col >= g.M || (DIAG && j > i)) continue;
+      if (col >= g.M || !sym_tile<DIAG, PART>(i, j)) continue;
       double2* p = reinterpret_cast<double2*>(C + (long)row * g.ldc + col);
       double v0 = acc[i][j][0], v1 = acc[i][j][1];
       if (g.accumulate) {
@@ -275,6 +359,33 @@ __global__ void __launch_bounds__((G * (G + 1) / 2 * KSUB + 1) * 32, 1) dgemm_sy
   else sym_consume<KC, false, G, KSUB, NCONS, TB>(g, smem, ktiles, gi, gj, lane, sub, blk);
 }
 
+// Balanced variant for the full order (G = 5, TB = 5: 160 < M <= 200).  The kernel above deals 10 full (25 DMMA tiles)
+// and 5 diagonal (15) warp blocks to the four SM sub-partitions as {80, 80, 90, 75} tiles per k4 step: the sub-partition
+// with 90 sets the pace (ncu: 23 % of the warp time at the k-tile barrier).  Here there is no dedicated producer warp:
+// 16 warps compute, one diagonal block is split 8 + 7 between the two warps that also feed the pipeline (one operand
+// panel each), and the sub-partitions carry {83, 82, 80, 80}:
+//   warp % 4 = 0:  F(1,0) F(2,0) F(2,1)  D(4,4) part 1 + panel A
+//   warp % 4 = 1:  F(3,0) F(3,1) F(3,2)  D(4,4) part 2 + panel B
+//   warp % 4 = 2:  F(4,0) F(4,1) D(0,0) D(1,1)
+//   warp % 4 = 3:  F(4,2) F(4,3) D(2,2) D(3,3)
+template <bool KC>
+__global__ void __launch_bounds__(512, 1) dgemm_sym16_kernel(const SymArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kbeg = blockIdx.x * g.k_per_split;
+  const int kend = min(g.K, kbeg + g.k_per_split);
+  if (kend <= kbeg) return;
+  const int ktiles = (kend - kbeg + SY_BK - 1) / SY_BK;
+  // (gi << 4 | gj) per warp
+  const unsigned long long tab = warp < 8 ? 0x4341312042403010ull : 0x3311444422003221ull;   // one byte per warp
+  const int ent = (int)((tab >> (8 * (warp & 7))) & 255);
+  const int gi = ent >> 4, gj = ent & 15;
+  if (warp == 12) sym_consume<KC, true, 5, 1, 16, 5, 1, 1>(g, smem, ktiles, gi, gj, lane, 0, 0, kbeg, kend);
+  else if (warp == 13) sym_consume<KC, true, 5, 1, 16, 5, 2, 2>(g, smem, ktiles, gi, gj, lane, 0, 0, kbeg, kend);
+  else if (gi == gj) sym_consume<KC, true, 5, 1, 16, 5>(g, smem, ktiles, gi, gj, lane, 0, 0);
+  else sym_consume<KC, false, 5, 1, 16, 5>(g, smem, ktiles, gi, gj, lane, 0, 0);
+}
+
 inline bool dgemm_sym_supported(int M) { return M >= 8 && M <= SY_MP && (M % 8) == 0; }
 
 // Warp blocks are TB x TB DMMA tiles (TB = 5: 40 rows, TB = 4: 32 rows), G <= 5 block rows; the launch for order M
@@ -337,7 +448,20 @@ inline cudaError_t dgemm_sym(cudaStream_t st, bool kc, int M, int K, const doubl
     case 34: CG_SYM_LAUNCH(3, 2, 4); break;
     case 44: CG_SYM_LAUNCH(4, 1, 4); break;
     case 54: CG_SYM_LAUNCH(5, 1, 4); break;
-    default: CG_SYM_LAUNCH(5, 1, 5); break;
+    default: {
+      static DeviceOnce attr_once;
+      unsigned long long attr_bit;
+      if (attr_once.need(&attr_bit)) {
+        cudaFuncSetAttribute((const void*)dgemm_sym16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SymCfg<5, 5>::SMEM_BYTES);
+        cudaFuncSetAttribute((const void*)dgemm_sym16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SymCfg<5, 5>::SMEM_BYTES);
+        attr_once.done(attr_bit);
+      }
+      if (kc) dgemm_sym16_kernel<true><<<splits, 512, SymCfg<5, 5>::SMEM_BYTES, st>>>(g);
+      else dgemm_sym16_kernel<false><<<splits, 512, SymCfg<5, 5>::SMEM_BYTES, st>>>(g);
+      break;
+    }
   }
 #undef CG_SYM_LAUNCH
   return cudaGetLastError();
