@@ -1,5 +1,5 @@
 """Text summary of an ncu report (`ncu -i X.ncu-rep --page raw --csv`): per launch, the metrics the roofline
-discussion in DESIGN.md cites.  Usage: python tools/ncu_summary.py report.ncu-rep > profiles/name.txt"""
+discussion in DESIGN.md cites.  Usage: python tools/ncu_summary.py report.ncu-rep | raw_page.csv > profiles/name.txt"""
 import csv
 import io
 import subprocess
@@ -13,7 +13,10 @@ WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'lts__t_sector_hit_rate.pct', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed']
-out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+if sys.argv[1].endswith('.csv'):      # an exported raw page (tools/gpu_final.sh keeps the CSV pages, not the reports)
+    out = open(sys.argv[1]).read()
+else:
+    out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 print('# ncu --set full --clock-control none, report %s' % sys.argv[1].split('/')[-1])
