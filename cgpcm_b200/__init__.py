@@ -5,7 +5,7 @@ Drop-in for ONE path of wesselb/cgpcm (``VCGPCM.from_recipe`` / ``precompute`` /
 FP64) behind the C-ABI of ``include/cgpcm_b200.h``.  There is no CPU fallback.
 """
 from . import batch, config, experiment, learn, sample, util
-from .cgpcm import VCGPCM, CGPCM, AKM, Session, Var, Objective, shard_bounds, window_costs, window_radius
+from .cgpcm import VCGPCM, CGPCM, AKM, Session, Var, Objective, shard_bounds, window_costs, window_radius, rebalance_costs
 from .data import Data, UncertainData
 from .engine import Engine, bvn_cdf, TERM_NAMES, n_params
 from ._lib import (build, lib, LIB_PATH, CgpcmError, GRAD_ALL, GRAD_S2, GRAD_S2F, GRAD_ALPHA, GRAD_GAMMA,

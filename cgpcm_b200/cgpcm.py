@@ -272,6 +272,27 @@ def shard_bounds(n, rank, world, cost=None):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def rebalance_costs(cost, bounds, times):
+    """Per-observation costs corrected by measured shard times: ``bounds[r] = (lo, hi)`` of rank ``r`` under ``cost`` and
+    ``times[r]`` the device time its sweeps took.  Every observation of shard ``r`` is rescaled by the ratio of the
+    shard's measured share to its modelled share, so that ``shard_bounds`` on the result moves the cuts towards equal
+    *measured* time (the model of ``window_costs`` is per observation; chunk windows are unions rounded to multiples
+    of eight and the GEMM kernels are less efficient on the narrow windows at the ends of a series: the end shards of
+    an 8-way split of the bench series ran 3 % and 10 % longer than the inner ones).  Pure host logic, no
+    communication: the caller gathers ``times``."""
+    cost = np.array(cost, dtype=np.float64)
+    times = np.asarray(times, dtype=np.float64)
+    if len(bounds) != times.shape[0] or np.any(times <= 0):
+        raise ValueError('one positive time per shard')
+    model = np.array([cost[lo:hi].sum() for lo, hi in bounds])
+    if np.any(model <= 0):
+        return cost
+    scale = (times / times.sum()) / (model / model.sum())
+    for (lo, hi), f in zip(bounds, scale):
+        cost[lo:hi] *= f
+    return cost
+
+
 def window_radius(alpha, gamma, omega, cull):
     """``|t - tx|`` beyond which every ``Ahx`` element has a Gaussian envelope below ``exp(-cull)``: the radius
     ``plan_chunks`` (csrc/cgpcm.cu) gives the windows of inducing inputs (``cull = 746``: exactly 0 in IEEE double)."""

@@ -106,7 +106,7 @@ struct Chunk {
   long n0;      // first observation
   int nv;       // valid observations
   int nc;       // padded observation count (multiple of 8)
-  int k_lo;     // first inducing input of the window (multiple of 8)
+  int k_lo;     // first inducing input of the window (even)
   int kwp;      // padded window width (multiple of 8)
   long off;     // element offset of this chunk's block in the sweep stores (prefix sum of nhp * nc * kwp)
 };
@@ -194,7 +194,7 @@ struct cgpcm_handle {
   std::string err;
   double timing[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long launches = 0;
-  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [7], [8]: before all-reduce #1 / #2
   // Side streams for the M x M factor / inverse chains that do not sit on the critical path of an evaluation: the
   // chains of Kh and Kx run beside each other (and beside the Axx sweep, which needs neither), those of the prior
   // covariance iKh + reg I and of the q(u) covariance beside the forward sweep.  Only the chain of P (which needs the
@@ -489,9 +489,13 @@ void plan_chunks_fixed(cgpcm_handle* h, const PsiConst& c, int chunk, std::vecto
       if (x >= tmin - R && x <= tmax + R) { lo = std::min(lo, k); hi = std::max(hi, k); }
     }
     if (hi < lo) { k_lo = 0; kwp = 8; return; }   // nothing in range: a token all-zero window
-    k_lo = lo / 8 * 8;
+    // The window starts at an EVEN inducing input (every kernel needs 16-byte aligned rows of the window blocks, not
+    // more) and is a multiple of 8 wide (DMMA row blocks).  Starting it at a multiple of 8 wasted up to 7 columns:
+    // whether a chunk got a 96- or a 104-wide window then depended on where its shard happened to begin.
+    k_lo = lo / 2 * 2;
     kwp = round_up(hi + 1 - k_lo, 8);
-    if (k_lo + kwp > h->nxp) kwp = h->nxp - k_lo;
+    if (kwp >= h->nxp) { k_lo = 0; kwp = h->nxp; }
+    else if (k_lo + kwp > h->nxp) k_lo = h->nxp - kwp;
   };
   while (n0 < N) {
     long rem = N - n0;
@@ -557,6 +561,11 @@ void plan_chunks(cgpcm_handle* h, const PsiConst& c, std::vector<Chunk>& out) {
       cost += el * (4.0 * h->nhp + 7.0 * ch.kwp) / 27e12 + el * 1.5e-11 + 0.21e-3;   // contractions + Psi kernels + per chunk
     }
     if (cost < best) { best = cost; out.swap(cand); h->chunk = chunk; }
+  }
+  if (getenv("CGPCM_DEBUG_PLAN")) {
+    fprintf(stderr, "plan: n_local %ld, budget %d, %zu chunks:", (long)h->n_local, h->chunk, out.size());
+    for (const Chunk& ch : out) fprintf(stderr, " (%d x %d @%d)", ch.nv, ch.kwp, ch.k_lo);
+    fprintf(stderr, "\n");
   }
 }
 
@@ -1470,6 +1479,7 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
     CK(cudaMemcpyAsync(h->fwd_tail, tail, sizeof tail, cudaMemcpyHostToDevice, st));
   }
   // ---- 3. all-reduce #1 (M_AXX0..M_Y are contiguous)
+  CK(cudaEventRecord(h->ev[7], st));     // this rank's own forward work ends here (the collective waits for the slowest rank)
   if (h->world > 1) {
     if (full) { if (allreduce(h, h->M(M_AXX0), 7 * l2)) return -2; }
     else { if (allreduce(h, h->M(M_C1), l2)) return -2; }
@@ -1607,10 +1617,13 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
       if (backward_sweep(h, ca, chunks, Hm, want_hyp, h->fwd_tail + 2)) return -2;
     }
     // ---- 6. all-reduce #2
+    CK(cudaEventRecord(h->ev[8], st));
     if (h->world > 1) {
       if (allreduce(h, h->M(M_HBAR), l2)) return -2;
       if (want_hyp && allreduce(h, h->fwd_tail + 2, 3)) return -2;
     }
+  } else {
+    CK(cudaEventRecord(h->ev[8], st));
   }
   CK(cudaEventRecord(h->ev[5], st));
   const double a = (h->causal ? 0.5 : 1.0) * sqrt(3.14159265358979323846 / (2.0 * alpha));
@@ -2831,6 +2844,13 @@ int cgpcm_elbo_grad(cgpcm_handle* h, const double* params, int32_t mode, uint32_
     h->timing[7] = h->gemm_flops;
     h->timing[8] = (double)h->gemm_launches;
     h->timing[9] = h->gemm_flops_exec;
+    {
+      // this rank's own sweep time, without the waits inside the collectives: what a caller balances shards with
+      float f = 0, b = 0;
+      cudaEventElapsedTime(&f, h->ev[1], h->ev[7]);
+      cudaEventElapsedTime(&b, h->ev[4], h->ev[8]);
+      h->timing[11] = f + b;
+    }
     if (is_device_ptr(elbo)) cudaMemcpy(elbo, &e, sizeof e, cudaMemcpyHostToDevice); else *elbo = e;
     if (terms) { if (is_device_ptr(terms)) cudaMemcpy(terms, tm, sizeof tm, cudaMemcpyHostToDevice); else memcpy(terms, tm, sizeof tm); }
   }

@@ -224,7 +224,8 @@ class Engine(object):
         self._ck(_lib.lib().cgpcm_last_timing(self._h, _lib.ptr(t)))
         return dict(total_ms=float(t[0]), forward_ms=float(t[1]), backward_ms=float(t[2]), algebra_ms=float(t[3]),
                     axx_ms=float(t[4]), gemm_ms=float(t[5]), launches=int(t[6]), gemm_flops=float(t[7]),
-                    gemm_launches=int(t[8]), gemm_flops_executed=float(t[9]), ahx_gen_ms=float(t[10]))
+                    gemm_launches=int(t[8]), gemm_flops_executed=float(t[9]), ahx_gen_ms=float(t[10]),
+                    own_sweeps_ms=float(t[11]))
 
 
 def bvn_cdf(x1, x2, rho):

@@ -178,6 +178,11 @@ int cgpcm_fpi_qz(cgpcm_handle* h, const double* params, const double* mu_z_in, c
 int cgpcm_elbo_qz(cgpcm_handle* h, const double* params, const double* mu_z, const double* var_z, double reg,
                   double* elbo, double* terms);
 
+/* Device times (ms) and counters of the last cgpcm_elbo_grad: [0] whole call, [1] forward sweep (incl. all-reduce #1),
+ * [2] backward sweep (incl. #2), [3] M x M algebra between them, [4] Axx kernel, [5] GEMM launches (option "profile"),
+ * [6] kernel launches, [7] algorithmic / [9] executed GEMM flops, [8] GEMM launches, [10] Ahx generation ("profile"),
+ * [11] this rank's own sweep time WITHOUT the waits inside the collectives (what a caller balances shards with:
+ * cgpcm_b200.rebalance_costs). */
 int cgpcm_last_timing(cgpcm_handle* h, double out[12]);
 
 /* The reference's native op: Phi_2(x1, x2; rho) element-wise on three FP64 vectors of length n

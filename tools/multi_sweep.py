@@ -16,7 +16,7 @@ import torch
 
 sys.path.insert(0, '.')
 import cgpcm_b200
-from cgpcm_b200.cgpcm import shard_bounds, window_costs, window_radius
+from cgpcm_b200.cgpcm import rebalance_costs, shard_bounds, window_costs, window_radius
 from tests.workload import sweep_workload
 
 ap = argparse.ArgumentParser()
@@ -49,6 +49,19 @@ for pt in a.points.split(','):
     eng.set_data(wl['t'][lo:hi], wl['y'][lo:hi], wl['th'], wl['tx'])
     for _ in range(a.warmup):
         out = eng.elbo_grad(wl['params'], reg=wl['reg'])
+    if world > 1:                       # shards of equal measured time (as bench.py does during its warm-up)
+        for _ in range(2):
+            tm = eng.last_timing()
+            mine = torch.tensor([tm['own_sweeps_ms']], dtype=torch.float64, device='cuda')
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            times = np.array([float(v.item()) for v in every])
+            bounds = [shard_bounds(n, r, world, cost) for r in range(world)]
+            cost = rebalance_costs(cost, bounds, times)
+            lo, hi = shard_bounds(n, rank, world, cost)
+            eng.set_data(wl['t'][lo:hi], wl['y'][lo:hi], wl['th'], wl['tx'])
+            out = eng.elbo_grad(wl['params'], reg=wl['reg'])
+            out = eng.elbo_grad(wl['params'], reg=wl['reg'])
     ms, flops = [], 0.0
     for _ in range(a.steps):
         torch.cuda.synchronize()
