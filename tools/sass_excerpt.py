@@ -21,8 +21,8 @@ for line in sass.splitlines():
         funcs[cur] = []
     elif cur and re.search(r'/\*[0-9a-f]{4}\*/', line):
         funcs[cur].append(line)
-HOT = ['dgemm_sl_kernel', 'dgemm_sym_kernel', 'dgemm_dmma_kernel', 'axx_sum_kernel', 'ahx_gen_kernel', 'ahx_dot_kernel',
-       'potrf_panel_kernel']
+HOT = ['dgemm_sl_kernel', 'dgemm_sym16_kernel', 'dgemm_sym_kernel', 'dgemm_dmma_kernel', 'axx_sum_kernel',
+       'ahx_gen_sep_kernel', 'ahx_dot_sep_kernel', 'ahx_gen_kernel', 'ahx_dot_kernel', 'potrf_panel_kernel']
 KEYS = ['DMMA', 'UBLKCP', 'SYNCS', 'LDGSTS', 'DFMA', 'DMUL', 'DADD', 'MUFU', 'BAR.SYNC']
 print('# cuobjdump -sass cgpcm_b200/lib/libcgpcm_b200.so (sm_100a), mnemonic counts per kernel instantiation')
 print('# %-64s %7s ' % ('kernel', 'instrs') + ' '.join('%8s' % k for k in KEYS))
