@@ -102,6 +102,8 @@ enum Sc {
   S_G_AHH_G, S_G_AXX_A, S_G_AXX_G, S_G_AXX_O, S_LOGDET_P0, S_LAM_LBAR0, S_S_BHH_S, S_LOGDET_KH, S_COUNT
 };
 
+constexpr int AXX_MAX_SLICES = 128;
+
 struct Chunk {
   long n0;      // first observation
   int nv;       // valid observations
@@ -178,6 +180,7 @@ struct cgpcm_handle {
   long axx_part_elems = 0;
   double* cheb_d = nullptr;    // Chebyshev table of the pair-hoisted BVN branch (bvn.cuh)
   int axx_slices = 0;
+  int axx_slices_opt = 0;      // option "axx_slices": 0 = automatic (axx_sweep)
   double* ypart = nullptr;     // [slices][nhp][ld] private Y accumulators
   int y_slices = 0;
   double* gpart = nullptr;     // partial sums of <Abar, dA/dtheta>
@@ -610,13 +613,13 @@ int ensure_ws(cgpcm_handle* h) {
 // sum_n Axx (and tangents) over this rank's observations -> M_AXX0..3
 int axx_sweep(cgpcm_handle* h, const PsiConst& c, const BvnTab& T, bool tangents, double* out4) {
   const int nt = (h->nx + AXX_TILE - 1) / AXX_TILE;
-  const int ntiles = nt * (nt + 1) / 2;
+  const int ntiles = nt * nt;        // 16 inducing inputs x 16 separations per tile (psi_kernels.cuh)
   // pair-hoisted Genz branch: causal model, rho >= 0.925 (rho = gamma / A is always positive here)
   const bool hoist = c.causal && !c.causal_id && T.high && T.rho > 0.0 && T.as_ > 0.0 && T.ng == 20;
   // Observation slices (grid.y).  Fewer slices would amortise the per-pair set-up of the hoisted branch over more
   // observations, but measured slower (13 slices: 15.4 ms against 13.7 ms at the bench shape, 2.59 against 2.32 ms on an
   // 8-GPU shard): the per-CTA observation ranges are cut by the windows, and more, smaller CTAs balance better.
-  int slices = h->axx_slices;
+  int slices = h->axx_slices_opt > 0 ? h->axx_slices_opt : h->axx_slices;
   dim3 grid(ntiles, slices);
   if (h->n_local > 0) {
     int deg = 0;
@@ -1039,8 +1042,8 @@ int cgpcm_create(cgpcm_handle** out, int device, int nh, int nx, int causal, int
   for (int k = 0; k < 2; ++k)
     if (cudaMalloc(&h->symacc[k], (size_t)SY_MAX_SPLITS * l2 * sizeof(double)) != cudaSuccess) return fail(-2);
   if (cudaMalloc(&h->cheb_d, (BVN_CHEB_MAXDEG + 1) * 20 * sizeof(double)) != cudaSuccess) return fail(-2);
-  h->axx_slices = 32;
-  h->axx_part_elems = (long)h->axx_slices * 4 * l2;
+  h->axx_slices = 64;      // tools/axx_probe.py: 10.88 / 10.45 / 10.37 ms at 32 / 64 / 96 (bench shape), 1.86 / 1.79 / 1.85 on an 8-way shard
+  h->axx_part_elems = (long)AXX_MAX_SLICES * 4 * l2;
   if (cudaMalloc(&h->axx_part, h->axx_part_elems * sizeof(double)) != cudaSuccess) return fail(-2);
   for (auto& e : h->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return fail(-2);
@@ -1149,6 +1152,11 @@ int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
   }
   if (!strcmp(key, "sl")) {
     h->sl_opt = (int)value;
+    return 0;
+  }
+  if (!strcmp(key, "axx_slices")) {
+    if (value < 0 || value > AXX_MAX_SLICES) { h->err = "axx_slices out of range"; return -1; }
+    h->axx_slices_opt = (int)value;      // 0 = automatic
     return 0;
   }
   if (!strcmp(key, "sep")) {

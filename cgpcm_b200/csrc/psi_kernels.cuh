@@ -98,9 +98,9 @@ inline void psi_make_const(double alpha, double gamma, double omega, int causal,
 constexpr int AXX_TILE = 16;
 
 // part layout: [slices][4][ld][ld]; slice blockIdx.y owns observations n_lo + blockIdx.y (+ gridDim.y ...)
-// of the tile's observation range and *stores* its lower-triangle partial sums (no zero-init needed).
-// When t is sorted the observation range of a (k, l) tile is cut down by binary search to the
-// observations within r_xx of both the tile's tx_k and tx_l ranges; everything outside is culled anyway.
+// of each pair's own observation range and *stores* its lower-triangle partial sums (no zero-init needed).
+// When t is sorted the range of a pair is the interval of observations whose envelope is not below exp(-cull)
+// (closed form + binary search); everything outside is culled anyway.
 template <bool TANGENTS, bool HOIST>
 __global__ void __launch_bounds__(256, HOIST ? 2 : 3) axx_sum_kernel(const double* __restrict__ t, int n_obs, int sorted,
                                                       const double* __restrict__ tx, int nx,
@@ -114,30 +114,40 @@ __global__ void __launch_bounds__(256, HOIST ? 2 : 3) axx_sum_kernel(const doubl
     for (int e = threadIdx.x; e < (deg + 1) * 20; e += blockDim.x) sB[e] = cheb[e];
     __syncthreads();
   }
-  // decode lower-triangular tile index
-  int tidx = blockIdx.x;
-  int tk = (int)((sqrt(8.0 * tidx + 1.0) - 1.0) * 0.5);
-  while ((tk + 1) * (tk + 2) / 2 <= tidx) ++tk;
-  while (tk * (tk + 1) / 2 > tidx) --tk;
-  int tl = tidx - tk * (tk + 1) / 2;
-  const int k0 = tk * AXX_TILE, l0 = tl * AXX_TILE;
-  const int k = k0 + (threadIdx.x >> 4);
-  const int l = l0 + (threadIdx.x & 15);
-  if (k >= nx || l >= nx || l > k) return;
+  // Thread <-> pair (k, l = k - s): a tile is 16 inducing inputs k x 16 separations s, and a warp holds two
+  // separations.  The observations with a non-zero element of a pair are an interval whose length depends on the
+  // separation only (below), so the lanes of a warp run (nearly) the same number of iterations, each over its own
+  // interval.  (Round 1 mapped 16 x 16 tiles of the (k, l) triangle to one common observation range per tile: ncu
+  // counted 23.4 active lanes per warp instruction -- the lanes whose pair was out of range idled through a full
+  // element evaluation of the others -- and the diagonal tiles ran half empty.)
+  const int nt = (nx + AXX_TILE - 1) / AXX_TILE;
+  const int kb = blockIdx.x / nt, sb = blockIdx.x - kb * nt;
+  const int k = kb * AXX_TILE + (threadIdx.x & 15);
+  const int l = k - (sb * AXX_TILE + (threadIdx.x >> 4));
+  if (k >= nx || l < 0) return;
   int n_lo = 0, n_hi = n_obs;
-  if (sorted && c.r_xx < 1e300) {
-    double kmin = tx[k0], kmax = kmin, lmin = tx[l0], lmax = lmin;
-    for (int j = 1; j < AXX_TILE; ++j) {
-      if (k0 + j < nx) { double v = tx[k0 + j]; kmin = fmin(kmin, v); kmax = fmax(kmax, v); }
-      if (l0 + j < nx) { double v = tx[l0 + j]; lmin = fmin(lmin, v); lmax = fmax(lmax, v); }
+  if (sorted) {
+    // G = -g1 (dk^2 + dl^2) + g2 dk dl = -(2 g1 - g2) u^2 - (2 g1 + g2) h^2 with u = t - (tx_k + tx_l) / 2 and
+    // h = (tx_k - tx_l) / 2: G >= -cull on |u| <= U.  The interval is widened by a few ulp; the element-wise test below
+    // still decides, so exactly the same elements are evaluated as with any other range.
+    const double a = tx[k], b = tx[l];
+    const double m = 0.5 * (a + b), hh = 0.5 * (a - b);
+    const double den = 2.0 * c.g1 - c.g2;
+    const double num = c.cull - (2.0 * c.g1 + c.g2) * hh * hh;
+    if (den > 0.0) {
+      if (num < 0.0) {
+        n_hi = 0;
+      } else {
+        const double U = sqrt(num / den) * (1.0 + 1e-12) + 1e-300;
+        const double lo = m - U - 1e-12 * fabs(m), hi = m + U + 1e-12 * fabs(m);
+        int x = 0, y = n_obs;                       // first n with t[n] >= lo
+        while (x < y) { int mid = (x + y) >> 1; if (__ldg(t + mid) < lo) x = mid + 1; else y = mid; }
+        n_lo = x;
+        y = n_obs;                                  // first n with t[n] > hi
+        while (x < y) { int mid = (x + y) >> 1; if (__ldg(t + mid) <= hi) x = mid + 1; else y = mid; }
+        n_hi = x;
+      }
     }
-    const double lo = fmax(kmin, lmin) - c.r_xx, hi = fmin(kmax, lmax) + c.r_xx;
-    int a = 0, b = n_obs;                       // first n with t[n] >= lo
-    while (a < b) { int m = (a + b) >> 1; if (__ldg(t + m) < lo) a = m + 1; else b = m; }
-    n_lo = a;
-    b = n_obs;                                  // first n with t[n] > hi
-    while (a < b) { int m = (a + b) >> 1; if (__ldg(t + m) <= hi) a = m + 1; else b = m; }
-    n_hi = a;
   }
   const double txk = tx[k], txl = tx[l];
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
