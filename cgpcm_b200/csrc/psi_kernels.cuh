@@ -151,9 +151,11 @@ __global__ void __launch_bounds__(256, HOIST ? 2 : 3) axx_sum_kernel(const doubl
   }
   const double txk = tx[k], txl = tx[l];
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  // HOIST (causal, rho >= 0.925): the pair constants of the Genz high-correlation branch (bvn.cuh)
+  // HOIST (causal, rho >= 0.925): the pair constants of the Genz high-correlation branch (bvn.cuh) -- 20 exp and a
+  // 20 x (deg + 1) table product per pair, skipped when this slice of the pair has no observation (most of them on a
+  // shard of a multi-GPU run)
   BvnPair R;
-  if (HOIST) bvn_pair_init((c.p - c.q) * (txk - txl), T, R, sA, sB, deg);
+  if (HOIST && n_lo + (int)blockIdx.y < n_hi) bvn_pair_init((c.p - c.q) * (txk - txl), T, R, sA, sB, deg);
   for (int n = n_lo + blockIdx.y; n < n_hi; n += gridDim.y) {
     const double tn = __ldg(t + n);
     const double dk = tn - txk, dl = tn - txl;
