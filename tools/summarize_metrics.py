@@ -56,7 +56,7 @@ out['kernels'] = dict(sorted(out['kernels'].items(), key=lambda kv: -kv[1]['ms']
 print(json.dumps(out, indent=1))
 if '--traffic' in sys.argv:
     tpath = sys.argv[sys.argv.index('--traffic') + 1]
-    sl = {n: k for n, k in out['kernels'].items() if 'dgemm_sl_kernel<13, 12, 0>' in n or 'dgemm_sl_kernel<13,12,0>' in n}
+    sl = {n: k for n, k in out['kernels'].items() if 'dgemm_sl_kernel<13, 12, 0' in n or 'dgemm_sl_kernel<13,12,0' in n}
     n, k = next(iter(sl.items())) if sl else (None, None)
     traffic = {'dram_bytes_per_step': out['total']['dram_bytes'],
                'fp64_flops_executed_per_step': out['total']['fp64_flops'],
