@@ -83,7 +83,10 @@ int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_
  * "gram" (0 = default: off; 1: cgpcm_precompute also builds the fourth-order tensor G = sum_n Ahx_n (x) Ahx_n, 8 (nh nx)^2
  * bytes, when it fits and pays, and MODE_FROZEN evaluations / fpi / SMF / predict_f contract with it instead of
  * sweeping over the observations; 2 = whenever it fits.  Opt-in because it is noisier: the cancellation against
- * m2 ~ iKh then happens after the sum over observations, ~sqrt(N) more rounding noise than the sweeps). */
+ * m2 ~ iKh then happens after the sum over observations, ~sqrt(N) more rounding noise than the sweeps),
+ * "sep" (1 = default: the Ahx construction / adjoint kernels of the default causal model use the separable form
+ * exp(E - z^2) = f_i g_nk, csrc/psi_kernels.cuh; 0 = the generic kernels, which causal_id = 1 and the acausal model
+ * always use), "axx_slices" (0 = default 64; observation slices of the Axx kernel's grid, <= 128). */
 int cgpcm_set_option(cgpcm_handle* h, const char* key, double value);
 
 /* Psi statistics at hyper-parameters hyp = {alpha, gamma, omega}: what `sess.run(mats[...])` returns
