@@ -102,7 +102,7 @@ enum Sc {
   S_G_AHH_G, S_G_AXX_A, S_G_AXX_G, S_G_AXX_O, S_LOGDET_P0, S_LAM_LBAR0, S_S_BHH_S, S_LOGDET_KH, S_COUNT
 };
 
-constexpr int AXX_MAX_SLICES = 128;
+constexpr int AXX_MAX_SLICES = 64;    // slice-private partial sums: 64 x 4 x ld^2 doubles (82 MB at M = 200)
 
 struct Chunk {
   long n0;      // first observation

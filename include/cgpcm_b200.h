@@ -86,7 +86,7 @@ int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_
  * m2 ~ iKh then happens after the sum over observations, ~sqrt(N) more rounding noise than the sweeps),
  * "sep" (1 = default: the Ahx construction / adjoint kernels of the default causal model use the separable form
  * exp(E - z^2) = f_i g_nk, csrc/psi_kernels.cuh; 0 = the generic kernels, which causal_id = 1 and the acausal model
- * always use), "axx_slices" (0 = default 64; observation slices of the Axx kernel's grid, <= 128). */
+ * always use), "axx_slices" (0 = default 64; observation slices of the Axx kernel's grid, <= 64). */
 int cgpcm_set_option(cgpcm_handle* h, const char* key, double value);
 
 /* Psi statistics at hyper-parameters hyp = {alpha, gamma, omega}: what `sess.run(mats[...])` returns
