@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(256) ahx_gen_kernel(const double* __restrict__
 // rows of the same (n, k) block, so g_nk costs one exp per AHX_IB elements: ahx_gen spends one exp per element instead of
 // two, ahx_dot none.  Padding (k >= nx, n >= n_valid) is expressed as d = 1e160, whose envelope is exactly 0.
 constexpr int AHX_IB = 8;
+constexpr int AHX_US = 4;         // observations ahx_gen_sep_kernel evaluates in lock-step (8: 143 registers, 0.9 ms slower)
 constexpr double AHX_FAR = 1e160;
 
 struct AhxRow { double th, e0, e1, z0, pf, fx; };   // pf = pref f_i, fx = f_i / sqrt(A)
@@ -378,34 +379,34 @@ __global__ void __launch_bounds__(256) ahx_gen_sep_kernel(const double* __restri
     const double txk = kok ? tx[kg] : 0.0;
 #pragma unroll
     for (int ii = 0; ii < AHX_IB; ++ii) ys[ii][threadIdx.x] = 0.0;
-    for (int n = n0; n < n1; n += AHX_U) {
-      double d[AHX_U], yv[AHX_U], w2[AHX_U], gk[AHX_U];
+    for (int n = n0; n < n1; n += AHX_US) {
+      double d[AHX_US], yv[AHX_US], w2[AHX_US], gk[AHX_US];
 #pragma unroll
-      for (int u = 0; u < AHX_U; ++u) {
+      for (int u = 0; u < AHX_US; ++u) {
         const bool live = kok && n + u < n_valid;
         d[u] = live ? __ldg(t + n + u) - txk : AHX_FAR;
         yv[u] = live ? __ldg(y + n + u) : 0.0;
         w2[u] = -c.omega * d[u] * d[u];
       }
-      cg_exp_neg<AHX_U, true>(w2, gk);
+      cg_exp_neg<AHX_US, true>(w2, gk);
       double* dst = A + ((long)i0 * nc + n) * kwp + k;
 #pragma unroll 1
       for (int ii = 0; ii < ib; ++ii, dst += (long)nc * kwp) {
         const AhxRow r = rows[ii];
-        double E[AHX_U], z[AHX_U], ex[AHX_U], q[AHX_U];
+        double E[AHX_US], z[AHX_US], ex[AHX_US], q[AHX_US];
         bool any = false;
 #pragma unroll
-        for (int u = 0; u < AHX_U; ++u) {
+        for (int u = 0; u < AHX_US; ++u) {
           E[u] = fma(d[u], fma(-c.e_dd, d[u], r.e1), r.e0);
           z[u] = fma(z1, d[u], r.z0);
           any = any || E[u] >= -c.cull;
         }
         double ysum = 0.0;
         if (any && i0 + ii < nh) {
-          cg_exp_neg<AHX_U, true>(E, ex);
-          cg_erfcx_abs<AHX_U>(z, q);
+          cg_exp_neg<AHX_US, true>(E, ex);
+          cg_erfcx_abs<AHX_US>(z, q);
 #pragma unroll
-          for (int u = 0; u < AHX_U; ++u) {
+          for (int u = 0; u < AHX_US; ++u) {
             const double rr = (r.pf * gk[u]) * q[u];
             double v = z[u] < 0.0 ? fma(p2, ex[u], -rr) : rr;
             v = E[u] >= -c.cull ? v : 0.0;
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(256) ahx_gen_sep_kernel(const double* __restri
           ys[ii][threadIdx.x] += ysum;
         } else {
 #pragma unroll
-          for (int u = 0; u < AHX_U; ++u)
+          for (int u = 0; u < AHX_US; ++u)
             if (n + u < n1) dst[(long)u * kwp] = 0.0;
         }
       }
