@@ -155,6 +155,12 @@ struct cgpcm_handle {
   // T1 = H A of the forward sweep (storeT) stay resident in HBM for the backward sweep instead of being
   // regenerated / recomputed -- 8 nhp N nx bytes each (32 GB at N = 1e5, M = 200; the B200 has 180 GB).
   int sep_opt = 1;             // 1: separable Ahx kernels for the default causal model (psi_kernels.cuh)
+  int last_info_tag = 0;       // matrix of the last failed factorisation (evaluate)
+  int tri_opt = 1;             // 1: Q / Hbar through the Cholesky factors of the window blocks (window_factors below)
+  double* wfac = nullptr;      // transposed factors of the chunks' window blocks, kwp x kwp each, back to back
+  long wfac_elems = 0;
+  WinDesc* wdesc = nullptr;
+  long wdesc_count = 0;
   int sl_opt = 1;              // 1: contractions with a small left operand run on the persistent kernel (dgemm_sl.cuh)
   int sms = 148;
   int store_opt = 1;
@@ -755,6 +761,67 @@ int right_mul_sym(cgpcm_handle* h, const double* X, const double* W, const Chunk
               ch.kwp, 0.0, out, ch.kwp);
 }
 
+// ---- Q = sum_n A_n iKx A_n^T and Hbar = sum_n A_n C1bar A_n^T through Cholesky factors of the window blocks ----------
+// Both middle matrices are definite on every window of inducing inputs: iKx[w] = L L^T, -C1bar[w] = r (Pinv / 2 +
+// lbar lbar^T / 2)[w] = L L^T.  With V' = A[:, w] L the contraction is the symmetric product V' V'^T, and the
+// right-multiply by a TRIANGULAR factor needs 54 % of the DMMAs of the product with the full block (dgemm_sl_tri).  The
+// factors of all chunks of a sweep come from one launch of window_chol_kernel (linalg.cuh), one CTA per chunk.
+bool tri_eligible(const cgpcm_handle* h, const std::vector<Chunk>& chunks) {
+  if (!h->tri_opt || !h->sl_opt || chunks.empty()) return false;
+  for (const Chunk& ch : chunks)
+    if (!dgemm_sl_tri_supported(ch.kwp, h->nhp * ch.nc)) return false;
+  return true;
+}
+
+// wfac[off_c ..] = transposed Cholesky factor of sign * M[window of chunk c]; offs[c] = off_c
+int window_factors(cgpcm_handle* h, const double* M, double sign, const std::vector<Chunk>& chunks, int tag,
+                   std::vector<long>& offs) {
+  std::vector<WinDesc> desc(chunks.size());
+  offs.resize(chunks.size());
+  long off = 0;
+  int kw_max = 8;
+  for (size_t ci = 0; ci < chunks.size(); ++ci) {
+    const Chunk& ch = chunks[ci];
+    desc[ci].k_lo = ch.k_lo; desc[ci].kw = ch.kwp; desc[ci].kv = std::max(0, std::min(ch.kwp, h->nx - ch.k_lo));
+    desc[ci].off = off;
+    offs[ci] = off;
+    off += (long)ch.kwp * ch.kwp;
+    kw_max = std::max(kw_max, ch.kwp);
+  }
+  if (off > h->wfac_elems) {
+    if (h->wfac) cudaFree(h->wfac);
+    h->wfac = nullptr; h->wfac_elems = 0;
+    CK(cudaMalloc(&h->wfac, off * sizeof(double)));
+    h->wfac_elems = off;
+  }
+  if ((long)chunks.size() > h->wdesc_count) {
+    if (h->wdesc) cudaFree(h->wdesc);
+    h->wdesc = nullptr; h->wdesc_count = 0;
+    CK(cudaMalloc(&h->wdesc, chunks.size() * sizeof(WinDesc)));
+    h->wdesc_count = (long)chunks.size();
+  }
+  // (pageable source: the copy is staged before the call returns, `desc` may go out of scope)
+  CK(cudaMemcpyAsync(h->wdesc, desc.data(), chunks.size() * sizeof(WinDesc), cudaMemcpyHostToDevice, h->st));
+  prof_close(h);
+  cudaError_t e = window_chol(h->st, M, h->ld, sign, h->wdesc, (int)chunks.size(), kw_max, h->wfac, h->info, tag);
+  L(h);
+  if (e != cudaSuccess) { h->err = std::string("window_chol launch failed: ") + cudaGetErrorString(e); return -2; }
+  return 0;
+}
+
+// out[(i,n)][l] = sum_{k <= l ...} X[(i,n)][k] L[k][l]  with St = L^T (upper triangular, kwp x kwp, dense)
+int right_mul_tri(cgpcm_handle* h, const double* X, const double* St, const Chunk& ch, double* out) {
+  const double full = 2.0 * ch.kwp * ch.kwp * (double)h->nhp * ch.nc;
+  h->gemm_flops_exec += full * dgemm_sl_tri_fraction(ch.kwp);
+  h->gemm_flops += (double)ch.kwp * (ch.kwp + 1.0) * h->nhp * ch.nc;     // the triangular product
+  h->gemm_launches++;
+  prof_gemm_begin(h);
+  cudaError_t e = dgemm_sl_tri(h->st, ch.kwp, h->nhp * ch.nc, St, ch.kwp, X, ch.kwp, out, ch.kwp, h->sms);
+  h->launches++;
+  if (e != cudaSuccess) { h->err = std::string("dgemm_sl_tri launch failed: ") + cudaGetErrorString(e); return -2; }
+  return 0;
+}
+
 // Forward sweep over chunks: C1 += A^T (H A), and when `full`: Q += A iKx A^T, Y += sum y A.
 int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& chunks, const double* Hm,
                   const double* iKx, bool full, bool keep_t) {
@@ -770,7 +837,12 @@ int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& 
   // resident slots; the frozen regime's blocks do not change between evaluations and are generated once
   const bool st = h->use_store;
   const bool have_a = st && !full && h->storeA_frozen_valid;
+  const bool tri = full && tri_eligible(h, chunks);
+  std::vector<long> woff;
+  if (tri && window_factors(h, iKx, 1.0, chunks, 6, woff)) return -2;
+  size_t ci = 0;
   for (const Chunk& ch : chunks) {
+    const size_t cidx = ci++;
     double* Ab = st ? h->storeA + ch.off : h->wsA;
     double* Tb = (st && keep_t) ? h->storeT + ch.off : h->wsT;
     if (!have_a && gen_chunk(h, c, ch, full, Ab)) return -2;
@@ -783,9 +855,15 @@ int forward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>& 
     if (full) {
       // V[(i,n)][l] = sum_k A[(i,n)][k] iKx[k][l]   (window block of iKx)
       // (computed as V^T = iKx A2^T with the transposed store: 200-row tiles split 104 + 96 instead of 128 + 72)
-      if (right_mul_sym(h, Ab, iKx, ch, h->wsV)) return -2;
-      // Q[i][j] += sum_(n,k) A[i][(n,k)] V[j][(n,k)]
-      if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, Ab, cols, h->wsV, cols, 1, 0)) return -2;
+      if (tri) {
+        // V' = A L with iKx[window] = L L^T;  Q += V' V'^T
+        if (right_mul_tri(h, Ab, h->wfac + woff[cidx], ch, h->wsV)) return -2;
+        if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsV, cols, h->wsV, cols, 1, 0)) return -2;
+      } else {
+        if (right_mul_sym(h, Ab, iKx, ch, h->wsV)) return -2;
+        // Q[i][j] += sum_(n,k) A[i][(n,k)] V[j][(n,k)]
+        if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, Ab, cols, h->wsV, cols, 1, 0)) return -2;
+      }
     }
   }
   if (st && !full) h->storeA_frozen_valid = true;
@@ -818,14 +896,25 @@ int backward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>&
     zero(h, h->gpart, h->gpart_elems);
   }
   const bool st = h->use_store;
+  // -C1bar = r (Pinv / 2 + lbar lbar^T / 2) is positive definite: Hbar = -sum_n (A_n L)(A_n L)^T with -C1bar[window] = L L^T
+  const bool tri = tri_eligible(h, chunks);
+  std::vector<long> woff;
+  if (tri && window_factors(h, h->M(M_C1BAR), -1.0, chunks, 7, woff)) return -2;
+  size_t ci = 0;
   for (const Chunk& ch : chunks) {
+    const size_t cidx = ci++;
     const double* Ab = st ? h->storeA + ch.off : h->wsA;
     if (!st && gen_chunk(h, c, ch, false)) return -2;
     const long cols = (long)ch.nc * ch.kwp;
-    // U1[(i,n)][l] = sum_k A[(i,n)][k] C1bar[k][l]
-    if (right_mul_sym(h, Ab, h->M(M_C1BAR), ch, h->wsV)) return -2;
-    // Hbar[i][j] += sum_(n,l) U1[i][(n,l)] A[j][(n,l)]
-    if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsV, cols, Ab, cols, 0, 0)) return -2;
+    if (tri) {
+      if (right_mul_tri(h, Ab, h->wfac + woff[cidx], ch, h->wsV)) return -2;
+      if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsV, cols, h->wsV, cols, 0, 0)) return -2;
+    } else {
+      // U1[(i,n)][l] = sum_k A[(i,n)][k] C1bar[k][l]
+      if (right_mul_sym(h, Ab, h->M(M_C1BAR), ch, h->wsV)) return -2;
+      // Hbar[i][j] += sum_(n,l) U1[i][(n,l)] A[j][(n,l)]
+      if (gemm_splitk_sym(h, true, true, h->nhp, (int)cols, h->wsV, cols, Ab, cols, 0, 0)) return -2;
+    }
     if (full) {
       // T1 = H A (kept from the forward sweep when stored) ;  Abar = T1 Wx  (window block)
       const double* Tb = st ? h->storeT + ch.off : h->wsT;
@@ -848,6 +937,11 @@ int backward_sweep(cgpcm_handle* h, const PsiConst& c, const std::vector<Chunk>&
     }
   }
   if (sym_finish(h, 0, h->nhp, h->M(M_HBAR))) return -2;
+  if (tri) {
+    double* hb = h->M(M_HBAR);
+    ew(h->st, h->ld * h->ld, [=] __device__(long idx) { hb[idx] = -hb[idx]; });
+    L(h);
+  }
   if (full) {
     sum3_kernel<<<1, 1024, 0, h->st>>>(h->gpart, gneed, g3);
     L(h);
@@ -1064,6 +1158,8 @@ int cgpcm_destroy(cgpcm_handle* h) {
                     h->wsV, h->axx_part, h->ypart, h->gpart, h->symacc[0], h->symacc[1], h->storeA, h->storeT, h->cheb_d, h->gram};
   for (double* p : ptrs)
     if (p) cudaFree(p);
+  if (h->wfac) cudaFree(h->wfac);
+  if (h->wdesc) cudaFree(h->wdesc);
   if (h->info) cudaFree(h->info);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
@@ -1157,6 +1253,10 @@ int cgpcm_set_option(cgpcm_handle* h, const char* key, double value) {
   if (!strcmp(key, "axx_slices")) {
     if (value < 0 || value > AXX_MAX_SLICES) { h->err = "axx_slices out of range"; return -1; }
     h->axx_slices_opt = (int)value;      // 0 = automatic
+    return 0;
+  }
+  if (!strcmp(key, "tri")) {
+    h->tri_opt = (int)value;
     return 0;
   }
   if (!strcmp(key, "sep")) {
@@ -1346,8 +1446,23 @@ namespace cgimpl {
 // `sample_host` (nh values, or NULL): the stochastic SMF bound elbo(smf=True, sample=...) (src/core/cgpcm.py:527-531):
 // the optimal q(z) is built from (sample, sample sample^T) instead of the moments of q(u); value only.  `loglik`
 // then also receives the pseudo-log-likelihood that VCGPCM.sample() hands to the slice sampler (cgpcm.py:857-866).
+int evaluate_once(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad_mask, double reg, bool freeze,
+                  double* elbo, double* terms, double* grad, const double* sample_host, double* loglik);
+
 int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad_mask, double reg, bool freeze,
              double* elbo, double* terms, double* grad, const double* sample_host = nullptr, double* loglik = nullptr) {
+  h->last_info_tag = 0;
+  int rc = evaluate_once(h, params_host, mode, grad_mask, reg, freeze, elbo, terms, grad, sample_host, loglik);
+  if (rc == -3 && h->tri_opt && (h->last_info_tag == 6 || h->last_info_tag == 7)) {
+    // a window block lost definiteness in FP64: contract with the full blocks from now on (the reference's formulation)
+    h->tri_opt = 0;
+    rc = evaluate_once(h, params_host, mode, grad_mask, reg, freeze, elbo, terms, grad, sample_host, loglik);
+  }
+  return rc;
+}
+
+int evaluate_once(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad_mask, double reg, bool freeze,
+                  double* elbo, double* terms, double* grad, const double* sample_host, double* loglik) {
   const int nh = h->nh, nx = h->nx, nhp = h->nhp, nxp = h->nxp;
   const long ld = h->ld, l2 = ld * ld;
   const long nvar = (long)nh * (nh + 1) / 2;
@@ -1802,12 +1917,14 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
   const double Ng = hs[S_COUNT + 0], sum_y2 = hs[S_COUNT + 1];
   if (info[0]) h->prior_valid = false;
   if (info[0]) {
-    static const char* names[] = {"?", "Kh", "Kx", "P", "iKh + reg I (prior of q(u))", "q(u) covariance"};
+    static const char* names[] = {"?", "Kh", "Kx", "P", "iKh + reg I (prior of q(u))", "q(u) covariance",
+                                  "iKx (a window block)", "-C1bar (a window block)"};
     int tag = info[0] / 100000;
     char b[160];
-    snprintf(b, sizeof b, "matrix %s is not positive definite (pivot %d)", tag >= 1 && tag <= 5 ? names[tag] : "?",
+    snprintf(b, sizeof b, "matrix %s is not positive definite (pivot %d)", tag >= 1 && tag <= 7 ? names[tag] : "?",
              info[0] % 100000);
     h->err = b;
+    h->last_info_tag = tag;
     return -3;
   }
   double sum_b, tr_bhh_m2 = hs[S_TR_BHH_M2];
@@ -2917,6 +3034,17 @@ int cgpcm_dgemm(int a_kc, int b_kc, int c_tr, int M, int N, int K, double alpha,
               c_split_stride, lower_only);
   }
   if (e != cudaSuccess) return -2;
+  return cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess ? 0 : -2;
+}
+
+int cgpcm_dgemm_tri(int M, int N, const double* S, int64_t lds, const double* B, int64_t ldb, double* C, int64_t ldc,
+                    void* stream) {
+  if (!S || !B || !C || (lds % 2) || (ldb % 2) || (ldc % 2)) return -1;
+  if (!dgemm_sl_tri_supported(M, N)) return -1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2) sms = 148;
+  if (dgemm_sl_tri((cudaStream_t)stream, M, N, S, lds, B, ldb, C, ldc, sms) != cudaSuccess) return -2;
   return cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess ? 0 : -2;
 }
 

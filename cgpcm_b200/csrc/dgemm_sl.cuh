@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <type_traits>
 
 #include "dgemm_dmma.cuh"
@@ -80,7 +81,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // One consumer warp's work on one output tile: MB x 2 blocks, K in k-tiles streamed through the ring.
-template <int MB, bool B_KC, int SKT>
+// TRI (one-half variants, K <= 112): the resident operand is UPPER TRIANGULAR, S[m][k] = 0 for k < m -- the transposed
+// Cholesky factor of a window block (cgpcm.cu: window_factors).  Row block mb is zero in every k4 step that ends before
+// column 8 mb, so its DMMAs and fragment loads are not issued: 54 % of the DMMAs of the full product at K = 96.  The
+// k-tile index is a template argument (the set of active blocks must be known at compile time: a run-time condition
+// around mma.sync costs a WARPSYNC and a branch per step).
+template <int MB, bool B_KC, int SKT, bool TRI = false>
 __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* Ssm, const double* ring,
                                                 uint64_t* full, uint64_t* empty, int& stage, uint32_t& phase,
                                                 int nkt, int m_base, int rows, int n0, int lane, int wq,
@@ -134,9 +140,51 @@ __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* S
     if (lane == 0) mbar_arrive(empty + stage);
     if (++stage == g.stages) { stage = 0; phase ^= 1u; }
   };
+  auto ktile_tri = [&](auto kt_tag, auto steps_tag) {
+    constexpr int KT = decltype(kt_tag)::value, STEPS = decltype(steps_tag)::value;
+    const double* Sk = Sp + KT * SL_BK;
+    double fa[MB], fb[2][2];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb)
+      if (mb <= ((KT * SL_BK + 3) >> 3)) fa[mb] = Sk[mb * 8 * sk];
+    mbar_wait(full + stage, phase);
+    const double* Bp = ring + stage * TILE + b_off;
+    load_b(Bp, 0, fb[0]);
+#pragma unroll
+    for (int k4 = 0; k4 < STEPS; ++k4) {
+      const bool more = k4 + 1 < STEPS;
+      const int mx = (KT * SL_BK + k4 * 4 + 3) >> 3;        // last row block with a non-zero in this k4 step
+      const int mx1 = (KT * SL_BK + k4 * 4 + 7) >> 3;       // ... in the next one
+      if (more) load_b(Bp, k4 + 1, fb[(k4 + 1) & 1]);
+      if (k4 == 1 && stagger && KT == min(6, nkt - 1)) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(stagger);
+      }
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        if (mb <= mx) {
+          dmma_8x8x4(acc[mb][0][0], acc[mb][0][1], fa[mb], fb[k4 & 1][0]);
+          dmma_8x8x4(acc[mb][1][0], acc[mb][1][1], fa[mb], fb[k4 & 1][1]);
+        }
+        if (more && mb >= 1 && mb - 1 <= mx1) fa[mb - 1] = Sk[(mb - 1) * 8 * sk + (k4 + 1) * 4];
+      }
+      if (more && MB - 1 <= mx1) fa[MB - 1] = Sk[(MB - 1) * 8 * sk + (k4 + 1) * 4];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + stage);
+    if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+  };
   const int nfull = g.K / SL_BK;
-  for (int kt = 0; kt < nfull; ++kt) ktile(kt, std::integral_constant<int, 4>());
-  if (nfull < nkt) ktile(nfull, std::integral_constant<int, 2>());
+  if (TRI) {
+#define CG_SL_KT(KT_)                                                                                    \
+  if (KT_ < nfull) ktile_tri(std::integral_constant<int, KT_>(), std::integral_constant<int, 4>());     \
+  else if (KT_ < nkt) ktile_tri(std::integral_constant<int, KT_>(), std::integral_constant<int, 2>());
+    CG_SL_KT(0) CG_SL_KT(1) CG_SL_KT(2) CG_SL_KT(3) CG_SL_KT(4) CG_SL_KT(5) CG_SL_KT(6)
+#undef CG_SL_KT
+  } else {
+    for (int kt = 0; kt < nfull; ++kt) ktile(kt, std::integral_constant<int, 4>());
+    if (nfull < nkt) ktile(nfull, std::integral_constant<int, 2>());
+  }
 
   // epilogue
   const int cols = g.N - n0;
@@ -192,7 +240,7 @@ __device__ __forceinline__ void sl_consume_tile(const SlArgs& g, const double* S
 template <int MB0, bool NARROW>
 struct SlSk { static constexpr int value = NARROW ? MB0 * 8 + 4 : SL_SK; };
 
-template <int MB0, int MB1, bool B_KC, bool NARROW>
+template <int MB0, int MB1, bool B_KC, bool NARROW, bool TRI = false>
 __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
   extern __shared__ __align__(128) unsigned char sl_smem_raw[];
   constexpr int TILE = B_KC ? SL_TILE_K : SL_TILE_N;
@@ -289,7 +337,7 @@ __global__ void __launch_bounds__(SL_NT, 1) dgemm_sl_kernel(const SlArgs g) {
     const int n0 = (q + it * cq) * SL_BN;
     uint64_t* sg = it == 0 ? stagger : nullptr;
     if constexpr (MB1 == 0 || MB1 == MB0) {
-      sl_consume_tile<MB0, B_KC, sk>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
+      sl_consume_tile<MB0, B_KC, sk, TRI>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
     } else {
       if (half == 0)
         sl_consume_tile<MB0, B_KC, sk>(g, Ssm, ring, full, empty, stage, phase, nkt, m_base, rows, n0, lane, wq, sg);
@@ -337,6 +385,45 @@ inline void dgemm_sl_launch(cudaStream_t st, bool b_kc, SlArgs g, int sms) {
   const size_t smem = dgemm_sl_smem(MB0, sk, b_kc, g.stages);
   if (b_kc) dgemm_sl_kernel<MB0, MB1, true, NARROW><<<sms, SL_NT, smem, st>>>(g);
   else dgemm_sl_kernel<MB0, MB1, false, NARROW><<<sms, SL_NT, smem, st>>>(g);
+}
+
+template <int MB0>
+inline void dgemm_sl_launch_tri(cudaStream_t st, SlArgs g, int sms) {
+  static DeviceOnce attr_once;
+  unsigned long long attr_bit;
+  if (attr_once.need(&attr_bit)) {
+    cudaFuncSetAttribute((const void*)dgemm_sl_kernel<MB0, 0, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    attr_once.done(attr_bit);
+  }
+  constexpr int sk = SlSk<MB0, true>::value;
+  g.stages = dgemm_sl_stages(MB0, sk, true);
+  const size_t smem = dgemm_sl_smem(MB0, sk, true, g.stages);
+  dgemm_sl_kernel<MB0, 0, true, true, true><<<sms, SL_NT, smem, st>>>(g);
+}
+
+inline bool dgemm_sl_tri_supported(int M, int N) { return dgemm_sl_supported(M, N, M) && M <= SL_MB * 8; }
+
+// C[n*ldc + m] = sum_{k >= m} S[m*lds + k] B[n*ldb + k]  for an UPPER-TRIANGULAR M x M operand S (everything below the
+// diagonal is taken as 0 without being read as such: those DMMA blocks are skipped).  DMMAs executed relative to the
+// full product: dgemm_sl_tri_fraction(M).
+inline cudaError_t dgemm_sl_tri(cudaStream_t st, int M, int N, const double* S, long lds, const double* B, long ldb,
+                                double* C, long ldc, int sms = 148) {
+  SlArgs g;
+  g.S = S; g.B = B; g.C = C; g.M = M; g.N = N; g.K = M; g.lds = lds; g.ldb = ldb; g.ldc = ldc; g.alpha = 1.0;
+  g.ctas0 = sms;
+  switch (dgemm_sl_blocks(M / 8)) {
+    case 5: dgemm_sl_launch_tri<5>(st, g, sms); break;
+    case 9: dgemm_sl_launch_tri<9>(st, g, sms); break;
+    case 12: dgemm_sl_launch_tri<12>(st, g, sms); break;
+    default: dgemm_sl_launch_tri<13>(st, g, sms); break;
+  }
+  return cudaGetLastError();
+}
+inline double dgemm_sl_tri_fraction(int M) {
+  const int mb = M / 8;
+  long act = 0;
+  for (int k4 = 0; k4 * 4 < M; ++k4) act += std::min(mb, ((k4 * 4 + 3) >> 3) + 1);
+  return (double)act / ((double)mb * (M / 4));
 }
 
 // b_kc = false: C[m*ldc + n] = alpha sum_k S[m*lds + k] B[k*ldb + n];  b_kc = true: C[n*ldc + m] = alpha sum_k S[m*lds + k] B[n*ldb + k]

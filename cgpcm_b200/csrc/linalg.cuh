@@ -127,6 +127,66 @@ inline cudaError_t potrf_lower(cudaStream_t st, double* A, int np, long ld, int*
   return cudaGetLastError();
 }
 
+// Batched Cholesky of window blocks of one symmetric matrix: CTA b factors  W_b = sign * M[k_lo : k_lo + kw, same]
+// (rows / columns >= kv are padding: identity) in shared memory and writes the TRANSPOSED factor, the upper-triangular
+// S_b[l][k] = L_b[k][l], dense kw x kw at out + off_b -- the resident operand of dgemm_sl_tri.  The windows are the
+// chunks' windows of inducing inputs: W_b = iKx[window] (sign +1) or -C1bar[window] (sign -1), both positive definite.
+struct WinDesc { int k_lo, kw, kv; long off; };
+
+__global__ void __launch_bounds__(256) window_chol_kernel(const double* __restrict__ M, long ld, double sign,
+                                                          const WinDesc* __restrict__ desc, double* __restrict__ out,
+                                                          int* __restrict__ info, int info_tag) {
+  extern __shared__ double Wsm[];
+  __shared__ int bad;
+  const WinDesc d = desc[blockIdx.x];
+  const int n = d.kw, P = n + 1, tid = threadIdx.x;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < n * n; e += blockDim.x) {
+    const int r = e / n, c = e - r * n;
+    double v = r == c ? 1.0 : 0.0;
+    if (r < d.kv && c < d.kv) v = sign * M[(long)(d.k_lo + r) * ld + d.k_lo + c];
+    Wsm[r * P + c] = v;
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+  for (int j = 0; j < n; ++j) {
+    if (tid == 0) {
+      double dj = Wsm[j * P + j];
+      if (!(dj > 0.0)) { bad = j + 1; dj = 1.0; }
+      Wsm[j * P + j] = sqrt(dj);
+    }
+    __syncthreads();
+    const double djj = Wsm[j * P + j];
+    for (int r = j + 1 + tid; r < n; r += blockDim.x) Wsm[r * P + j] /= djj;
+    __syncthreads();
+    for (int c = j + 1 + tx; c < n; c += 32) {
+      const double lc = Wsm[c * P + j];
+      for (int r = j + 1 + ty; r < n; r += 8)
+        if (c <= r) Wsm[r * P + c] -= Wsm[r * P + j] * lc;
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && bad && info) atomicCAS(info, 0, info_tag * 100000 + d.k_lo + bad);
+  double* o = out + d.off;
+  for (int e = tid; e < n * n; e += blockDim.x) {
+    const int l = e / n, k = e - l * n;
+    o[e] = k >= l ? Wsm[k * P + l] : 0.0;
+  }
+}
+
+inline cudaError_t window_chol(cudaStream_t st, const double* M, long ld, double sign, const WinDesc* desc_d, int count,
+                               int kw_max, double* out, int* info, int info_tag) {
+  static DeviceOnce attr_once;
+  unsigned long long attr_bit;
+  if (attr_once.need(&attr_bit)) {
+    cudaFuncSetAttribute((const void*)window_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 121 * 8);
+    attr_once.done(attr_bit);
+  }
+  if (count <= 0) return cudaSuccess;
+  window_chol_kernel<<<count, 256, (size_t)kw_max * (kw_max + 1) * sizeof(double), st>>>(M, ld, sign, desc_d, out, info, info_tag);
+  return cudaGetLastError();
+}
+
 // X diagonal blocks = inverse of the diagonal blocks of L; rest of X zeroed.  grid = number of blocks.
 __global__ void __launch_bounds__(256) trtri_diag_kernel(const double* __restrict__ L, double* __restrict__ X, int np,
                                                          long ld) {

@@ -86,7 +86,11 @@ int cgpcm_set_data(cgpcm_handle* h, const double* t, const double* y, int64_t n_
  * m2 ~ iKh then happens after the sum over observations, ~sqrt(N) more rounding noise than the sweeps),
  * "sep" (1 = default: the Ahx construction / adjoint kernels of the default causal model use the separable form
  * exp(E - z^2) = f_i g_nk, csrc/psi_kernels.cuh; 0 = the generic kernels, which causal_id = 1 and the acausal model
- * always use), "axx_slices" (0 = default 64; observation slices of the Axx kernel's grid, <= 64). */
+ * always use), "axx_slices" (0 = default 64; observation slices of the Axx kernel's grid, <= 64),
+ * "tri" (1 = default: when every chunk has a window of <= 104 inducing inputs, Q = sum A iKx A^T and Hbar = sum A C1bar A^T
+ * are contracted as V' V'^T with V' = A L and L L^T = iKx[window] / -C1bar[window] -- the triangular right-multiply needs
+ * 54 % of the DMMAs; if a window block is not positive definite in FP64 the handle falls back to 0 = the products with
+ * the full blocks, the reference's formulation, and repeats the evaluation). */
 int cgpcm_set_option(cgpcm_handle* h, const char* key, double value);
 
 /* Psi statistics at hyper-parameters hyp = {alpha, gamma, omega}: what `sess.run(mats[...])` returns
@@ -205,6 +209,11 @@ int cgpcm_dgemm(int a_kc, int b_kc, int c_tr, int M, int N, int K, double alpha,
  * work: NULL or a device buffer of 148 * M * M doubles for the K-slice partial results. */
 int cgpcm_dgemm_sym(int kc, int M, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                     int64_t ldc, double* work, void* stream);
+/* cgpcm_dgemm_tri: C[n*ldc + m] = sum_{k >= m} S[m*lds + k] B[n*ldb + k] for an upper-triangular M x M operand S
+ * (16 <= M <= 104, M % 8 == 0, N >= 9472): the right-multiply by the transposed Cholesky factor of a window block;
+ * DMMA blocks below the diagonal are not issued. */
+int cgpcm_dgemm_tri(int M, int N, const double* S, int64_t lds, const double* B, int64_t ldb, double* C, int64_t ldc,
+                    void* stream);
 int cgpcm_cholinv(double* A, double* Ainv, double* logdet, int n, int64_t ld, int* info_host);
 /* cgpcm_math_test: the in-register exp / erfc of the Psi kernels (csrc/cgmath.cuh) on n arguments (host or device):
  * out_exp[i] = exp(min(x[i], 0)), out_erfc[i] = erfc(x[i]), evaluated four at a time; *mismatch = elements whose

@@ -238,3 +238,21 @@ def test_flushing_exp_and_erfcx_against_mpmath():
         want = mp.erfc(mp.mpf(a)) * mp.exp(mp.mpf(a) ** 2)
         worst = max(worst, float(abs(mp.mpf(float(got)) - want) / mp.mpf(float(np.spacing(float(want))))))
     assert worst <= 5.0, worst
+
+
+@pytest.mark.parametrize('M', [40, 72, 88, 96, 104])
+def test_triangular_right_multiply_against_torch(M):
+    """dgemm_sl_tri (csrc/dgemm_sl.cuh): C[n][m] = sum_{k >= m} S[m][k] B[n][k] for an upper-triangular resident operand,
+    with the DMMA blocks below the diagonal skipped -- the right-multiply by the transposed Cholesky factor of a window
+    block (Q = sum A iKx A^T as V' V'^T).  Against torch on the full columns, ragged tail included."""
+    import torch
+    N = 64 * 148 + 8 * 37
+    g = torch.Generator(device='cpu').manual_seed(M)
+    S = torch.triu(torch.randn(M, M, dtype=torch.float64, generator=g)).cuda()
+    B = torch.randn(N, M, dtype=torch.float64, generator=g).cuda()
+    C = torch.full((N, M), float('nan'), dtype=torch.float64, device='cuda')
+    rc = _lib.lib().cgpcm_dgemm_tri(M, N, S.data_ptr(), M, B.data_ptr(), M, C.data_ptr(), M, None)
+    assert rc == 0
+    ref = B @ S.t()
+    err = float((C - ref).abs().max() / ref.abs().max())
+    assert err < 1e-14, err
