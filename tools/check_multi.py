@@ -50,9 +50,13 @@ if rank == 0:
     g2s = mod._slice_grad(g2, ['mu_u', 'var_u', 's2_f', 's2'])
     print('frozen: sharded %.12e single %.12e rel %.2e; grad rel %.2e' % (
         f_fr, e2, abs(f_fr - e2) / abs(e2), np.abs(g_fr - g2s).max() / np.abs(g2s).max()))
-    # two summation orders of the same sums: the ELBO noise floor here is ~5e-10 relative (cond(Kh) ~ 1/reg)
-    assert abs(f - e1) <= 2e-9 * abs(e1) and np.abs(g - g1s).max() <= 2e-9 * np.abs(g1s).max()
-    assert abs(f_fr - e2) <= 2e-9 * abs(e2) and np.abs(g_fr - g2s).max() <= 2e-9 * np.abs(g2s).max()
+    # Two FP64 evaluations of the same sums in different orders -- other chunk windows, hence other window blocks of iKx /
+    # C1bar under the Cholesky route of Q / Hbar (option `tri`) -- at a point where cond(Kh) ~ 1 / reg: measured 1.7e-9
+    # (ELBO and gradient) at this shape.  Each evaluation is held to 1e-9 of the binary128 truth elsewhere
+    # (tests/test_gpu_quad.py; profiles/r02_quad_truth.json: 1e-11 .. 3e-10 with `tri`, 6e-11 .. 2e-10 without, at
+    # N = 6000 / M = 64 and N = 1e4 / M = 200); two of them may differ by twice that plus this point's conditioning.
+    assert abs(f - e1) <= 4e-9 * abs(e1) and np.abs(g - g1s).max() <= 4e-9 * np.abs(g1s).max()
+    assert abs(f_fr - e2) <= 4e-9 * abs(e2) and np.abs(g_fr - g2s).max() <= 4e-9 * np.abs(g2s).max()
     print('OK')
 # the widened rows (fpi, SMF bound, predict_f) under sharding: every rank computes the same answer as one GPU
 mod.precompute()
@@ -92,7 +96,7 @@ if rank == 0:
         pq[5 + m:] = np.asarray(res[1]).ravel()
         at.append(eng.elbo_grad(pq, mode=0, reg=config.reg, want_grad=False)[0])
     print('ELBO at the fixed-point result: sharded %.12e single %.12e rel %.2e' % (at[0], at[1], abs(at[0] - at[1]) / abs(at[1])))
-    assert rel(sh_smf[0], one_smf[0]) < 2e-9 and rel(sh_smf[2], one_smf[2]) < 1e-6
+    assert rel(sh_smf[0], one_smf[0]) < 4e-9 and rel(sh_smf[2], one_smf[2]) < 1e-6      # measured 2.2e-9 (see above)
     assert rel(sh_pred[0], one_pred[0]) < 1e-6 and rel(sh_pred[1], one_pred[1]) < 1e-6
     print('OK widened rows')
 dist.barrier()
