@@ -1453,8 +1453,10 @@ int evaluate(cgpcm_handle* h, const double* params_host, int mode, uint32_t grad
              double* elbo, double* terms, double* grad, const double* sample_host = nullptr, double* loglik = nullptr) {
   h->last_info_tag = 0;
   int rc = evaluate_once(h, params_host, mode, grad_mask, reg, freeze, elbo, terms, grad, sample_host, loglik);
-  if (rc == -3 && h->tri_opt && (h->last_info_tag == 6 || h->last_info_tag == 7)) {
-    // a window block lost definiteness in FP64: contract with the full blocks from now on (the reference's formulation)
+  if (rc == -3 && h->tri_opt && (h->last_info_tag == 6 || h->last_info_tag == 7) && h->world == 1) {
+    // a window block lost definiteness in FP64: contract with the full blocks from now on (the reference's formulation).
+    // (With several ranks the evaluation is NOT repeated here -- the other ranks may not have seen a failure and a
+    // second pass would issue collectives they do not join; the caller gets the error and can set "tri" to 0 on every rank.)
     h->tri_opt = 0;
     rc = evaluate_once(h, params_host, mode, grad_mask, reg, freeze, elbo, terms, grad, sample_host, loglik);
   }
