@@ -95,9 +95,31 @@ def ahh_with_tangents(th, alpha, gamma):
     return F, dF + [0 * F]
 
 
-def elbo_grad(params, t, y, th, tx, reg, mode=1, frozen=None):
+def windowed_gram(A, W, chunk, sign=1.0):
+    """``sum_n A_n W A_n^T`` the way the CUDA path contracts it with option ``tri`` (csrc/cgpcm.cu: window_factors,
+    right_mul_tri): per chunk of observations, the window ``w`` = the columns where the chunk's ``A`` is not exactly 0,
+    ``sign * W[w, w] = L L^T`` (Cholesky: the block must be positive definite), ``V' = A[:, :, w] L`` and
+    ``sign * sum V' V'^T``.  Returns the sum and the widest window."""
+    N, nh, nx = A.shape
+    out = np.zeros((nh, nh))
+    widest = 0
+    for n0 in range(0, N, chunk):
+        Ac = A[n0:n0 + chunk]
+        live = np.nonzero(np.any(Ac != 0.0, axis=(0, 1)))[0]
+        if live.size == 0:
+            continue
+        lo, hi = live[0], live[-1] + 1
+        widest = max(widest, hi - lo)
+        Lw = np.linalg.cholesky(sign * W[lo:hi, lo:hi])
+        V = Ac[:, :, lo:hi] @ Lw
+        out += np.einsum('nil,njl->ij', V, V)
+    return sign * out, widest
+
+
+def elbo_grad(params, t, y, th, tx, reg, mode=1, frozen=None, tri_chunk=None):
     """ELBO, terms[7], gradient.  mode 1 = full regime, mode 0 = Psi frozen (``frozen`` = dict of
-    sum_Axx, Q, Y, Ahh, a, A, iKh, iKx, Kx, logdetKx computed at the freeze-time hypers)."""
+    sum_Axx, Q, Y, Ahh, a, A, iKh, iKx, Kx, logdetKx computed at the freeze-time hypers).  ``tri_chunk``: contract
+    ``Q`` and ``Hbar`` through the Cholesky factors of the window blocks, in chunks of that many observations."""
     nh, nx, N = len(th), len(tx), len(t)
     s2, s2_f, alpha, gamma, omega = np.exp(params[:5])
     mu = params[5:5 + nh]
@@ -116,7 +138,7 @@ def elbo_grad(params, t, y, th, tx, reg, mode=1, frozen=None):
         sum_Axx, dAxx_a, dAxx_g, dAxx_o = axx_with_tangents(t, tx, alpha, gamma, omega)
         dAxx = [dAxx_a, dAxx_g, dAxx_o]
         A, dA = ahx_with_tangents(t, th, tx, alpha, gamma, omega)
-        Q = np.einsum('nik,kl,njl->ij', A, iKx, A)
+        Q = windowed_gram(A, iKx, tri_chunk)[0] if tri_chunk else np.einsum('nik,kl,njl->ij', A, iKx, A)
         Y = np.einsum('n,nik->ik', y, A)
     else:
         f = frozen
@@ -148,8 +170,11 @@ def elbo_grad(params, t, y, th, tx, reg, mode=1, frozen=None):
     C1bar = r * Pbar
     c0bar = lbar @ (Y.T @ mu)
     Ybar = c0 * np.outer(mu, lbar)
-    U1 = np.einsum('nik,kl->nil', A, C1bar)
-    Hbar = np.einsum('nil,njl->ij', U1, A)
+    if tri_chunk:
+        Hbar = windowed_gram(A, C1bar, tri_chunk, sign=-1.0)[0]      # -C1bar = r (Pinv / 2 + lbar lbar^T / 2) > 0
+    else:
+        U1 = np.einsum('nik,kl->nil', A, C1bar)
+        Hbar = np.einsum('nil,njl->ij', U1, A)
     m2bar = Hbar - .5 * r * sum_Bhh
     varbar = m2bar - .5 * (iSo - ivar)
     Lbar = np.tril(2 * varbar @ L)

@@ -52,3 +52,25 @@ def test_frozen_regime(name):
     assert abs(e0 - e1) < 1e-9 * abs(e0)
     scale = np.max(np.abs(g0))
     np.testing.assert_allclose(g1, g0, rtol=1e-7, atol=1e-9 * scale)
+
+
+def test_triangular_window_route_matches_full_blocks():
+    """Option `tri` of the CUDA path, restated on the host (tests/adjoint_proto.windowed_gram): Q = sum_n A_n iKx A_n^T and
+    Hbar = sum_n A_n C1bar A_n^T through Cholesky factors of the window blocks -- iKx[w] and -C1bar[w] are positive
+    definite on every window -- give the ELBO and gradient of the full-block products, on a sweep-like series whose
+    windows of exact zeros are narrower than nx and in chunks that do not divide the series."""
+    from tests.workload import sweep_workload
+    wl = sweep_workload(260, 128)
+    th = np.ascontiguousarray(wl['th'][::10])                         # 13 filter inducing points keep the host loops short
+    a, g, o = wl['hyp']
+    mu_u, var_u = om.init_q(th, a, g, wl['reg'], np.random.default_rng(5))
+    p = om.pack(0.1, float(np.exp(wl['params'][1])), a, g, o, mu_u, var_u)
+    args = (p, wl['t'], wl['y'], th, wl['tx'], wl['reg'])
+    e0, t0, g0 = ap.elbo_grad(*args)
+    e1, t1, g1 = ap.elbo_grad(*args, tri_chunk=48)
+    A, _ = ap.ahx_with_tangents(wl['t'], th, wl['tx'], a, g, o)
+    widest = ap.windowed_gram(A[:96], np.eye(128), 48)[1]
+    assert 8 < widest < 128, widest                                   # the windows are exercised
+    sc = np.abs(t0).max()
+    assert abs(e1 - e0) <= 1e-9 * sc and np.abs(t1 - t0).max() <= 1e-9 * sc
+    assert np.abs(g1 - g0).max() <= 1e-9 * np.abs(g0).max()
