@@ -3,7 +3,8 @@
 cgpcm_dgemm_sym, and checks each result against torch.matmul on a slice.
 
     T1    = H A          200 x 200 times 200 x (nc * kw)            dgemm_sl_kernel<13, 12, 0>
-    V^T   = W  A2^T      kw x kw   times kw  x (200 * nc), C^T      dgemm_sl_kernel<12, 0, 1>   (also U1, Abar)
+    V^T   = W  A2^T      kw x kw   times kw  x (200 * nc), C^T      dgemm_sl_kernel<12, 0, 1>   (Abar; V, U1 without `tri`)
+    V'^T  = L^T A2^T     the same with an upper-triangular operand    dgemm_sl_kernel<12, 0, 1, 1, 1>  (V', U' with `tri`)
     Q    += A V^T        200 x 200 lower triangle over K = nc * kw   dgemm_sym_kernel<1, ...>    (also Hbar)
     C1   += A2^T T1_2    kw x kw   lower triangle over K = 200 * nc  dgemm_sym_kernel<0, ...>
 """
@@ -63,6 +64,15 @@ def run_v():
 ms = timeit(run_v)
 ref = A.view(nh * nc, kw)[:4096] @ W.t()
 report('V = A2 W^T (right-multiply)', ms, 2.0 * kw * kw * nh * nc, float((V.view(nh * nc, kw)[:4096] - ref).abs().max()))
+
+# V' = A2 L with a lower-triangular L (the resident operand is S = L^T, upper triangular; option `tri`)
+Lt = torch.triu(torch.randn(kw, kw, dtype=torch.float64, device=dev))
+Vt = torch.empty(nh * cols, dtype=torch.float64, device=dev)
+def run_vt():
+    assert L.cgpcm_dgemm_tri(kw, nh * nc, Lt.data_ptr(), kw, A.data_ptr(), kw, Vt.data_ptr(), kw, None) == 0
+ms = timeit(run_vt)
+ref = A.view(nh * nc, kw)[:4096] @ Lt.t()
+report("V' = A2 L (triangular right-multiply)", ms, 1.0 * kw * (kw + 1) * nh * nc, float((Vt.view(nh * nc, kw)[:4096] - ref).abs().max()))
 
 # Q = A V^T lower triangle (k contiguous), C1 = A2^T T1_2 (m contiguous)
 work = torch.empty(148, nh, nh, dtype=torch.float64, device=dev)
